@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — particle-update throughput of the hot path on config C5 (BASELINE.json configs[4]).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's path on the host CPU
+
+Workload: one effect instance of 64 Mi particles, attributes {position, velocity,
+age, lifetime} (32 B AoS record -> two float4 SoA planes), update = [Accel((0,-9.8,0)), LinearDrag(0.5)]
++ Euler integration + age/lifetime kill, dt = 1/60, lifetime 1e9 (nothing dies: steady state), alive
+list = identity. A "step" is one full simulate(): (init skipped: 0 spawns) -> fused indirect+prefix-sum
+bookkeeping kernel -> update kernel. For N GPUs the 64 Mi particles are sharded by index range
+(64Mi/N per rank, strong scaling), no collective on the data path.
+
+One JSON line is printed by rank 0 (see the task contract): value = particle-steps/s over the whole
+job with all state resident in HBM; e2e = same metric through the C ABI with the per-frame HOST tables
+(spawners, batch infos, prefix sums, sim params) uploaded and the draw-indirect instance count read
+back every step; roofline = update kernel algorithmic bytes (72 B/particle-step) / its CUDA-event
+duration vs the measured HBM copy peak; cpu_baseline = the CPU oracle (C port, OpenMP) on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+TOTAL_PARTICLES = 64 * 1024 * 1024
+BYTES_PER_PARTICLE_STEP = 72  # 4 (alive idx read) + 32 (record read) + 32 (record write) + 4 (alive idx write); SURVEY §8d
+DT = 1.0 / 60.0
+METRIC = "particle-steps/sec at 64M particles"
+UNIT = "particle-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=TOTAL_PARTICLES, help="total particles over all GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's multi-threaded C5 update (oracle/vfx_oracle.c::orc_update_c5_parallel)
+# ---------------------------------------------------------------------------------------------------
+class CpuC5:
+    def __init__(self, particles: int):
+        import numpy as np
+        from oracle import c_oracle as O
+        self.np, self.O = np, O
+        self.orc = O.load()
+        self.n = particles
+        self.threads = min(self.orc.orc_max_threads(), os.cpu_count() or 1)
+        self.particles = np.empty((particles, 8), dtype=np.float32)
+        self.indirect = np.zeros((particles, 3), dtype=np.uint32)
+        self.indirect[:, 2] = np.arange(particles, dtype=np.uint32)
+        self.orc.orc_fill_c5(O.ptr(self.particles), O.ptr(self.indirect), 0, particles, 42, 1e9, 1e9)
+        self.flags = np.zeros(particles, dtype=np.uint8)
+        self.sim = O.SimParams(DT, 0, DT, 0, DT, 0, 1)
+        self.md = (O.EffectMetadata * 1)()
+        self.md[0].capacity = particles
+        self.md[0].alive_count = particles
+        self.md[0].max_spawn = 0
+        self.md[0].indirect_render_index = 0
+        self.sp = (O.Spawner * 1)()
+        self.sp[0].seed = 42
+        self.draw = np.zeros(5, dtype=np.uint32)
+        self.prefix = np.zeros(1, dtype=np.uint32)
+        self.bi = (O.BatchInfo * 1)()
+        self.bi[0].prefix_sum_count = 1
+        self.dispatch = np.zeros(3, dtype=np.uint32)
+        self.k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+
+    def step(self):
+        """One full frame: indirect -> prefix sum -> update (all of vfx_*.wgsl's work for this config)."""
+        o, P, u32 = self.orc, C.POINTER, C.c_uint32
+        o.orc_indirect(C.byref(self.sim), self.md, self.draw.ctypes.data_as(P(u32)), self.sp, self.prefix.ctypes.data_as(P(u32)), None, 0)
+        o.orc_prefix_sum(self.bi, 1, self.prefix.ctypes.data_as(P(u32)), self.dispatch.ctypes.data_as(P(u32)))
+        alive = o.orc_update_c5_parallel(C.byref(self.sim), self.draw.ctypes.data_as(P(u32)), self.O.ptr(self.particles),
+                                         self.O.ptr(self.indirect), self.sp, self.md, self.k, self.O.ptr(self.flags), self.threads)
+        return alive
+
+
+def cpu_baseline(seconds: float, sample: int = 8 * 1024 * 1024):
+    arm = CpuC5(sample)
+    arm.step()  # warm-up
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        arm.step()
+        steps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or steps >= 200:
+            break
+    return {"value": sample * steps / el, "unit": UNIT, "cores": arm.threads, "kind": "port",
+            "sample": f"{steps} full frames (indirect+prefix-sum+update) of a {sample}-particle C5 instance, {el:.1f} s wall, "
+                      f"oracle/vfx_oracle.c OpenMP x{arm.threads}",
+            "gbps": BYTES_PER_PARTICLE_STEP * sample * steps / el / 1e9}
+
+
+def run_reference(args):
+    """--impl reference: the reference's path cannot be built here (no Rust toolchain, no Vulkan ICD —
+    SURVEY.md §0.3), so this times the oracle's C port of it on all host cores. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8 * 1024 * 1024
+    arm = CpuC5(sample)
+    for _ in range(max(1, min(args.warmup, 2))):
+        arm.step()
+    steps = max(1, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        arm.step()
+    el = time.perf_counter() - t0
+    value = sample * steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5 synthetic 64M-particle SoA buffer, Accel+LinearDrag update (bounded CPU sample)",
+                   "particles_per_step": sample, "dt": DT},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": "port",
+                         "sample": f"{steps} frames of an {sample}-particle C5 instance per step, OpenMP x{arm.threads} "
+                                   "(oracle port: the Rust/wgpu reference cannot be built in this image)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import bevy_hanabi_b200 as hb
+    from bevy_hanabi_b200 import _native as N
+    from bevy_hanabi_b200 import recipes, runtime as R
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — hanabi_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = max(world, 1)
+    if args.scaling == "strong":
+        per_rank = args.particles // n_gpus
+    else:
+        per_rank = args.particles
+    total = per_rank * n_gpus
+
+    stream = torch.cuda.current_stream()
+    ctx = hb.Context(local_rank, stream.cuda_stream)
+    slab = ctx.slab_create(per_rank, recipes.C5_STRIDE)
+    effect = ctx.effect_compile(recipes.c5_lowered())
+    # shard `rank` owns rows [rank*per_rank, (rank+1)*per_rank) of the logical 64M instance: same
+    # counter-based state as a 1-GPU run would hold for those rows (seed mixes the global row)
+    ctx.slab_fill_c5(slab, 0, per_rank, 42 + rank, 1e9, 1e9)
+    md = R.initial_metadata(per_rank, 0, 8)
+    md.alive_count = per_rank
+    md.max_spawn = 0
+    ctx.metadata_insert(0, md)
+    ctx.draw_args_insert(0)
+    spawners = (N.Spawner * 1)(R.make_spawner(spawn=0, seed=42))
+    batches = (N.BatchInfo * 1)(N.BatchInfo(0, 0, 0, 0, 0, 1))
+    prefix = (N.u32 * 1)(0)
+    launches = (N.BatchLaunch * 1)(N.BatchLaunch.make(effect, slab, 0, 0))
+    sim_t = [0.0]
+
+    def upload_tables():
+        ctx.upload_spawners_raw(spawners, 1)
+        ctx.upload_batches_raw(batches, 1, prefix, 1)
+        ctx.set_sim_params(DT, sim_t[0], 1)
+        sim_t[0] += DT
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # -- device-resident loop (value): tables uploaded once, only the 64-byte frame header moves per step
+    upload_tables()
+    def step_resident():
+        ctx.simulate_raw(launches, 1)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    ms = timed(step_resident, args.steps)
+    gpu_launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = total * args.steps / (ms * 1e-3)
+
+    # -- roofline leg: the update kernel alone, timed by CUDA events recorded around each launch on the launching stream
+    ctx.enable_kernel_timing(True)
+    ctx.kernel_time_ms()
+    for _ in range(args.steps):
+        step_resident()
+    k_ms, k_n = ctx.kernel_time_ms()
+    ctx.enable_kernel_timing(False)
+    k_avg_ms = k_ms / max(k_n, 1)
+    if world > 1:
+        t = torch.tensor([k_avg_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        k_avg_ms = float(t.item())
+    achieved = BYTES_PER_PARTICLE_STEP * per_rank / (k_avg_ms * 1e-3) / 1e9
+
+    # -- end-to-end loop: host tables up, simulate, instance count back, every step
+    pinned = N.lib.hnb_host_alloc(20)
+    out = (N.DrawIndexedIndirectArgs * 1).from_address(pinned)
+    def step_e2e():
+        upload_tables()
+        ctx.simulate_raw(launches, 1)
+        N.check(N.lib.hnb_read_draw_args_async(ctx._h, 0, 1, pinned))
+        ctx.sync()
+        if out[0].instance_count != per_rank:
+            raise RuntimeError(f"instance_count {out[0].instance_count} != {per_rank}")
+    for _ in range(3):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = total * args.steps / (ms_e2e * 1e-3)
+    h2d = 64 + 24 + 4 + 128 + 3 * 4  # frame header + batch info + tile size + spawner row + range/spawn-prefix/prefix words
+    h2d = 64 + 24 + 4 + 4 + 128 + 12
+
+    # -- correctness guard inside the bench: the state must have advanced (age = steps*dt) and nothing died
+    mdr = ctx.read_metadata(0)
+    assert mdr.alive_count == per_rank and mdr.max_update == per_rank, "bench state corrupted"
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak = json.loads(peaks_path.read_text()).get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5 synthetic 64M-particle SoA buffer, Accel+LinearDrag update, sharded by index range",
+                       "particles_total": total, "particles_per_gpu": per_rank, "dt": DT, "steps_per_sec": args.steps / (ms * 1e-3),
+                       "l2": "inputs larger than L2 (per-GPU working set %.0f MB per step)" % (per_rank * 72 / 1e6),
+                       "parallelism": f"index-range shards x{n_gpus}, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "note": "host per-frame tables (spawner row, batch info, prefix sums, sim params) copied in, "
+                            "draw-indirect instance_count copied out and checked on the host every step; particle state "
+                            "stays in HBM as in the reference (it is never on the host there either)"},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "hnb_update", "kernel_ms": k_avg_ms, "peak_source": peak_src,
+                         "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP},
+            "clocks": clocks,
+        }
+        prof = ROOT / "profiles" / "traffic.json"
+        if prof.exists():
+            try:
+                line["roofline"]["traffic"] = json.loads(prof.read_text()).get("hnb_update_dram_bytes_per_launch")
+            except Exception:
+                pass
+        if not args.no_cpu_baseline and n_gpus == 1:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    N.lib.hnb_host_free(pinned)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,318 @@
+// hnb_static_kernels.cu — effect-independent kernels, compiled ahead of time by nvcc for sm_100a.
+//
+//   k_indirect        ≙ src/render/vfx_indirect.wgsl main()   (:31-90)
+//   k_prefix_sum      ≙ src/render/vfx_prefix_sum.wgsl main() (:14-43)
+//   k_bookkeeping     = both of the above fused into one launch (one CTA per batch), used by
+//                       hnb_simulate(); results identical to running them back to back
+//   k_fill_dispatch_args ≙ src/render/vfx_utils.wgsl fill_dispatch_args (:54-67)
+//   slab helpers: reset (effect_cache.rs:300-323), AoS<->SoA transposes, synthetic fill, checksum
+//
+// In addition to the reference's outputs the indirect step (a) applies the alive_count /
+// particle_counter increments that the reference's init pass performs with per-particle atomics
+// (vfx_init.wgsl:141,151) — our init kernel assigns ranks instead and defers the counter update to
+// this per-instance step — and (b) the prefix step also scans the per-instance update TILE counts
+// consumed by the persistent update kernel.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "hnb_wgsl.cuh"
+#include "hnb_tables.cuh"
+#include "hnb_static_kernels.h"
+
+namespace hnb {
+
+// ---------------------------------------------------------------------------------------------
+// Per-instance step shared by k_indirect and k_bookkeeping.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 indirect_one_effect(const StaticTables& T, u32 global_effect_index) {
+    Spawner* spawner = &T.spawners[global_effect_index];
+    const u32 effect_metadata_index = spawner->effect_metadata_index;
+    EffectMetadata* md = &T.metadata[effect_metadata_index];
+
+    // (a) deferred init accounting: number of init threads of this instance that passed the caps of
+    // vfx_init.wgsl:115-137 in the init launch that preceded this pass (0 if there was none).
+    const u32 range = T.spawn_range[global_effect_index];
+    u32 alive_count = md->alive_count;
+    if (range != 0u) {
+        u32 requested;
+        if (range & 0x80000000u) {
+            // GPU-event driven instance: requested = event_count (vfx_init.wgsl:123-129)
+            requested = u32(T.child_infos[md->global_child_index].event_count);
+        } else {
+            requested = u32(spawner->spawn);
+        }
+        u32 n = min(range & 0x7fffffffu, requested);
+        n = min(n, md->max_spawn);
+        alive_count += n;
+        md->alive_count = alive_count;
+        md->particle_counter += n;
+        T.spawn_range[global_effect_index] = 0u;
+    }
+
+    // vfx_indirect.wgsl:52-89
+    const u32 dri_base = HNB_DRAW_INDEXED_INDIRECT_STRIDE * spawner->draw_indirect_index;
+    T.draw_args[dri_base + 1u] = 0u;
+    const u32 capacity = md->capacity;
+    const u32 dead_count = capacity - alive_count;
+    T.prefix_sum[global_effect_index] = alive_count;
+    md->max_update = alive_count;
+    md->max_spawn = dead_count;
+    const u32 ping = md->indirect_write_index;
+    const u32 pong = 1u - ping;
+    md->indirect_write_index = pong;
+    spawner->render_indirect_read_index = pong;
+    return alive_count;
+}
+
+__global__ void k_indirect(StaticTables T) {
+    const u32 global_effect_index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (global_effect_index >= T.frame->sim.num_effects) return;
+    // HAS_GPU_SPAWN_EVENTS: clear the event counts AFTER they were consumed by init (:38-46). The
+    // reference indexes the child-info array with the effect index; we do the same.
+    // NOTE: the deferred accounting above needs event_count, so it is read before being cleared
+    // only when the clearing thread and the reading thread are the same; to stay race-free the clear
+    // happens in a second kernel phase (see k_clear_events).
+    indirect_one_effect(T, global_effect_index);
+}
+
+__global__ void k_clear_events(StaticTables T) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T.frame->sim.num_effects) return;
+    if (i < T.num_child_infos) T.child_infos[i].event_count = 0;
+}
+
+// Serial scan of one batch by one thread, exactly like the reference (vfx_prefix_sum.wgsl:27-42).
+__global__ void k_prefix_sum(StaticTables T) {
+    const u32 batch_index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (batch_index >= T.frame->num_batches) return;
+    BatchInfo* bi = &T.batch_infos[batch_index];
+    const u32 offset = bi->prefix_sum_offset;
+    const u32 end = offset + bi->prefix_sum_count;
+    const u32 tile = T.batch_tile_size[batch_index];
+    u32 sum = 0u, tiles = 0u;
+    for (u32 i = offset; i < end; i += 1u) {
+        const u32 count = T.prefix_sum[i];
+        T.prefix_sum[i] = sum;
+        T.tile_prefix[i] = tiles;
+        sum += count;
+        tiles += (count + tile - 1u) / tile;
+    }
+    bi->total_update_count = sum;
+    T.dispatch_args[batch_index * 3u + 0u] = (sum + 63u) >> 6u;
+    T.dispatch_args[batch_index * 3u + 1u] = 1u;
+    T.dispatch_args[batch_index * 3u + 2u] = 1u;
+    T.batch_tiles[batch_index] = tiles;
+    T.tickets[batch_index] = 0u;
+}
+
+// Fused indirect + prefix-sum: CTA b owns batch b. Requires that the batches tile the spawner table
+// (checked on the host: HNB_ERR_BATCH_COVERAGE), which Batcher::push guarantees in the reference
+// (prefix sums and spawners are allocated in sync, vfx_indirect.wgsl:66).
+#define BK_THREADS 256
+__global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T) {
+    __shared__ u32 s_warp_a[BK_THREADS / 32], s_warp_t[BK_THREADS / 32];
+    __shared__ u32 s_carry_a, s_carry_t;
+    const u32 batch_index = blockIdx.x;
+    BatchInfo* bi = &T.batch_infos[batch_index];
+    const u32 offset = bi->prefix_sum_offset;
+    const u32 count = bi->prefix_sum_count;
+    const u32 tile = T.batch_tile_size[batch_index];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5u;
+    if (tid == 0) { s_carry_a = 0u; s_carry_t = 0u; }
+    __syncthreads();
+    for (u32 chunk = 0; chunk < count; chunk += BK_THREADS) {
+        const u32 i = chunk + tid;
+        u32 a = 0u, t = 0u;
+        if (i < count) {
+            a = indirect_one_effect(T, offset + i);
+            t = (a + tile - 1u) / tile;
+        }
+        // block-wide exclusive scan of (a, t)
+        u32 ia = a, it = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 ua = __shfl_up_sync(0xffffffffu, ia, d), ut = __shfl_up_sync(0xffffffffu, it, d);
+            if (lane >= d) { ia += ua; it += ut; }
+        }
+        if (lane == 31) { s_warp_a[warp] = ia; s_warp_t[warp] = it; }
+        __syncthreads();
+        u32 wa = 0u, wt = 0u;
+        for (u32 w = 0; w < warp; ++w) { wa += s_warp_a[w]; wt += s_warp_t[w]; }
+        const u32 carry_a = s_carry_a, carry_t = s_carry_t;
+        if (i < count) {
+            T.prefix_sum[offset + i] = carry_a + wa + ia - a;
+            T.tile_prefix[offset + i] = carry_t + wt + it - t;
+        }
+        __syncthreads();
+        if (tid == BK_THREADS - 1) { s_carry_a = carry_a + wa + ia; s_carry_t = carry_t + wt + it; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const u32 sum = s_carry_a;
+        bi->total_update_count = sum;
+        T.dispatch_args[batch_index * 3u + 0u] = (sum + 63u) >> 6u;
+        T.dispatch_args[batch_index * 3u + 1u] = 1u;
+        T.dispatch_args[batch_index * 3u + 2u] = 1u;
+        T.batch_tiles[batch_index] = s_carry_t;
+        T.tickets[batch_index] = 0u;
+    }
+}
+
+// vfx_utils.wgsl:54-67
+__global__ void k_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
+                                     u32 dst_stride, u32 count) {
+    const u32 thread_index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (thread_index >= count) return;
+    const u32 s = src_offset + thread_index * src_stride;
+    const u32 d = dst_offset + thread_index * dst_stride;
+    const u32 thread_count = src[s];
+    dst[d] = (thread_count + 63u) >> 6u;
+    dst[d + 1u] = 1u;
+    dst[d + 2u] = 1u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slab helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void k_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 count) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    ping[first + i] = 0u;
+    pong[first + i] = 0u;
+    dead[first + i] = first + i;  // effect_cache.rs:317-319
+}
+
+// AoS rows (stride_words u32 each) <-> planes. Plane p covers words [word_off[p], word_off[p]+words[p]).
+__global__ void k_aos_to_planes(const u32* aos, PlaneSet planes, u32 first, u32 count, u32 stride_words) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const u64 total = u64(count) * stride_words;
+    if (i >= total) return;
+    const u32 row = u32(i / stride_words), w = u32(i % stride_words);
+    const u32 p = planes.word_to_plane[w];
+    const u32 lane = w - planes.word_off[p];
+    ((u32*)planes.ptr[p])[u64(first + row) * planes.words[p] + lane] = aos[i];
+}
+__global__ void k_planes_to_aos(u32* aos, PlaneSet planes, u32 first, u32 count, u32 stride_words) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const u64 total = u64(count) * stride_words;
+    if (i >= total) return;
+    const u32 row = u32(i / stride_words), w = u32(i % stride_words);
+    const u32 p = planes.word_to_plane[w];
+    const u32 lane = w - planes.word_off[p];
+    aos[i] = ((const u32*)planes.ptr[p])[u64(first + row) * planes.words[p] + lane];
+}
+__global__ void k_indirect_interleave(u32* rows3, const u32* ping, const u32* pong, const u32* dead, u32 first, u32 count) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    rows3[3u * i + 0u] = ping[first + i];
+    rows3[3u * i + 1u] = pong[first + i];
+    rows3[3u * i + 2u] = dead[first + i];
+}
+__global__ void k_indirect_deinterleave(const u32* rows3, u32* ping, u32* pong, u32* dead, u32 first, u32 count) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    ping[first + i] = rows3[3u * i + 0u];
+    pong[first + i] = rows3[3u * i + 1u];
+    dead[first + i] = rows3[3u * i + 2u];
+}
+
+// Synthetic C5 state: counter-based so that the CPU oracle can regenerate any row.
+//   s = pcg_hash(row ^ seed); six successive pcg_hash -> position, velocity in [-1,1); one more -> lifetime
+__global__ void k_fill_c5(float4* pos_age, float4* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed,
+                          f32 lifetime_lo, f32 lifetime_hi) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u32 row = first + i;
+    u32 s = pcg_hash(row ^ seed);
+    f32 v[7];
+    for (int k = 0; k < 7; ++k) { s = pcg_hash(s); v[k] = to_float01(s); }
+    pos_age[row] = make_float4(v[0] * 2.0f - 1.0f, v[1] * 2.0f - 1.0f, v[2] * 2.0f - 1.0f, 0.0f);
+    vel_life[row] = make_float4(v[3] * 2.0f - 1.0f, v[4] * 2.0f - 1.0f, v[5] * 2.0f - 1.0f,
+                                lifetime_lo + v[6] * (lifetime_hi - lifetime_lo));
+    ping[row] = i;  // instance-local identity alive list in both columns
+    pong[row] = i;
+}
+
+// Order-independent checksum: sum over rows of a 64-bit mix of the row's AoS words and row index.
+__global__ void k_checksum(PlaneSet planes, u32 first, u32 count, u32 stride_words, u64* out) {
+    u64 acc = 0;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += u64(gridDim.x) * blockDim.x) {
+        u64 h = 0xcbf29ce484222325ull ^ u64(i);
+        for (u32 w = 0; w < stride_words; ++w) {
+            const u32 p = planes.word_to_plane[w];
+            const u32 lane = w - planes.word_off[p];
+            const u32 x = ((const u32*)planes.ptr[p])[u64(first + i) * planes.words[p] + lane];
+            h = (h ^ u64(x)) * 0x100000001b3ull;
+        }
+        h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+        acc += h;
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31u) == 0) atomicAdd((unsigned long long*)out, (unsigned long long)acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-callable launchers (declared in hnb_static_kernels.h)
+// ---------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(u64 n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t st) {
+    if (num_effects == 0) return cudaSuccess;
+    k_indirect<<<blocks_for(num_effects, 64), 64, 0, st>>>(T);
+    if (T.num_child_infos) k_clear_events<<<blocks_for(num_effects, 64), 64, 0, st>>>(T);
+    return cudaGetLastError();
+}
+cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st) {
+    if (num_batches == 0) return cudaSuccess;
+    k_prefix_sum<<<blocks_for(num_batches, 64), 64, 0, st>>>(T);
+    return cudaGetLastError();
+}
+cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, cudaStream_t st) {
+    if (num_batches == 0) return cudaSuccess;
+    k_bookkeeping<<<num_batches, BK_THREADS, 0, st>>>(T);
+    if (T.num_child_infos) k_clear_events<<<blocks_for(num_effects, 64), 64, 0, st>>>(T);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
+                                      u32 dst_stride, u32 count, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_fill_dispatch_args<<<blocks_for(count, 64), 64, 0, st>>>(src, dst, src_offset, src_stride, dst_offset, dst_stride, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_slab_reset<<<blocks_for(count, 256), 256, 0, st>>>(ping, pong, dead, first, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_aos_to_planes(const u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_aos_to_planes<<<blocks_for(u64(count) * stride_words, 256), 256, 0, st>>>(aos, planes, first, count, stride_words);
+    return cudaGetLastError();
+}
+cudaError_t launch_planes_to_aos(u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_planes_to_aos<<<blocks_for(u64(count) * stride_words, 256), 256, 0, st>>>(aos, planes, first, count, stride_words);
+    return cudaGetLastError();
+}
+cudaError_t launch_indirect_interleave(u32* rows3, const u32* ping, const u32* pong, const u32* dead, u32 first, u32 count, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_indirect_interleave<<<blocks_for(count, 256), 256, 0, st>>>(rows3, ping, pong, dead, first, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_indirect_deinterleave(const u32* rows3, u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_indirect_deinterleave<<<blocks_for(count, 256), 256, 0, st>>>(rows3, ping, pong, dead, first, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_c5(void* pos_age, void* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed, f32 lo, f32 hi, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_fill_c5<<<blocks_for(count, 256), 256, 0, st>>>((float4*)pos_age, (float4*)vel_life, ping, pong, first, count, seed, lo, hi);
+    return cudaGetLastError();
+}
+cudaError_t launch_checksum(const PlaneSet& planes, u32 first, u32 count, u32 stride_words, u64* out, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_checksum<<<148 * 4, 256, 0, st>>>(planes, first, count, stride_words, out);
+    return cudaGetLastError();
+}
+
+}  // namespace hnb

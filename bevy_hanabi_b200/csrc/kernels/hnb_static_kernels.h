@@ -1,0 +1,49 @@
+// hnb_static_kernels.h — host-callable launchers of the ahead-of-time compiled kernels
+// (hnb_static_kernels.cu). Includable from plain C++ (g++) and from nvcc.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hnb_tables.cuh"
+
+namespace hnb {
+
+// Device pointers of the context-wide tables used by the per-instance / per-batch passes.
+struct StaticTables {
+    const FrameHeader* frame;
+    Spawner* spawners;
+    u32* spawn_range;        // per instance: init threads mapped to it this frame (bit31: event driven); zeroed after use
+    u32* prefix_sum;
+    u32* tile_prefix;
+    BatchInfo* batch_infos;
+    const u32* batch_tile_size;  // per batch: rows per update tile of the batch's compiled effect
+    u32* dispatch_args;      // DispatchIndirectArgs rows as u32[3]
+    u32* batch_tiles;
+    u32* tickets;
+    EffectMetadata* metadata;
+    u32* draw_args;
+    ChildInfo* child_infos;
+    u32 num_child_infos;
+};
+
+// SoA planes of one slab, with the word -> plane map used by the AoS <-> SoA transposes.
+struct PlaneSet {
+    void* ptr[HNB_MAX_PLANES];
+    u32 words[HNB_MAX_PLANES];     // u32 words per row of plane p (4, 2 or 1)
+    u32 word_off[HNB_MAX_PLANES];  // first AoS word covered by plane p
+    unsigned char word_to_plane[HNB_MAX_PLANES * 4];
+};
+
+cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t st);
+cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st);
+cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, cudaStream_t st);
+cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
+                                      u32 dst_stride, u32 count, cudaStream_t st);
+cudaError_t launch_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st);
+cudaError_t launch_aos_to_planes(const u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st);
+cudaError_t launch_planes_to_aos(u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st);
+cudaError_t launch_indirect_interleave(u32* rows3, const u32* ping, const u32* pong, const u32* dead, u32 first, u32 count, cudaStream_t st);
+cudaError_t launch_indirect_deinterleave(const u32* rows3, u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st);
+cudaError_t launch_fill_c5(void* pos_age, void* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed, f32 lo, f32 hi, cudaStream_t st);
+cudaError_t launch_checksum(const PlaneSet& planes, u32 first, u32 count, u32 stride_words, u64* out, cudaStream_t st);
+
+}  // namespace hnb

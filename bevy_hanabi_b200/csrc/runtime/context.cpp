@@ -1,0 +1,1087 @@
+// context.cpp — Level-1 runtime behind include/hanabi_b200.h: context, slabs, compiled effects,
+// per-frame tables and the simulate() driver.
+//
+// Mirrors, on the host side, what the reference keeps in EffectCache / EffectsMeta / Batcher /
+// PropertyCache (src/render/{effect_cache,batch,property}.rs, mod.rs) and the pass recording of
+// simulate() (src/render/mod.rs:6942-7613) — flattened into plain device arrays, one CUDA stream,
+// and one host->device copy per frame.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../kernels/hnb_static_kernels.h"
+#include "driver.h"
+#include "effect_source.h"
+#include "hanabi_b200.h"
+#include "nvrtc_compile.h"
+
+using namespace hnb_rt;
+
+static_assert(sizeof(hnb_spawner) == 128 && sizeof(hnb::Spawner) == 128, "GpuSpawnerParams is 128 bytes");
+static_assert(sizeof(hnb_effect_metadata) == 60 && sizeof(hnb::EffectMetadata) == 60, "GpuEffectMetadata is 60 bytes");
+static_assert(sizeof(hnb_batch_info) == 24 && sizeof(hnb::BatchInfo) == 24, "GpuBatchInfo is 24 bytes");
+static_assert(sizeof(hnb_sim_params) == 28 && sizeof(hnb::SimParams) == 28, "GpuSimParams is 28 bytes");
+static_assert(sizeof(hnb_draw_indexed_indirect_args) == 20, "GpuDrawIndexedIndirectArgs is 20 bytes");
+static_assert(sizeof(hnb_indirect_index) == 12, "GpuIndirectIndex is 12 bytes");
+static_assert(sizeof(hnb_child_info) == 8 && sizeof(hnb::ChildInfo) == 8, "GpuChildInfo is 8 bytes");
+static_assert(sizeof(hnb::FrameHeader) == 64, "frame header is 64 bytes");
+
+// ---------------------------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_last_error;
+
+struct HnbError : std::runtime_error {
+    int32_t code;
+    HnbError(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] void fail(int32_t code, const std::string& msg) { throw HnbError(code, msg); }
+
+#define CUDA_CHECK(expr)                                                                                     \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) fail(HNB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+template <typename F> int32_t guarded(F&& f) {
+    try {
+        f();
+        return HNB_OK;
+    } catch (const HnbError& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::invalid_argument& e) {
+        g_last_error = e.what();
+        return HNB_ERR_INVALID_ARG;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return HNB_ERR_CUDA;
+    }
+}
+
+uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Objects
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Slab {
+    bool live = false;
+    uint32_t capacity = 0, stride = 0;
+    std::vector<Plane> planes;
+    void* d_planes[HNB_RT_MAX_PLANES] = {};
+    uint32_t *ping = nullptr, *pong = nullptr, *dead = nullptr;
+};
+
+struct KernelModule {
+    CUmodule mod = nullptr;
+    CUfunction init = nullptr, update = nullptr;
+    int update_blocks_per_sm = 1;
+    std::string log;
+};
+
+struct Effect {
+    bool live = false;
+    uint64_t hash = 0;
+    KernelModule* km = nullptr;
+    uint32_t tile_k = 4, flags = 0, particle_stride = 0, parent_stride = 0;
+    uint32_t props_size = 0, props_stride = 0, props_rows = 0;
+    char* d_props = nullptr;
+    std::string name;
+};
+
+struct EventBuffer {
+    uint32_t capacity = 0;
+    uint32_t* d = nullptr;
+};
+
+struct ArenaLayout {
+    size_t off_batch_infos, off_tile_size, off_spawners, off_range, off_spawn_prefix, off_prefix_sum, total;
+    static ArenaLayout make(uint32_t E, uint32_t B) {
+        ArenaLayout l;
+        size_t o = sizeof(hnb::FrameHeader);
+        l.off_batch_infos = o; o += size_t(B) * sizeof(hnb_batch_info);
+        l.off_tile_size = o; o += size_t(B) * 4;
+        o = align_up(o, 16);
+        l.off_spawners = o; o += size_t(E) * sizeof(hnb_spawner);
+        l.off_range = o; o += size_t(E) * 4;
+        l.off_spawn_prefix = o; o += size_t(E) * 4;
+        l.off_prefix_sum = o; o += size_t(E) * 4;
+        l.total = o;
+        return l;
+    }
+};
+
+}  // namespace
+
+struct hnb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DriverApi drv;
+    uint64_t launches = 0;
+    bool graphs = true;
+
+    // per-frame arena (host pinned + device mirror), exact-size layout for (E, B)
+    uint32_t E = 0, B = 0;
+    ArenaLayout lay = ArenaLayout::make(0, 0);
+    char* h_arena = nullptr;
+    char* d_arena = nullptr;
+    size_t arena_cap = 0;
+    bool dirty_tables = true;  // spawners / batch infos / prefix sums changed since last flush
+    uint32_t epoch = 0;
+
+    // persistent device tables
+    uint32_t md_rows = 0, draw_rows = 0, child_rows = 0;
+    hnb::EffectMetadata* d_metadata = nullptr;
+    uint32_t* d_draw_args = nullptr;
+    hnb::ChildInfo* d_child_infos = nullptr;
+    // per-instance / per-batch scratch
+    uint32_t scratch_E = 0, scratch_B = 0;
+    uint32_t *d_tile_prefix = nullptr, *d_dispatch_args = nullptr, *d_batch_tiles = nullptr, *d_tickets = nullptr;
+    std::vector<unsigned long long*> d_tile_state;  // per batch
+    std::vector<uint32_t> tile_state_cap;
+
+    std::vector<Slab> slabs;
+    std::vector<Effect> effects;
+    std::vector<EventBuffer> event_buffers;
+    std::unordered_map<uint64_t, std::unique_ptr<KernelModule>> modules;  // ≙ ShaderCache
+
+    // kernel timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    double update_ms = 0.0;
+    uint64_t update_launches = 0;
+
+    hnb::FrameHeader* header() { return reinterpret_cast<hnb::FrameHeader*>(h_arena); }
+    template <typename T> T* h_at(size_t off) { return reinterpret_cast<T*>(h_arena + off); }
+    template <typename T> T* d_at(size_t off) { return reinterpret_cast<T*>(d_arena + off); }
+};
+
+namespace {
+
+void ensure_arena(hnb_ctx* c, uint32_t E, uint32_t B) {
+    if (E == c->E && B == c->B && c->h_arena) return;
+    ArenaLayout nl = ArenaLayout::make(E, B);
+    size_t need = std::max<size_t>(nl.total, 256);
+    char* nh = c->h_arena;
+    if (need > c->arena_cap) {
+        size_t cap = std::max(need * 2, size_t(4096));
+        CUDA_CHECK(cudaMallocHost((void**)&nh, cap));
+        memset(nh, 0, cap);
+        char* nd = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&nd, cap));
+        CUDA_CHECK(cudaMemsetAsync(nd, 0, cap, c->stream));
+        if (c->h_arena) {
+            // repack below from the old arena
+        }
+        // move: copy old host contents into the new buffer at the new offsets
+        std::vector<char> old(c->h_arena ? c->lay.total : 0);
+        if (c->h_arena) memcpy(old.data(), c->h_arena, c->lay.total);
+        if (c->h_arena) {
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            cudaFreeHost(c->h_arena);
+            cudaFree(c->d_arena);
+        }
+        const ArenaLayout ol = c->lay;
+        const uint32_t oE = c->E, oB = c->B;
+        c->h_arena = nh;
+        c->d_arena = nd;
+        c->arena_cap = cap;
+        if (!old.empty()) {
+            memcpy(nh, old.data(), sizeof(hnb::FrameHeader));
+            uint32_t mB = std::min(oB, B), mE = std::min(oE, E);
+            memcpy(nh + nl.off_batch_infos, old.data() + ol.off_batch_infos, size_t(mB) * sizeof(hnb_batch_info));
+            memcpy(nh + nl.off_tile_size, old.data() + ol.off_tile_size, size_t(mB) * 4);
+            memcpy(nh + nl.off_spawners, old.data() + ol.off_spawners, size_t(mE) * sizeof(hnb_spawner));
+            memcpy(nh + nl.off_range, old.data() + ol.off_range, size_t(mE) * 4);
+            memcpy(nh + nl.off_spawn_prefix, old.data() + ol.off_spawn_prefix, size_t(mE) * 4);
+            memcpy(nh + nl.off_prefix_sum, old.data() + ol.off_prefix_sum, size_t(mE) * 4);
+        }
+    } else if (c->h_arena) {
+        // same buffer, new offsets: repack through a temporary copy
+        std::vector<char> old(c->lay.total);
+        memcpy(old.data(), c->h_arena, c->lay.total);
+        const ArenaLayout ol = c->lay;
+        uint32_t mB = std::min(c->B, B), mE = std::min(c->E, E);
+        memset(c->h_arena + sizeof(hnb::FrameHeader), 0, nl.total - sizeof(hnb::FrameHeader));
+        memcpy(nh + nl.off_batch_infos, old.data() + ol.off_batch_infos, size_t(mB) * sizeof(hnb_batch_info));
+        memcpy(nh + nl.off_tile_size, old.data() + ol.off_tile_size, size_t(mB) * 4);
+        memcpy(nh + nl.off_spawners, old.data() + ol.off_spawners, size_t(mE) * sizeof(hnb_spawner));
+        memcpy(nh + nl.off_range, old.data() + ol.off_range, size_t(mE) * 4);
+        memcpy(nh + nl.off_spawn_prefix, old.data() + ol.off_spawn_prefix, size_t(mE) * 4);
+        memcpy(nh + nl.off_prefix_sum, old.data() + ol.off_prefix_sum, size_t(mE) * 4);
+    }
+    c->lay = nl;
+    c->E = E;
+    c->B = B;
+    c->dirty_tables = true;
+}
+
+template <typename T> void grow_device(T*& p, uint32_t& rows, uint32_t need, cudaStream_t st) {
+    if (need <= rows) return;
+    uint32_t cap = std::max<uint32_t>(need, std::max<uint32_t>(rows * 2, 16));
+    T* np = nullptr;
+    CUDA_CHECK(cudaMalloc((void**)&np, size_t(cap) * sizeof(T)));
+    CUDA_CHECK(cudaMemsetAsync(np, 0, size_t(cap) * sizeof(T), st));
+    if (p) {
+        CUDA_CHECK(cudaMemcpyAsync(np, p, size_t(rows) * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(p);
+    }
+    p = np;
+    rows = cap;
+}
+
+void ensure_scratch(hnb_ctx* c) {
+    if (c->E > c->scratch_E) {
+        if (c->d_tile_prefix) cudaFree(c->d_tile_prefix);
+        uint32_t cap = std::max<uint32_t>(c->E * 2, 64);
+        CUDA_CHECK(cudaMalloc((void**)&c->d_tile_prefix, size_t(cap) * 4));
+        CUDA_CHECK(cudaMemsetAsync(c->d_tile_prefix, 0, size_t(cap) * 4, c->stream));
+        c->scratch_E = cap;
+    }
+    if (c->B > c->scratch_B) {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (c->d_dispatch_args) { cudaFree(c->d_dispatch_args); cudaFree(c->d_batch_tiles); cudaFree(c->d_tickets); }
+        uint32_t cap = std::max<uint32_t>(c->B * 2, 16);
+        CUDA_CHECK(cudaMalloc((void**)&c->d_dispatch_args, size_t(cap) * 12));
+        CUDA_CHECK(cudaMalloc((void**)&c->d_batch_tiles, size_t(cap) * 4));
+        CUDA_CHECK(cudaMalloc((void**)&c->d_tickets, size_t(cap) * 4));
+        CUDA_CHECK(cudaMemsetAsync(c->d_dispatch_args, 0, size_t(cap) * 12, c->stream));
+        CUDA_CHECK(cudaMemsetAsync(c->d_batch_tiles, 0, size_t(cap) * 4, c->stream));
+        CUDA_CHECK(cudaMemsetAsync(c->d_tickets, 0, size_t(cap) * 4, c->stream));
+        c->scratch_B = cap;
+        c->d_tile_state.resize(cap, nullptr);
+        c->tile_state_cap.resize(cap, 0);
+    }
+}
+
+hnb::StaticTables static_tables(hnb_ctx* c) {
+    hnb::StaticTables T{};
+    T.frame = c->d_at<hnb::FrameHeader>(0);
+    T.spawners = c->d_at<hnb::Spawner>(c->lay.off_spawners);
+    T.spawn_range = c->d_at<uint32_t>(c->lay.off_range);
+    T.prefix_sum = c->d_at<uint32_t>(c->lay.off_prefix_sum);
+    T.tile_prefix = c->d_tile_prefix;
+    T.batch_infos = c->d_at<hnb::BatchInfo>(c->lay.off_batch_infos);
+    T.batch_tile_size = c->d_at<uint32_t>(c->lay.off_tile_size);
+    T.dispatch_args = c->d_dispatch_args;
+    T.batch_tiles = c->d_batch_tiles;
+    T.tickets = c->d_tickets;
+    T.metadata = c->d_metadata;
+    T.draw_args = c->d_draw_args;
+    T.child_infos = c->d_child_infos;
+    T.num_child_infos = c->child_rows ? c->child_rows : 0;
+    return T;
+}
+
+// One host->device copy of the frame block. `with_tables` false: only the 64-byte header.
+void flush_arena(hnb_ctx* c, bool with_ranges) {
+    if (!c->h_arena) ensure_arena(c, c->E, c->B);
+    size_t bytes;
+    if (c->dirty_tables) bytes = c->lay.total;
+    else if (with_ranges) bytes = c->lay.off_prefix_sum;  // everything but the GPU-rewritten prefix sums
+    else bytes = sizeof(hnb::FrameHeader);
+    CUDA_CHECK(cudaMemcpyAsync(c->d_arena, c->h_arena, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->dirty_tables = false;
+}
+
+void next_epoch(hnb_ctx* c) {
+    c->epoch = (c->epoch + 1u) & 0x3fffffffu;
+    if (c->epoch == 0) c->epoch = 1;  // 0 = "never written" in tile states
+    c->header()->epoch = c->epoch;
+    c->header()->num_batches = c->B;
+}
+
+Slab& get_slab(hnb_ctx* c, hnb_slab s) {
+    if (s >= c->slabs.size() || !c->slabs[s].live) fail(HNB_ERR_INVALID_ARG, "invalid slab handle");
+    return c->slabs[s];
+}
+Effect& get_effect(hnb_ctx* c, hnb_effect e) {
+    if (e >= c->effects.size() || !c->effects[e].live) fail(HNB_ERR_INVALID_ARG, "invalid effect handle");
+    return c->effects[e];
+}
+
+hnb::PlaneSet plane_set(const Slab& s) {
+    hnb::PlaneSet ps{};
+    for (size_t p = 0; p < s.planes.size(); ++p) {
+        ps.ptr[p] = s.d_planes[p];
+        ps.words[p] = s.planes[p].width / 4;
+        ps.word_off[p] = s.planes[p].offset / 4;
+        for (uint32_t w = 0; w < s.planes[p].width / 4; ++w) ps.word_to_plane[s.planes[p].offset / 4 + w] = (unsigned char)p;
+    }
+    return ps;
+}
+
+hnb::SlabView slab_view(const Slab& s) {
+    hnb::SlabView v{};
+    for (size_t p = 0; p < s.planes.size(); ++p) v.planes[p] = s.d_planes[p];
+    v.particle_index[0] = s.ping;
+    v.particle_index[1] = s.pong;
+    v.dead_index = s.dead;
+    v.capacity_rows = s.capacity;
+    return v;
+}
+
+void check_rows(const Slab& s, uint32_t first, uint32_t count) {
+    if (uint64_t(first) + count > s.capacity) fail(HNB_ERR_OUT_OF_RANGE, "row range exceeds slab capacity");
+}
+
+// Staging through a device buffer in chunks (AoS <-> planes transposes run on the device).
+constexpr size_t kChunkBytes = size_t(64) << 20;
+
+KernelModule* get_module(hnb_ctx* c, const std::string& source, const std::string& name, uint64_t hash) {
+    auto it = c->modules.find(hash);
+    if (it != c->modules.end()) return it->second.get();
+    std::string cubin, log;
+    if (!nvrtc_compile_sm100a(source, name + ".cu", cubin, log)) fail(HNB_ERR_NVRTC, log);
+    auto km = std::make_unique<KernelModule>();
+    km->log = log;
+    CUresult r = c->drv.ModuleLoadData(&km->mod, cubin.data());
+    if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuModuleLoadData: " + cu_error_string(c->drv, r));
+    r = c->drv.ModuleGetFunction(&km->init, km->mod, "hnb_init");
+    if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuModuleGetFunction(hnb_init): " + cu_error_string(c->drv, r));
+    r = c->drv.ModuleGetFunction(&km->update, km->mod, "hnb_update");
+    if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuModuleGetFunction(hnb_update): " + cu_error_string(c->drv, r));
+    int bps = 0;
+    r = c->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&bps, km->update, 256, 0);
+    if (r != CUDA_SUCCESS || bps < 1) bps = 1;
+    km->update_blocks_per_sm = bps;
+    KernelModule* out = km.get();
+    c->modules.emplace(hash, std::move(km));
+    return out;
+}
+
+struct LaunchPlan {
+    Effect* fx;
+    Slab* slab;
+    uint32_t batch;
+    uint32_t total_spawn;
+    hnb::BatchParams params;
+    uint32_t init_blocks;
+    uint32_t update_blocks;
+};
+
+void ensure_tile_state(hnb_ctx* c, uint32_t batch, uint32_t tiles) {
+    if (c->tile_state_cap[batch] >= tiles) return;
+    if (c->d_tile_state[batch]) {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_tile_state[batch]);
+    }
+    uint32_t cap = tiles + tiles / 2 + 64;
+    CUDA_CHECK(cudaMalloc((void**)&c->d_tile_state[batch], size_t(cap) * 8));
+    CUDA_CHECK(cudaMemsetAsync(c->d_tile_state[batch], 0, size_t(cap) * 8, c->stream));
+    c->tile_state_cap[batch] = cap;
+}
+
+// Build the kernel parameters of one batch and write its per-instance init thread ranges and tile
+// size into the host arena.
+LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
+    LaunchPlan lp{};
+    lp.fx = &get_effect(c, bl.effect);
+    lp.slab = &get_slab(c, bl.slab);
+    if (lp.fx->particle_stride != lp.slab->stride) fail(HNB_ERR_LAYOUT, "effect particle stride does not match the slab");
+    if (bl.batch_info_index >= c->B) fail(HNB_ERR_OUT_OF_RANGE, "batch_info_index out of range");
+    lp.batch = bl.batch_info_index;
+    lp.total_spawn = bl.total_spawn_count;
+    const hnb_batch_info& bi = c->h_at<hnb_batch_info>(c->lay.off_batch_infos)[lp.batch];
+    if (uint64_t(bi.prefix_sum_offset) + bi.prefix_sum_count > c->E || uint64_t(bi.spawner_base) + bi.prefix_sum_count > c->E)
+        fail(HNB_ERR_OUT_OF_RANGE, "batch references instances outside the uploaded spawner table");
+    const uint32_t tile = 256u * lp.fx->tile_k;
+    c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile;
+
+    const bool consume = (lp.fx->flags & HNB_EFFECT_CONSUME_GPU_SPAWN_EVENTS) != 0;
+    uint32_t init_threads = 0;
+    if (consume) {
+        if (bl.consume_events >= c->event_buffers.size()) fail(HNB_ERR_INVALID_ARG, "event-driven effect needs a consume_events buffer");
+        init_threads = ceil_div(c->event_buffers[bl.consume_events].capacity, 64) * 64;
+    } else {
+        init_threads = ceil_div(lp.total_spawn, 64) * 64;  // dispatch_workgroups(ceil(n/64)), mod.rs:7157-7173
+    }
+    if (set_ranges) {
+        uint32_t* range = c->h_at<uint32_t>(c->lay.off_range);
+        const uint32_t* sp = c->h_at<uint32_t>(c->lay.off_spawn_prefix);
+        for (uint32_t i = 0; i < bi.prefix_sum_count; ++i) {
+            uint32_t g = bi.prefix_sum_offset + i;
+            uint32_t r = 0;
+            if (init_threads) {
+                uint32_t end = (i + 1 < bi.prefix_sum_count) ? sp[g + 1] : init_threads;
+                r = end > sp[g] ? end - sp[g] : 0;
+                if (consume && r) r |= 0x80000000u;
+            }
+            range[g] = r;
+        }
+    }
+    ensure_tile_state(c, lp.batch, lp.slab->capacity / tile + bi.prefix_sum_count + 1);
+
+    hnb::BatchParams& P = lp.params;
+    P.frame = c->d_at<hnb::FrameHeader>(0);
+    P.spawners = c->d_at<hnb::Spawner>(c->lay.off_spawners);
+    P.spawn_prefix = c->d_at<uint32_t>(c->lay.off_spawn_prefix);
+    P.prefix_sum = c->d_at<uint32_t>(c->lay.off_prefix_sum);
+    P.tile_prefix = c->d_tile_prefix;
+    P.batch_info = c->d_at<hnb::BatchInfo>(c->lay.off_batch_infos) + lp.batch;
+    P.batch_tiles = c->d_batch_tiles + lp.batch;
+    P.ticket = c->d_tickets + lp.batch;
+    P.tile_state = c->d_tile_state[lp.batch];
+    P.metadata = c->d_metadata;
+    P.draw_args = c->d_draw_args;
+    P.child_infos = c->d_child_infos;
+    P.properties = lp.fx->d_props;
+    P.properties_stride = lp.fx->props_stride;
+    P.slab = slab_view(*lp.slab);
+    if (bl.parent_slab != 0xFFFFFFFFu) P.parent_slab = slab_view(get_slab(c, bl.parent_slab));
+    if (consume) P.consume_events = c->event_buffers[bl.consume_events].d;
+    for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
+        if (bl.emit_events[i] != 0xFFFFFFFFu) {
+            if (bl.emit_events[i] >= c->event_buffers.size()) fail(HNB_ERR_INVALID_ARG, "invalid emit event buffer");
+            P.emit_events[i] = c->event_buffers[bl.emit_events[i]].d;
+            P.emit_events_capacity[i] = c->event_buffers[bl.emit_events[i]].capacity;
+        }
+    }
+    P.init_thread_count = init_threads;
+    lp.init_blocks = ceil_div(init_threads, 256);
+    uint32_t max_tiles = lp.slab->capacity / tile + bi.prefix_sum_count + 1;
+    lp.update_blocks = std::min<uint32_t>(max_tiles, uint32_t(lp.fx->km->update_blocks_per_sm) * uint32_t(c->sm_count));
+    if (lp.update_blocks == 0) lp.update_blocks = 1;
+    if (lp.fx->props_size && !lp.fx->d_props) fail(HNB_ERR_NOT_READY, "effect uses properties but none were uploaded");
+    return lp;
+}
+
+void launch_kernel(hnb_ctx* c, CUfunction f, uint32_t blocks, hnb::BatchParams& P) {
+    void* args[] = {&P};
+    CUresult r = c->drv.LaunchKernel(f, blocks, 1, 1, 256, 1, 1, 0, (CUstream)c->stream, args, nullptr);
+    if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuLaunchKernel: " + cu_error_string(c->drv, r));
+    c->launches++;
+}
+
+void launch_update(hnb_ctx* c, LaunchPlan& lp) {
+    std::pair<cudaEvent_t, cudaEvent_t> ev{};
+    if (c->timing) {
+        if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); }
+        else { CUDA_CHECK(cudaEventCreate(&ev.first)); CUDA_CHECK(cudaEventCreate(&ev.second)); }
+        CUDA_CHECK(cudaEventRecord(ev.first, c->stream));
+    }
+    launch_kernel(c, lp.fx->km->update, lp.update_blocks, lp.params);
+    if (c->timing) {
+        CUDA_CHECK(cudaEventRecord(ev.second, c->stream));
+        c->ev_pending.push_back(ev);
+    }
+}
+
+void check_coverage(hnb_ctx* c, const std::vector<LaunchPlan>& plans) {
+    // the fused bookkeeping kernel visits instances batch by batch: the launched batches must tile
+    // [0, num_effects) exactly (Batcher::push allocates spawners and prefix entries in sync)
+    std::vector<std::pair<uint32_t, uint32_t>> ranges;
+    const hnb_batch_info* bis = c->h_at<hnb_batch_info>(c->lay.off_batch_infos);
+    for (uint32_t b = 0; b < c->B; ++b) ranges.push_back({bis[b].prefix_sum_offset, bis[b].prefix_sum_count});
+    std::sort(ranges.begin(), ranges.end());
+    uint32_t pos = 0;
+    for (auto& r : ranges) {
+        if (r.first != pos) fail(HNB_ERR_BATCH_COVERAGE, "batches do not tile the spawner table");
+        pos += r.second;
+    }
+    if (pos != c->header()->sim.num_effects) fail(HNB_ERR_BATCH_COVERAGE, "batches do not cover sim_params.num_effects instances");
+    for (uint32_t b = 0; b < c->B; ++b)
+        if (bis[b].spawner_base != bis[b].prefix_sum_offset) fail(HNB_ERR_BATCH_COVERAGE, "spawner_base must equal prefix_sum_offset");
+    std::vector<bool> seen(c->B, false);
+    for (auto& p : plans) {
+        if (seen[p.batch]) fail(HNB_ERR_INVALID_ARG, "batch launched twice");
+        seen[p.batch] = true;
+    }
+    for (uint32_t b = 0; b < c->B; ++b)
+        if (!seen[b]) fail(HNB_ERR_NOT_READY, "every uploaded batch must be launched by hnb_simulate");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* hnb_last_error(void) { return g_last_error.c_str(); }
+const char* hnb_version(void) { return "hanabi_b200 0.1.0 (sm_100a)"; }
+
+int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx** out) {
+    return guarded([&] {
+        if (!out) fail(HNB_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            (void)cudaGetLastError();
+            fail(HNB_ERR_NO_DEVICE, std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                                        "): hanabi_b200 has no CPU fallback");
+        }
+        if (cuda_device < 0 || cuda_device >= n) fail(HNB_ERR_INVALID_ARG, "cuda_device out of range");
+        CUDA_CHECK(cudaSetDevice(cuda_device));
+        CUDA_CHECK(cudaFree(0));
+        auto c = std::make_unique<hnb_ctx>();
+        c->device = cuda_device;
+        std::string err;
+        if (!load_driver_api(c->drv, err)) fail(HNB_ERR_NO_DEVICE, err);
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, cuda_device));
+        c->sm_count = prop.multiProcessorCount;
+        if (prop.major != 10) fail(HNB_ERR_NO_DEVICE, "hanabi_b200 kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+        if (external_stream) {
+            c->stream = (cudaStream_t)external_stream;
+        } else {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            c->own_stream = true;
+        }
+        ensure_arena(c.get(), 0, 0);
+        *out = c.release();
+    });
+}
+
+void hnb_ctx_destroy(hnb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& s : c->slabs) {
+        if (!s.live) continue;
+        for (auto p : s.d_planes) if (p) cudaFree(p);
+        cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead);
+    }
+    for (auto& e : c->effects) if (e.d_props) cudaFree(e.d_props);
+    for (auto& b : c->event_buffers) if (b.d) cudaFree(b.d);
+    for (auto& m : c->modules) if (m.second->mod) c->drv.ModuleUnload(m.second->mod);
+    for (auto p : c->d_tile_state) if (p) cudaFree(p);
+    for (auto& ev : c->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& ev : c->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (c->h_arena) cudaFreeHost(c->h_arena);
+    if (c->d_arena) cudaFree(c->d_arena);
+    cudaFree(c->d_metadata); cudaFree(c->d_draw_args); cudaFree(c->d_child_infos);
+    cudaFree(c->d_tile_prefix); cudaFree(c->d_dispatch_args); cudaFree(c->d_batch_tiles); cudaFree(c->d_tickets);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int32_t hnb_sync(hnb_ctx* c) {
+    return guarded([&] { CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+}
+uintptr_t hnb_ctx_stream(hnb_ctx* c) { return (uintptr_t)c->stream; }
+uint64_t hnb_ctx_launch_count(hnb_ctx* c) { return c->launches; }
+int32_t hnb_ctx_set_graphs(hnb_ctx* c, int32_t enabled) {
+    c->graphs = enabled != 0;
+    return HNB_OK;
+}
+
+// ---- slabs ----------------------------------------------------------------------------------
+int32_t hnb_slab_create(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, hnb_slab* out) {
+    return guarded([&] {
+        if (!out || capacity_rows == 0) fail(HNB_ERR_INVALID_ARG, "bad slab arguments");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Slab s;
+        s.capacity = capacity_rows;
+        s.stride = stride;
+        s.planes = cut_planes(stride);
+        for (size_t p = 0; p < s.planes.size(); ++p) {
+            CUDA_CHECK(cudaMalloc(&s.d_planes[p], size_t(capacity_rows) * s.planes[p].width));
+#ifndef NDEBUG
+            // debug builds of the reference poison particle buffers (effect_cache.rs:284-296)
+#endif
+            CUDA_CHECK(cudaMemsetAsync(s.d_planes[p], 0, size_t(capacity_rows) * s.planes[p].width, c->stream));
+        }
+        CUDA_CHECK(cudaMalloc((void**)&s.ping, size_t(capacity_rows) * 4));
+        CUDA_CHECK(cudaMalloc((void**)&s.pong, size_t(capacity_rows) * 4));
+        CUDA_CHECK(cudaMalloc((void**)&s.dead, size_t(capacity_rows) * 4));
+        CUDA_CHECK(hnb::launch_slab_reset(s.ping, s.pong, s.dead, 0, capacity_rows, c->stream));
+        c->launches++;
+        s.live = true;
+        c->slabs.push_back(s);
+        *out = (hnb_slab)(c->slabs.size() - 1);
+    });
+}
+
+int32_t hnb_slab_destroy(hnb_ctx* c, hnb_slab h) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (auto& p : s.d_planes) if (p) { cudaFree(p); p = nullptr; }
+        cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead);
+        s.live = false;
+    });
+}
+
+int32_t hnb_slab_reset_rows(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        CUDA_CHECK(hnb::launch_slab_reset(s.ping, s.pong, s.dead, first, count, c->stream));
+        c->launches++;
+    });
+}
+
+int32_t hnb_slab_upload_aos(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, const void* aos) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count == 0) return;
+        const uint32_t rows_per_chunk = (uint32_t)std::max<size_t>(1, kChunkBytes / s.stride);
+        uint32_t* stage = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&stage, size_t(std::min(rows_per_chunk, count)) * s.stride));
+        hnb::PlaneSet ps = plane_set(s);
+        for (uint32_t done = 0; done < count; done += rows_per_chunk) {
+            uint32_t n = std::min(rows_per_chunk, count - done);
+            CUDA_CHECK(cudaMemcpyAsync(stage, (const char*)aos + size_t(done) * s.stride, size_t(n) * s.stride, cudaMemcpyHostToDevice, c->stream));
+            CUDA_CHECK(hnb::launch_aos_to_planes(stage, ps, first + done, n, s.stride / 4, c->stream));
+            c->launches++;
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        }
+        cudaFree(stage);
+    });
+}
+
+int32_t hnb_slab_download_aos(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, void* aos) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count == 0) return;
+        const uint32_t rows_per_chunk = (uint32_t)std::max<size_t>(1, kChunkBytes / s.stride);
+        uint32_t* stage = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&stage, size_t(std::min(rows_per_chunk, count)) * s.stride));
+        hnb::PlaneSet ps = plane_set(s);
+        for (uint32_t done = 0; done < count; done += rows_per_chunk) {
+            uint32_t n = std::min(rows_per_chunk, count - done);
+            CUDA_CHECK(hnb::launch_planes_to_aos(stage, ps, first + done, n, s.stride / 4, c->stream));
+            c->launches++;
+            CUDA_CHECK(cudaMemcpyAsync((char*)aos + size_t(done) * s.stride, stage, size_t(n) * s.stride, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        }
+        cudaFree(stage);
+    });
+}
+
+int32_t hnb_slab_upload_indirect(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, const hnb_indirect_index* rows) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count == 0) return;
+        uint32_t* stage = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&stage, size_t(count) * 12));
+        CUDA_CHECK(cudaMemcpyAsync(stage, rows, size_t(count) * 12, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(hnb::launch_indirect_deinterleave(stage, s.ping, s.pong, s.dead, first, count, c->stream));
+        c->launches++;
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(stage);
+    });
+}
+
+int32_t hnb_slab_download_indirect(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, hnb_indirect_index* rows) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count == 0) return;
+        uint32_t* stage = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&stage, size_t(count) * 12));
+        CUDA_CHECK(hnb::launch_indirect_interleave(stage, s.ping, s.pong, s.dead, first, count, c->stream));
+        c->launches++;
+        CUDA_CHECK(cudaMemcpyAsync(rows, stage, size_t(count) * 12, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(stage);
+    });
+}
+
+int32_t hnb_slab_fill_c5(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint32_t seed, float lo, float hi) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (s.stride != 32) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 needs the 32-byte {position,age,velocity,lifetime} layout");
+        CUDA_CHECK(hnb::launch_fill_c5(s.d_planes[0], s.d_planes[1], s.ping, s.pong, first, count, seed, lo, hi, c->stream));
+        c->launches++;
+    });
+}
+
+int32_t hnb_slab_checksum(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint64_t* out) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        unsigned long long* d = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&d, 8));
+        CUDA_CHECK(cudaMemsetAsync(d, 0, 8, c->stream));
+        CUDA_CHECK(hnb::launch_checksum(plane_set(s), first, count, s.stride / 4, d, c->stream));
+        c->launches++;
+        CUDA_CHECK(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    });
+}
+
+// ---- effects --------------------------------------------------------------------------------
+int32_t hnb_effect_generate_source(const hnb_effect_desc* desc, char* out, size_t cap, size_t* len) {
+    return guarded([&] {
+        if (!desc) fail(HNB_ERR_INVALID_ARG, "desc is NULL");
+        std::string src = generate_effect_source(*desc);
+        if (len) *len = src.size();
+        if (out && cap) {
+            size_t n = std::min(cap - 1, src.size());
+            memcpy(out, src.data(), n);
+            out[n] = 0;
+        }
+    });
+}
+
+int32_t hnb_nvrtc_check(const char* source, size_t* cubin_size) {
+    return guarded([&] {
+        std::string cubin, log;
+        if (!nvrtc_compile_sm100a(source, "check.cu", cubin, log)) fail(HNB_ERR_NVRTC, log);
+        g_last_error = log;  // compiler log (ptxas -v) available to the caller even on success
+        if (cubin_size) *cubin_size = cubin.size();
+    });
+}
+
+int32_t hnb_effect_compile(hnb_ctx* c, const hnb_effect_desc* desc, hnb_effect* out) {
+    return guarded([&] {
+        if (!desc || !out) fail(HNB_ERR_INVALID_ARG, "NULL argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        std::string src = generate_effect_source(*desc);
+        Effect fx;
+        fx.hash = fnv1a64(src);
+        fx.name = desc->name ? desc->name : "effect";
+        fx.km = get_module(c, src, fx.name, fx.hash);
+        fx.tile_k = choose_tile_k(*desc);
+        fx.flags = desc->flags;
+        fx.particle_stride = desc->particle_stride;
+        fx.parent_stride = desc->parent_particle_stride;
+        fx.props_size = desc->properties_size;
+        fx.props_stride = (uint32_t)align_up(desc->properties_size, 16);
+        fx.live = true;
+        c->effects.push_back(fx);
+        *out = (hnb_effect)(c->effects.size() - 1);
+    });
+}
+
+int32_t hnb_effect_destroy(hnb_ctx* c, hnb_effect h) {
+    return guarded([&] {
+        Effect& fx = get_effect(c, h);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (fx.d_props) cudaFree(fx.d_props);
+        fx.d_props = nullptr;
+        fx.live = false;  // the compiled module stays in the cache (ShaderCache never evicts either)
+    });
+}
+
+int32_t hnb_upload_properties(hnb_ctx* c, hnb_effect h, uint32_t array_index, const void* blob, uint32_t bytes) {
+    return guarded([&] {
+        Effect& fx = get_effect(c, h);
+        if (fx.props_size == 0) fail(HNB_ERR_INVALID_ARG, "effect has no properties");
+        if (bytes != fx.props_size) fail(HNB_ERR_LAYOUT, "property blob size does not match the effect's PropertyLayout");
+        if (array_index >= fx.props_rows) {
+            uint32_t cap = std::max<uint32_t>(array_index + 1, std::max<uint32_t>(fx.props_rows * 2, 4));
+            char* np = nullptr;
+            CUDA_CHECK(cudaMalloc((void**)&np, size_t(cap) * fx.props_stride));
+            CUDA_CHECK(cudaMemsetAsync(np, 0, size_t(cap) * fx.props_stride, c->stream));
+            if (fx.d_props) {
+                CUDA_CHECK(cudaMemcpyAsync(np, fx.d_props, size_t(fx.props_rows) * fx.props_stride, cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                cudaFree(fx.d_props);
+            }
+            fx.d_props = np;
+            fx.props_rows = cap;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(fx.d_props + size_t(array_index) * fx.props_stride, blob, bytes, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));  // blob is pageable caller memory
+    });
+}
+
+// ---- per-frame tables -------------------------------------------------------------------------
+int32_t hnb_set_sim_params(hnb_ctx* c, const hnb_sim_params* p) {
+    return guarded([&] {
+        if (!p) fail(HNB_ERR_INVALID_ARG, "params is NULL");
+        memcpy(&c->header()->sim, p, sizeof(*p));
+    });
+}
+
+int32_t hnb_upload_spawners(hnb_ctx* c, const hnb_spawner* rows, uint32_t n) {
+    return guarded([&] {
+        if (n && !rows) fail(HNB_ERR_INVALID_ARG, "rows is NULL");
+        ensure_arena(c, n, c->B);
+        memcpy(c->h_arena + c->lay.off_spawners, rows, size_t(n) * sizeof(hnb_spawner));
+        c->dirty_tables = true;
+    });
+}
+
+int32_t hnb_upload_batches(hnb_ctx* c, const hnb_batch_info* rows, uint32_t nb, const uint32_t* prefix, uint32_t np) {
+    return guarded([&] {
+        if ((nb && !rows) || (np && !prefix)) fail(HNB_ERR_INVALID_ARG, "NULL table");
+        ensure_arena(c, std::max(c->E, np), nb);
+        if (np > c->E) fail(HNB_ERR_OUT_OF_RANGE, "more prefix entries than instances");
+        memcpy(c->h_arena + c->lay.off_batch_infos, rows, size_t(nb) * sizeof(hnb_batch_info));
+        memcpy(c->h_arena + c->lay.off_spawn_prefix, prefix, size_t(np) * 4);
+        memcpy(c->h_arena + c->lay.off_prefix_sum, prefix, size_t(np) * 4);  // same buffer in the reference (batch.rs:194-216)
+        memset(c->h_arena + c->lay.off_range, 0, size_t(c->E) * 4);
+        c->dirty_tables = true;
+    });
+}
+
+int32_t hnb_metadata_insert(hnb_ctx* c, uint32_t row, const hnb_effect_metadata* md) {
+    return guarded([&] {
+        if (!md) fail(HNB_ERR_INVALID_ARG, "md is NULL");
+        grow_device(c->d_metadata, c->md_rows, row + 1, c->stream);
+        CUDA_CHECK(cudaMemcpyAsync(c->d_metadata + row, md, sizeof(*md), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_draw_args_insert(hnb_ctx* c, uint32_t row, const hnb_draw_indexed_indirect_args* a) {
+    return guarded([&] {
+        if (!a) fail(HNB_ERR_INVALID_ARG, "args is NULL");
+        uint32_t words = c->draw_rows * 5;
+        if (row >= c->draw_rows) {
+            uint32_t need_rows = std::max<uint32_t>(row + 1, std::max<uint32_t>(c->draw_rows * 2, 16));
+            uint32_t need_words = need_rows * 5;
+            grow_device(c->d_draw_args, words, need_words, c->stream);
+            c->draw_rows = words / 5;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(c->d_draw_args + size_t(row) * 5, a, sizeof(*a), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_event_buffer_create(hnb_ctx* c, uint32_t capacity, hnb_event_buffer* out) {
+    return guarded([&] {
+        if (!out || !capacity) fail(HNB_ERR_INVALID_ARG, "bad event buffer arguments");
+        EventBuffer b;
+        b.capacity = capacity;
+        CUDA_CHECK(cudaMalloc((void**)&b.d, size_t(capacity) * 4));
+        CUDA_CHECK(cudaMemsetAsync(b.d, 0, size_t(capacity) * 4, c->stream));
+        c->event_buffers.push_back(b);
+        *out = (hnb_event_buffer)(c->event_buffers.size() - 1);
+    });
+}
+
+int32_t hnb_child_info_insert(hnb_ctx* c, uint32_t row, const hnb_child_info* info) {
+    return guarded([&] {
+        if (!info) fail(HNB_ERR_INVALID_ARG, "info is NULL");
+        uint32_t rows = c->child_rows;
+        // child_rows tracks the logical array length (arrayLength() in vfx_indirect.wgsl:43)
+        uint32_t cap = c->child_rows;
+        if (row >= cap) {
+            hnb::ChildInfo* np = nullptr;
+            uint32_t ncap = row + 1;
+            CUDA_CHECK(cudaMalloc((void**)&np, size_t(ncap) * sizeof(hnb::ChildInfo)));
+            CUDA_CHECK(cudaMemsetAsync(np, 0, size_t(ncap) * sizeof(hnb::ChildInfo), c->stream));
+            if (c->d_child_infos) {
+                CUDA_CHECK(cudaMemcpyAsync(np, c->d_child_infos, size_t(rows) * sizeof(hnb::ChildInfo), cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_child_infos);
+            }
+            c->d_child_infos = np;
+            c->child_rows = ncap;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(c->d_child_infos + row, info, sizeof(*info), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_read_child_info(hnb_ctx* c, uint32_t row, hnb_child_info* out) {
+    return guarded([&] {
+        if (row >= c->child_rows) fail(HNB_ERR_OUT_OF_RANGE, "child info row out of range");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_child_infos + row, sizeof(*out), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_event_buffer_download(hnb_ctx* c, hnb_event_buffer h, uint32_t first, uint32_t count, uint32_t* out) {
+    return guarded([&] {
+        if (h >= c->event_buffers.size()) fail(HNB_ERR_INVALID_ARG, "invalid event buffer");
+        auto& b = c->event_buffers[h];
+        if (uint64_t(first) + count > b.capacity) fail(HNB_ERR_OUT_OF_RANGE, "event range out of bounds");
+        CUDA_CHECK(cudaMemcpyAsync(out, b.d + first, size_t(count) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+// ---- the hot path -----------------------------------------------------------------------------
+int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
+    return guarded([&] {
+        if (n && !batches) fail(HNB_ERR_INVALID_ARG, "batches is NULL");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        if (c->header()->sim.num_effects > c->E) fail(HNB_ERR_NOT_READY, "sim_params.num_effects exceeds the uploaded spawner table");
+        ensure_scratch(c);
+        std::vector<LaunchPlan> plans;
+        plans.reserve(n);
+        for (uint32_t i = 0; i < n; ++i) plans.push_back(plan_batch(c, batches[i], true));
+        check_coverage(c, plans);  // nothing has been enqueued yet: a bad frame is skipped as a whole
+        next_epoch(c);
+        flush_arena(c, true);
+        // pass "hanabi:init" (mod.rs:7025-7179)
+        for (auto& lp : plans)
+            if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params);
+        // passes "hanabi:indirect_dispatch" + "hanabi:update_prefix_sum" (mod.rs:7182-7275), fused
+        CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, c->stream));
+        c->launches += 1 + (c->child_rows ? 1 : 0);
+        // pass "hanabi:update" (mod.rs:7280-7370)
+        for (auto& lp : plans) launch_update(c, lp);
+    });
+}
+
+int32_t hnb_pass_init(hnb_ctx* c, const hnb_batch_launch* b) {
+    return guarded([&] {
+        if (!b) fail(HNB_ERR_INVALID_ARG, "batch is NULL");
+        ensure_scratch(c);
+        LaunchPlan lp = plan_batch(c, *b, true);
+        c->header()->num_batches = c->B;
+        if (c->header()->epoch == 0) next_epoch(c);
+        flush_arena(c, true);
+        if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params);
+    });
+}
+
+int32_t hnb_pass_indirect(hnb_ctx* c) {
+    return guarded([&] {
+        ensure_scratch(c);
+        c->header()->num_batches = c->B;
+        flush_arena(c, false);
+        uint32_t ne = c->header()->sim.num_effects;
+        if (ne > c->E) fail(HNB_ERR_NOT_READY, "sim_params.num_effects exceeds the uploaded spawner table");
+        CUDA_CHECK(hnb::launch_indirect(static_tables(c), ne, c->stream));
+        c->launches += ne ? (1 + (c->child_rows ? 1 : 0)) : 0;
+    });
+}
+
+int32_t hnb_pass_prefix_sum(hnb_ctx* c) {
+    return guarded([&] {
+        ensure_scratch(c);
+        c->header()->num_batches = c->B;
+        // default tile size for batches never planned by a launch
+        uint32_t* ts = c->h_at<uint32_t>(c->lay.off_tile_size);
+        for (uint32_t b = 0; b < c->B; ++b) if (ts[b] == 0) ts[b] = 1024;
+        flush_arena(c, false);
+        CUDA_CHECK(hnb::launch_prefix_sum(static_tables(c), c->B, c->stream));
+        c->launches += c->B ? 1 : 0;
+    });
+}
+
+int32_t hnb_pass_update(hnb_ctx* c, const hnb_batch_launch* b) {
+    return guarded([&] {
+        if (!b) fail(HNB_ERR_INVALID_ARG, "batch is NULL");
+        ensure_scratch(c);
+        LaunchPlan lp = plan_batch(c, *b, false);
+        next_epoch(c);
+        flush_arena(c, false);
+        launch_update(c, lp);
+    });
+}
+
+int32_t hnb_pass_fill_dispatch_args(hnb_ctx* c, const uint32_t* src, uint32_t src_offset, uint32_t src_stride, uint32_t* dst,
+                                    uint32_t dst_len, uint32_t dst_offset, uint32_t dst_stride, uint32_t count) {
+    return guarded([&] {
+        if (count == 0) return;
+        uint32_t src_len = src_offset + (count - 1) * src_stride + 1;
+        if (dst_offset + (count - 1) * dst_stride + 3 > dst_len) fail(HNB_ERR_OUT_OF_RANGE, "dst too small");
+        uint32_t *ds = nullptr, *dd = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&ds, size_t(src_len) * 4));
+        CUDA_CHECK(cudaMalloc((void**)&dd, size_t(dst_len) * 4));
+        CUDA_CHECK(cudaMemcpyAsync(ds, src, size_t(src_len) * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dd, dst, size_t(dst_len) * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(hnb::launch_fill_dispatch_args(ds, dd, src_offset, src_stride, dst_offset, dst_stride, count, c->stream));
+        c->launches++;
+        CUDA_CHECK(cudaMemcpyAsync(dst, dd, size_t(dst_len) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(ds);
+        cudaFree(dd);
+    });
+}
+
+// ---- readback ---------------------------------------------------------------------------------
+int32_t hnb_read_metadata(hnb_ctx* c, uint32_t row, hnb_effect_metadata* out) {
+    return guarded([&] {
+        if (row >= c->md_rows) fail(HNB_ERR_OUT_OF_RANGE, "metadata row out of range");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_metadata + row, sizeof(*out), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t hnb_read_draw_args(hnb_ctx* c, uint32_t row, hnb_draw_indexed_indirect_args* out) {
+    return guarded([&] {
+        if (row >= c->draw_rows) fail(HNB_ERR_OUT_OF_RANGE, "draw args row out of range");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_draw_args + size_t(row) * 5, sizeof(*out), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t hnb_read_draw_args_async(hnb_ctx* c, uint32_t first, uint32_t count, hnb_draw_indexed_indirect_args* pinned_out) {
+    return guarded([&] {
+        if (uint64_t(first) + count > c->draw_rows) fail(HNB_ERR_OUT_OF_RANGE, "draw args rows out of range");
+        CUDA_CHECK(cudaMemcpyAsync(pinned_out, c->d_draw_args + size_t(first) * 5, size_t(count) * 20, cudaMemcpyDeviceToHost, c->stream));
+    });
+}
+int32_t hnb_read_spawner(hnb_ctx* c, uint32_t row, hnb_spawner* out) {
+    return guarded([&] {
+        if (row >= c->E) fail(HNB_ERR_OUT_OF_RANGE, "spawner row out of range");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_arena + c->lay.off_spawners + size_t(row) * 128, 128, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t hnb_read_batch_info(hnb_ctx* c, uint32_t row, hnb_batch_info* out) {
+    return guarded([&] {
+        if (row >= c->B) fail(HNB_ERR_OUT_OF_RANGE, "batch row out of range");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_arena + c->lay.off_batch_infos + size_t(row) * 24, 24, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t hnb_read_prefix_sum(hnb_ctx* c, uint32_t first, uint32_t count, uint32_t* out) {
+    return guarded([&] {
+        if (uint64_t(first) + count > c->E) fail(HNB_ERR_OUT_OF_RANGE, "prefix range out of bounds");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_arena + c->lay.off_prefix_sum + size_t(first) * 4, size_t(count) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t hnb_read_dispatch_args(hnb_ctx* c, uint32_t row, hnb_dispatch_indirect_args* out) {
+    return guarded([&] {
+        if (row >= c->scratch_B) fail(HNB_ERR_OUT_OF_RANGE, "dispatch args row out of range");
+        CUDA_CHECK(cudaMemcpyAsync(out, c->d_dispatch_args + size_t(row) * 3, 12, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+void* hnb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void hnb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int32_t hnb_ctx_enable_kernel_timing(hnb_ctx* c, int32_t enabled) {
+    c->timing = enabled != 0;
+    return HNB_OK;
+}
+int32_t hnb_ctx_kernel_time_ms(hnb_ctx* c, double* update_ms_total, uint64_t* update_launches) {
+    return guarded([&] {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (auto& ev : c->ev_pending) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+            c->update_ms += ms;
+            c->update_launches++;
+            c->ev_free.push_back(ev);
+        }
+        c->ev_pending.clear();
+        if (update_ms_total) *update_ms_total = c->update_ms;
+        if (update_launches) *update_launches = c->update_launches;
+        c->update_ms = 0.0;
+        c->update_launches = 0;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// effect_source.h — generation of the per-effect CUDA C translation unit.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "hanabi_b200.h"
+
+#define HNB_RT_MAX_PLANES 16
+
+namespace hnb_rt {
+
+struct ValueTypeInfo {
+    const char* cuda;  // type name in generated code, e.g. "vec3<f32>"
+    const char* elem;  // element type name
+    int count;         // number of 32-bit components
+    char kind;         // 'f','i','u','b'
+};
+ValueTypeInfo value_type_info(uint32_t value_type);
+
+// One SoA plane: bytes [offset, offset+width) of the reference AoS record; width is 16, 8 or 4.
+struct Plane {
+    uint32_t offset;
+    uint32_t width;
+};
+// Cut an AoS record of `stride_bytes` into planes: as many 16-byte planes as fit, then an 8- and/or
+// 4-byte tail. Because the reference layout keeps vec3/vec4 16-byte aligned and vec2 8-byte aligned
+// (attributes.rs:1516-1670) no attribute straddles two planes.
+std::vector<Plane> cut_planes(uint32_t stride_bytes);
+
+// Rows per thread of the update tile for this effect (tile = 256 * k rows).
+uint32_t choose_tile_k(const hnb_effect_desc& d);
+
+// The complete translation unit (throws std::invalid_argument on a bad description).
+std::string generate_effect_source(const hnb_effect_desc& d);
+
+}  // namespace hnb_rt
