@@ -220,7 +220,10 @@ def run_b200(args):
         per_rank = args.particles
     total = per_rank * n_gpus
 
-    stream = torch.cuda.current_stream()
+    # all work goes on ONE explicit non-default stream shared by torch (events, barriers) and the backend
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = hb.Context(local_rank, stream.cuda_stream)
     slab = ctx.slab_create(per_rank, recipes.C5_STRIDE)
     effect = ctx.effect_compile(recipes.c5_lowered())
@@ -308,8 +311,7 @@ def run_b200(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = total * args.steps / (ms_e2e * 1e-3)
-    h2d = 64 + 24 + 4 + 128 + 3 * 4  # frame header + batch info + tile size + spawner row + range/spawn-prefix/prefix words
-    h2d = 64 + 24 + 4 + 4 + 128 + 12
+    h2d = 64 + 24 + 4 + 4 + 128 + 12  # frame header + batch info + tile size (+pad) + spawner row + range/spawn-prefix/prefix words
 
     # -- correctness guard inside the bench: the state must have advanced (age = steps*dt) and nothing died
     mdr = ctx.read_metadata(0)

@@ -184,6 +184,8 @@ SIGNATURES = {
     "hnb_read_draw_args_async": (i32, [vp, u32, u32, vp]),
     "hnb_host_alloc": (vp, [C.c_size_t]),
     "hnb_host_free": (None, [vp]),
+    "hnb_ctx_read_debug": (i32, [vp, P(C.c_uint64), i32]),
+    "hnb_ctx_measure_sm_mhz": (i32, [vp, u32, P(C.c_double)]),
     "hnb_ctx_enable_kernel_timing": (i32, [vp, i32]),
     "hnb_ctx_kernel_time_ms": (i32, [vp, P(C.c_double), P(C.c_uint64)]),
 }

@@ -13,14 +13,18 @@
 //   hnb_update_body(Particle&, Ctx&) -> bool  = {{AGE_CODE}} {{REAP_CODE}} {{UPDATE_CODE}}, returns is_alive
 //
 // Design:
-//   * update is a persistent, single-pass "process + stable compaction" kernel. A CTA takes tiles of
-//     HNB_TILE rows of ONE effect instance from a ticket counter; rows are read through the alive list
-//     (coalesced u32), particles through float4 SoA planes, processed in registers, written back, and
-//     the survivors' indices are compacted into the write list in row order using warp ballots inside
-//     the tile and a decoupled look-back chain across the tiles of the same instance. Dead rows are
-//     pushed on the dead stack in the same canonical (row) order. The only atomic on the path is the
-//     tile ticket: the per-particle contended atomics of the reference (vfx_update.wgsl:150,160,164)
-//     are replaced by exact ranks, which also makes list ORDER deterministic (= serial thread order).
+//   * update is a persistent, single-pass "process + stable compaction" kernel with WARP-AUTONOMOUS
+//     tiles: every warp of the persistent grid takes tiles of tile_rows = 32*K*chunks rows of ONE effect
+//     instance from a ticket counter. Rows are read through the alive
+//     list (coalesced u32), particles through float4 SoA planes, processed in registers and written
+//     back; survivors are compacted into the write list in row order with warp ballots inside the tile
+//     and a decoupled look-back chain (one 64-bit state word per tile) across the tiles of the same
+//     instance; dead rows are pushed on the dead stack in the same canonical (row) order. There is no
+//     block barrier and — in ordered mode — the only atomic is the tile ticket: the per-particle contended
+//     atomics of the reference (vfx_update.wgsl:150,160,164) become exact ranks, which also makes the
+//     list ORDER deterministic (= the reference's threads run in ascending global_invocation_id).
+//     With HNB_RELAXED_ORDER the chain is replaced by one warp-aggregated atomic per tile (counts and
+//     sets identical, order scheduling dependent like the reference).
 //   * init pops dead slots by rank as well: thread k of an instance takes dead[alive_count + k]
 //     (vfx_init.wgsl:141-143 in serial order); the alive_count / particle_counter increments are
 //     applied by the bookkeeping kernel that follows (hnb_static_kernels.cu).
@@ -30,12 +34,24 @@ namespace hnb {
 
 #define HNB_BLOCK 256
 #define HNB_WARPS (HNB_BLOCK / 32)
-#define HNB_TILE (HNB_BLOCK * HNB_TILE_K)
+// A tile is 1..HNB_MAX_CHUNKS sub-tiles of 32*K rows (BatchParams::tile_rows); at most 32 rows per
+// lane, i.e. 1024 rows per tile, so that the tile's alive-list entries fit a 4 KB per-warp stash.
+#define HNB_ROWS_PER_LANE 32
+#define HNB_MAX_CHUNKS (HNB_ROWS_PER_LANE / HNB_TILE_K)
+#ifndef HNB_LOOKBACK_GROUPS
+#define HNB_LOOKBACK_GROUPS 4  // predecessors examined per look-back round trip = 32 * groups
+#endif
 #ifndef HNB_SMEM_EFFECTS
 #define HNB_SMEM_EFFECTS 2048  // tile_prefix entries staged in shared memory (8 KB)
 #endif
 #ifndef HNB_MIN_BLOCKS
-#define HNB_MIN_BLOCKS 3
+#define HNB_MIN_BLOCKS 4
+#endif
+#ifndef HNB_PROFILE
+#define HNB_PROFILE 0  // 1: accumulate per-phase cycle counters into BatchParams::debug (diagnostics)
+#endif
+#ifndef HNB_LOOKBACK_SLEEP_NS
+#define HNB_LOOKBACK_SLEEP_NS 0  // back-off between polls of an unpublished predecessor (0 = spin)
 #endif
 
 // --- tile state word of the decoupled look-back: [63:34] epoch | [33:32] flag | [31:0] value ---
@@ -139,18 +155,15 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
 // ---------------------------------------------------------------------------------------------
 // update  ≙ vfx_update.wgsl main()
 // ---------------------------------------------------------------------------------------------
-struct UpdateShared {
-    u32 tile;
-    u32 alive_before;
-    u32 tile_alive;
-    u32 warp_alive[HNB_TILE_K * HNB_WARPS];  // per (k, warp) alive counts, then their exclusive scan
-    u32 tile_prefix[HNB_SMEM_EFFECTS + 1];
-};
-
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_update(const BatchParams P) {
-    __shared__ UpdateShared sh;
+    __shared__ u32 sh_tile_prefix[HNB_SMEM_EFFECTS + 1];
+    // survivor ballots of the tile a warp is working on (one word per 32 rows), pass 1 -> pass 2
+    __shared__ u32 sh_survivors[HNB_WARPS][HNB_ROWS_PER_LANE];
+    // alive-list entries of that tile (pass 1 reads them from global memory once, pass 2 from here)
+    __shared__ u32 sh_pidx[HNB_WARPS][HNB_ROWS_PER_LANE][32];
 #if HNB_HAS_PROPERTIES
-    __shared__ __align__(16) unsigned char sh_props[sizeof(Properties)];
+    // per-warp staging slot of the current instance's Properties record
+    __shared__ __align__(16) unsigned char sh_props[HNB_WARPS][(sizeof(Properties) + 15) / 16 * 16];
 #endif
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
@@ -163,200 +176,272 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     const u32 epoch = P.frame->epoch;
     const bool staged = n_effects <= HNB_SMEM_EFFECTS;
     if (staged) {
-        for (u32 i = tid; i < n_effects; i += HNB_BLOCK) sh.tile_prefix[i] = g_tile_prefix[i];
+        for (u32 i = tid; i < n_effects; i += HNB_BLOCK) sh_tile_prefix[i] = g_tile_prefix[i];
+        if (tid == 0) sh_tile_prefix[n_effects] = total_tiles;
     }
-    u32 staged_effect = HNB_INVALID;
-    (void)staged_effect;
+    __syncthreads();  // the only block barrier of the kernel
 
-    for (;;) {
-        __syncthreads();  // previous tile fully done (protects sh.* and sh_props); also covers the staging above
-        if (tid == 0) sh.tile = atomicAdd(P.ticket, 1u);
-        __syncthreads();
-        const u32 tile = sh.tile;
-        if (tile >= total_tiles) break;
+    u64* const states = P.tile_state;
+    // rows per tile = 32 lanes * K rows per lane * chunks; the chunk count is chosen per launch by the
+    // host (and used by the bookkeeping kernel for the tile prefix), so it is a run-time value here
+    const u32 tile_rows = P.tile_rows;
+    const u32 chunks = tile_rows / (32u * HNB_TILE_K);
+    u32* const survivors = sh_survivors[warp];
+    u32(*const pidx_stash)[32] = sh_pidx[warp];
 
-        // Which instance does this tile belong to? (per-CTA replacement of the per-thread binary search
-        // of vfx_update.wgsl:51-72; all threads read the same shared words: broadcast, no conflicts)
-        u32 effect_index, tile_in_effect;
-        if (staged) {
-            effect_index = hnb_find_effect(sh.tile_prefix, 0u, n_effects, tile);
-            tile_in_effect = tile - sh.tile_prefix[effect_index];
-        } else {
-            effect_index = hnb_find_effect(g_tile_prefix, 0u, n_effects, tile);
-            tile_in_effect = tile - g_tile_prefix[effect_index];
-        }
-        Spawner* spawner = &P.spawners[bi.spawner_base + effect_index];
-        const u32 base_particle = spawner->slab_offset;
-        const u32 spawner_seed = spawner->seed;
-        EffectMetadata* md = &P.metadata[spawner->effect_metadata_index];
-        const u32 max_update = md->max_update;  // :119
-        const u32 write_index = md->indirect_write_index;
-        const u32 read_index = 1u - write_index;
-        const u32* __restrict__ read_col = P.slab.particle_index[read_index] + base_particle;
-        u32* __restrict__ write_col = P.slab.particle_index[write_index] + base_particle;
+    // cached descriptor of the instance the current tile belongs to (reloaded when a tile leaves
+    // [inst_first_tile, inst_end_tile))
+    u32 inst_first_tile = 1u, inst_end_tile = 0u;  // empty range
+    Spawner* spawner = nullptr;
+    EffectMetadata* md = nullptr;
+    u32 base_particle = 0u, spawner_seed = 0u, max_update = 0u, write_index = 0u, render_index = 0u;
+    const u32* __restrict__ read_col = nullptr;
+    u32* __restrict__ write_col = nullptr;
 
-        Ctx hnb_ctx;
-        hnb_ctx.sim = &P.frame->sim;
-        hnb_ctx.spawner = spawner;
-        hnb_ctx.particle_counter = 0u;
-#if HNB_HAS_PROPERTIES
-        if (staged_effect != effect_index) {
-            const u32* src = (const u32*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
-            for (u32 i = tid; i < sizeof(Properties) / 4u; i += HNB_BLOCK) ((u32*)sh_props)[i] = src[i];
-            staged_effect = effect_index;
-            __syncthreads();
-        }
-        hnb_ctx.props = (const Properties*)sh_props;
+    Ctx hnb_ctx;
+    hnb_ctx.sim = &P.frame->sim;
+    hnb_ctx.particle_counter = 0u;
+    hnb_ctx.props = nullptr;
+#if HNB_EMIT_EVENTS
+    hnb_ctx.child_infos = P.child_infos;
+    for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
+        hnb_ctx.emit_events[i] = P.emit_events[i];
+        hnb_ctx.emit_events_capacity[i] = P.emit_events_capacity[i];
+    }
+#endif
+
+    // Tiles are handed out by a ticket counter (so that every tile's predecessors in the look-back
+    // chain have already been taken by a running warp); the ticket of the NEXT tile is requested
+    // between the look-back and pass 2 of the current one (see below).
+    u32 tile = 0u;
+    if (lane == 0) tile = atomicAdd(P.ticket, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+#if HNB_PROFILE
+    // per-warp cycle accounting of the three phases (diagnostics only)
+    long long prof_t0 = clock64(), prof_pass1 = 0, prof_lookback = 0, prof_pass2 = 0, prof_polls = 0, prof_tiles = 0;
+    const long long prof_start = prof_t0;
+#define HNB_PROF_MARK(acc) { const long long _t = clock64(); acc += _t - prof_t0; prof_t0 = _t; }
 #else
-        hnb_ctx.props = nullptr;
+#define HNB_PROF_MARK(acc)
+#endif
+
+    while (tile < total_tiles) {
+
+        if (tile < inst_first_tile || tile >= inst_end_tile) {
+            // Which instance does this tile belong to? (per-warp replacement of the per-thread binary
+            // search of vfx_update.wgsl:51-72; all lanes read the same words: broadcast)
+            u32 effect_index;
+            if (staged) {
+                effect_index = hnb_find_effect(sh_tile_prefix, 0u, n_effects, tile);
+                inst_first_tile = sh_tile_prefix[effect_index];
+                inst_end_tile = sh_tile_prefix[effect_index + 1u];
+            } else {
+                effect_index = hnb_find_effect(g_tile_prefix, 0u, n_effects, tile);
+                inst_first_tile = g_tile_prefix[effect_index];
+                inst_end_tile = effect_index + 1u < n_effects ? g_tile_prefix[effect_index + 1u] : total_tiles;
+            }
+            spawner = &P.spawners[bi.spawner_base + effect_index];
+            base_particle = spawner->slab_offset;
+            spawner_seed = spawner->seed;
+            md = &P.metadata[spawner->effect_metadata_index];
+            max_update = md->max_update;  // :119
+            write_index = md->indirect_write_index;
+            render_index = md->indirect_render_index;
+            read_col = P.slab.particle_index[1u - write_index] + base_particle;
+            write_col = P.slab.particle_index[write_index] + base_particle;
+            hnb_ctx.spawner = spawner;
+#if HNB_HAS_PROPERTIES
+            {
+                const u32* src = (const u32*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
+                __syncwarp();
+                for (u32 i = lane; i < sizeof(Properties) / 4u; i += 32u) ((u32*)sh_props[warp])[i] = src[i];
+                __syncwarp();
+                hnb_ctx.props = (const Properties*)sh_props[warp];
+            }
 #endif
 #if HNB_EMIT_EVENTS
-        hnb_ctx.child_infos = P.child_infos;
-        hnb_ctx.base_child_index = md->base_child_index;
-        for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
-            hnb_ctx.emit_events[i] = P.emit_events[i];
-            hnb_ctx.emit_events_capacity[i] = P.emit_events_capacity[i];
-        }
+            hnb_ctx.base_child_index = md->base_child_index;
 #endif
-
-        const u32 row0 = tile_in_effect * HNB_TILE;
-
-        // 1) alive-list entries of this tile: row = row0 + k*BLOCK + tid (coalesced)
-        u32 pidx[HNB_TILE_K];
-        bool valid[HNB_TILE_K];
-#pragma unroll
-        for (int k = 0; k < HNB_TILE_K; ++k) {
-            const u32 row = row0 + k * HNB_BLOCK + tid;
-            valid[k] = row < max_update;
-            pidx[k] = valid[k] ? read_col[row] : 0u;
         }
-        // 2) gather the particle records (all loads in flight before any use)
-        RawParticle raw[HNB_TILE_K];
+        const u32 tile_in_effect = tile - inst_first_tile;
+        const u32 row0 = tile_in_effect * tile_rows;
+
+        // ---- pass 1: stream the tile's rows in `chunks` sub-tiles of 32*K rows:
+        //      alive-list entry -> particle record -> simulate -> write back; remember who survived.
+        u32 tile_alive = 0u;
+        u32 pidx_next[HNB_TILE_K];
 #pragma unroll
         for (int k = 0; k < HNB_TILE_K; ++k) {
-            if (valid[k]) hnb_load_raw(raw[k], P.slab, base_particle + pidx[k]);
-            else hnb_raw_zero(raw[k]);
+            const u32 row = row0 + k * 32u + lane;
+            pidx_next[k] = row < max_update ? read_col[row] : 0u;
         }
-        // 3) simulate + write back (WRITEBACK_CODE: every attribute except PREV/NEXT, lib.rs:1270-1281)
-        bool alive[HNB_TILE_K];
+#pragma unroll 1
+        for (u32 j = 0; j < chunks; ++j) {
+            u32 pidx[HNB_TILE_K];
+            bool valid[HNB_TILE_K];
+            RawParticle raw[HNB_TILE_K];
+            // gather the particle records (all loads in flight before any use)
 #pragma unroll
-        for (int k = 0; k < HNB_TILE_K; ++k) {
-            alive[k] = false;
-            if (valid[k]) {
-                Particle particle;
-                hnb_unpack(raw[k], particle);
-                hnb_ctx.particle_index = pidx[k];
-                hnb_ctx.seed = pcg_hash(pidx[k] ^ spawner_seed);  // :138
-                hnb_ctx.is_alive = true;
-                alive[k] = hnb_update_body(particle, hnb_ctx);
-                hnb_pack<false>(particle, raw[k]);
-                hnb_store_raw(raw[k], P.slab, base_particle + pidx[k]);
+            for (int k = 0; k < HNB_TILE_K; ++k) {
+                const u32 row = row0 + (j * HNB_TILE_K + k) * 32u + lane;
+                pidx[k] = pidx_next[k];
+                pidx_stash[j * HNB_TILE_K + k][lane] = pidx[k];
+                valid[k] = row < max_update;
+                if (valid[k]) hnb_load_raw(raw[k], P.slab, base_particle + pidx[k]);
+                else hnb_raw_zero(raw[k]);
+            }
+            // prefetch the alive-list entries of the next sub-tile (coalesced u32)
+            if (j + 1 < chunks) {
+#pragma unroll
+                for (int k = 0; k < HNB_TILE_K; ++k) {
+                    const u32 row = row0 + ((j + 1) * HNB_TILE_K + k) * 32u + lane;
+                    pidx_next[k] = row < max_update ? read_col[row] : 0u;
+                }
+            }
+            // simulate + write back (WRITEBACK_CODE: every attribute except PREV/NEXT, lib.rs:1270-1281)
+#pragma unroll
+            for (int k = 0; k < HNB_TILE_K; ++k) {
+                bool alive = false;
+                if (valid[k]) {
+                    Particle particle;
+                    hnb_unpack(raw[k], particle);
+                    hnb_ctx.particle_index = pidx[k];
+                    hnb_ctx.seed = pcg_hash(pidx[k] ^ spawner_seed);  // :138
+                    hnb_ctx.is_alive = true;
+                    alive = hnb_update_body(particle, hnb_ctx);
+                    hnb_pack<false>(particle, raw[k]);
+                    hnb_store_raw(raw[k], P.slab, base_particle + pidx[k]);
+                }
+                const u32 ballot = __ballot_sync(0xffffffffu, alive);
+                if (lane == 0) survivors[j * HNB_TILE_K + k] = ballot;
+                tile_alive += __popc(ballot);
             }
         }
-        // 4) ranks of the survivors inside the tile (row order = (k, warp, lane))
-        u32 rank[HNB_TILE_K];
-#pragma unroll
-        for (int k = 0; k < HNB_TILE_K; ++k) {
-            const u32 ballot = __ballot_sync(0xffffffffu, alive[k]);
-            rank[k] = __popc(ballot & hnb_lanemask_lt());
-            if (lane == 0) sh.warp_alive[k * HNB_WARPS + warp] = __popc(ballot);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // exclusive scan of the K*WARPS (<= 32) counts
-            const u32 n = HNB_TILE_K * HNB_WARPS;
-            const u32 v = lane < n ? sh.warp_alive[lane] : 0u;
-            u32 incl = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (lane < n) sh.warp_alive[lane] = incl - v;
-            const u32 tile_alive = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();  // ballots visible to all lanes for pass 2
 
-            // 5) exclusive prefix over the previous tiles of this instance
-            u32 alive_before = 0u;
+        HNB_PROF_MARK(prof_pass1)
+        // ---- exclusive prefix over the previous tiles of this instance
+        u32 alive_before = 0u;
 #if HNB_RELAXED_ORDER
-            // Reference-style order (vfx_update.wgsl:164): one aggregated atomic per tile.
-            if (lane == 0) alive_before = atomicAdd(&P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * md->indirect_render_index + 1u], tile_alive);
-            alive_before = __shfl_sync(0xffffffffu, alive_before, 0);
+        // Reference-style order (vfx_update.wgsl:164) with one warp-aggregated atomic per tile.
+        if (lane == 0) alive_before = atomicAdd(&P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * render_index + 1u], tile_alive);
+        alive_before = __shfl_sync(0xffffffffu, alive_before, 0);
 #else
-            u64* states = P.tile_state;
-            if (tile_in_effect == 0u) {
-                if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, tile_alive));
-            } else {
-                if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_AGGREGATE, tile_alive));
-                const u32 first_tile = tile - tile_in_effect;
-                u32 pos = tile - 1u;  // newest predecessor examined by lane 0
-                for (;;) {
-                    const bool in_range = (pos >= first_tile + lane) && (pos >= lane);
-                    u64 s = 0;
-                    bool ready = true, is_prefix = true;
-                    if (in_range) {
-                        s = hnb_ld_state(&states[pos - lane]);
-                        ready = (u32(s >> 34) == epoch) && ((s >> 32) & 3ull) != 0ull;
-                        is_prefix = ((s >> 32) & 3ull) == HNB_FLAG_PREFIX;
+        if (tile_in_effect == 0u) {
+            if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, tile_alive));
+        } else {
+            if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_AGGREGATE, tile_alive));
+            // Walk back over the predecessors' states, HNB_LOOKBACK_GROUPS x 32 of them per round trip
+            // (lane l of group g examines tile pos - 32g - l), summing AGGREGATEs until the first
+            // PREFIX. Tiles before the instance's first tile count as a PREFIX of 0.
+            u32 pos = tile - 1u;  // newest predecessor not yet accounted for
+            for (;;) {
+                u64 s[HNB_LOOKBACK_GROUPS];
+#pragma unroll
+                for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
+                    const u32 back = 32u * g + lane;
+                    s[g] = (pos >= inst_first_tile + back) ? hnb_ld_state(&states[pos - back])
+                                                           : hnb_pack_state(epoch, HNB_FLAG_PREFIX, 0u);
+                }
+                bool done = false, stalled = false;
+#pragma unroll
+                for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
+                    if (!done && !stalled) {
+                        const u32 flag = (u32(s[g] >> 34) == epoch) ? (u32(s[g] >> 32) & 3u) : 0u;
+                        const u32 ready_mask = __ballot_sync(0xffffffffu, flag != 0u);
+                        const u32 prefix_mask = __ballot_sync(0xffffffffu, flag == u32(HNB_FLAG_PREFIX));
+                        const u32 first_p = prefix_mask ? (u32)(__ffs(prefix_mask) - 1) : 32u;
+                        const u32 need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
+                        if ((ready_mask & need) != need) {
+                            stalled = true;  // a needed predecessor has not published yet: poll again from here
+                        } else {
+                            u32 contrib = lane <= first_p ? u32(s[g]) : 0u;
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                            alive_before += contrib;
+                            if (prefix_mask) done = true; else pos -= 32u;
+                        }
                     }
-                    // lanes past the first tile of the instance act as a PREFIX of 0 (terminates the walk)
-                    const u32 ready_mask = __ballot_sync(0xffffffffu, ready);
-                    const u32 prefix_mask = __ballot_sync(0xffffffffu, ready && is_prefix);
-                    const u32 first_p = prefix_mask ? (u32)(__ffs(prefix_mask) - 1) : 32u;
-                    const u32 need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
-                    if ((ready_mask & need) != need) continue;  // a needed predecessor has not published yet
-                    u32 contrib = (in_range && lane <= first_p) ? u32(s) : 0u;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                    alive_before += contrib;
-                    if (prefix_mask) break;
-                    pos -= 32u;
                 }
-                if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, alive_before + tile_alive));
-            }
+                if (done) break;
+                if (stalled) {
+#if HNB_PROFILE
+                    prof_polls++;
 #endif
-            if (lane == 0) {
-                sh.alive_before = alive_before;
-                sh.tile_alive = tile_alive;
+#if HNB_LOOKBACK_SLEEP_NS > 0
+                    __nanosleep(HNB_LOOKBACK_SLEEP_NS);
+#endif
+                }
             }
+            if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, alive_before + tile_alive));
         }
-        __syncthreads();
-        const u32 alive_before = sh.alive_before;
-
-        // 6) compact: survivors into the write list, the dead onto the dead stack (:148-166)
-#pragma unroll
-        for (int k = 0; k < HNB_TILE_K; ++k) {
-            if (valid[k]) {
-                const u32 row = row0 + k * HNB_BLOCK + tid;
-                // number of surviving rows before `row` in this instance
-                const u32 alive_rank = alive_before + sh.warp_alive[k * HNB_WARPS + warp] + rank[k];
-                if (alive[k]) {
-                    write_col[alive_rank] = pidx[k];
-                } else {
-#if HNB_RELAXED_ORDER
-                    const u32 alive_index = atomicSub(&md->alive_count, 1u) - 1u;
-                    P.slab.dead_index[base_particle + alive_index] = base_particle + pidx[k];
-                    atomicAdd(&md->max_spawn, 1u);
-#else
-                    // `row - alive_rank` dead rows precede this one: serial-order value of
-                    // atomicSub(alive_count,1)-1 given alive_count == max_update at pass start.
-                    const u32 alive_index = max_update - 1u - (row - alive_rank);
-                    P.slab.dead_index[base_particle + alive_index] = base_particle + pidx[k];
 #endif
+
+        HNB_PROF_MARK(prof_lookback)
+        // Request the next tile now: pass 2 below never waits on anybody, so its duration hides the
+        // atomic's round trip. (Requesting it any earlier would park a taken-but-unstarted tile behind
+        // this warp's look-back wait, and later tiles wait for that tile's aggregate: a convoy.)
+        u32 next_tile = 0u;
+        if (lane == 0) next_tile = atomicAdd(P.ticket, 1u);
+
+        // ---- pass 2: compact. Survivors go to the write list, the dead onto the dead stack (:148-166).
+        //      The alive-list entries come back from the per-warp shared-memory stash.
+        {
+            u32 alive_rank_base = alive_before;
+#pragma unroll 4
+            for (u32 jk = 0; jk < chunks * HNB_TILE_K; ++jk) {
+                const u32 row = row0 + jk * 32u + lane;
+                const u32 ballot = survivors[jk];
+                if (row < max_update) {
+                    const u32 pidx = pidx_stash[jk][lane];
+                    // number of surviving rows before `row` in this instance
+                    const u32 alive_rank = alive_rank_base + __popc(ballot & hnb_lanemask_lt());
+                    if ((ballot >> lane) & 1u) {
+                        write_col[alive_rank] = pidx;
+                    } else {
+#if HNB_RELAXED_ORDER
+                        const u32 alive_index = atomicSub(&md->alive_count, 1u) - 1u;
+                        P.slab.dead_index[base_particle + alive_index] = base_particle + pidx;
+                        atomicAdd(&md->max_spawn, 1u);
+#else
+                        // `row - alive_rank` dead rows precede this one: serial-order value of
+                        // atomicSub(alive_count,1)-1 given alive_count == max_update at pass start.
+                        const u32 alive_index = max_update - 1u - (row - alive_rank);
+                        P.slab.dead_index[base_particle + alive_index] = base_particle + pidx;
+#endif
+                    }
                 }
+                alive_rank_base += __popc(ballot);
             }
         }
 #if !HNB_RELAXED_ORDER
-        // 7) the last tile of the instance publishes the totals (replaces the per-particle atomics on
-        //    instance_count / alive_count / max_spawn)
-        if (tid == 0 && row0 + HNB_TILE >= max_update) {
-            const u32 alive_total = alive_before + sh.tile_alive;
+        // the last tile of the instance publishes the totals (replaces the per-particle atomics on
+        // instance_count / alive_count / max_spawn)
+        if (lane == 0 && tile + 1u == inst_end_tile) {
+            const u32 alive_total = alive_before + tile_alive;
             const u32 dead_total = max_update - alive_total;
-            P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * md->indirect_render_index + 1u] = alive_total;
+            P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * render_index + 1u] = alive_total;
             md->alive_count = md->alive_count - dead_total;
             md->max_spawn = md->max_spawn + dead_total;
         }
 #endif
+        tile = __shfl_sync(0xffffffffu, next_tile, 0);
+#if HNB_PROFILE
+        prof_tiles++;
+        HNB_PROF_MARK(prof_pass2)
+#endif
     }
+#if HNB_PROFILE
+    if (lane == 0 && P.debug) {
+        atomicAdd(&P.debug[0], (unsigned long long)prof_pass1);
+        atomicAdd(&P.debug[1], (unsigned long long)prof_lookback);
+        atomicAdd(&P.debug[2], (unsigned long long)prof_pass2);
+        atomicAdd(&P.debug[3], (unsigned long long)prof_polls);
+        atomicAdd(&P.debug[4], (unsigned long long)prof_tiles);
+        atomicAdd(&P.debug[5], 1ull);  // warps
+        atomicMax(&P.debug[6], (unsigned long long)(clock64() - prof_start));  // longest-lived warp (cycles)
+    }
+#endif
 }
 
 }  // namespace hnb

@@ -251,6 +251,19 @@ __global__ void k_checksum(PlaneSet planes, u32 first, u32 count, u32 stride_wor
     if ((threadIdx.x & 31u) == 0) atomicAdd((unsigned long long*)out, (unsigned long long)acc);
 }
 
+// Effective SM clock: cycles elapsed on one SM over ~`window_ns` of the global timer.
+__global__ void k_measure_sm_clock(u64* out, u64 window_ns) {
+    u64 t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < window_ns);
+    const long long c1 = clock64();
+    out[0] = u64(c1 - c0);
+    out[1] = t1 - t0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-callable launchers (declared in hnb_static_kernels.h)
 // ---------------------------------------------------------------------------------------------
@@ -307,6 +320,10 @@ cudaError_t launch_indirect_deinterleave(const u32* rows3, u32* ping, u32* pong,
 cudaError_t launch_fill_c5(void* pos_age, void* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed, f32 lo, f32 hi, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
     k_fill_c5<<<blocks_for(count, 256), 256, 0, st>>>((float4*)pos_age, (float4*)vel_life, ping, pong, first, count, seed, lo, hi);
+    return cudaGetLastError();
+}
+cudaError_t launch_measure_sm_clock(u64* out2, u64 window_ns, cudaStream_t st) {
+    k_measure_sm_clock<<<1, 1, 0, st>>>(out2, window_ns);
     return cudaGetLastError();
 }
 cudaError_t launch_checksum(const PlaneSet& planes, u32 first, u32 count, u32 stride_words, u64* out, cudaStream_t st) {

@@ -95,6 +95,9 @@ struct BatchParams {
     u32 emit_events_capacity[HNB_MAX_EVENT_BINDINGS];
     u32 init_thread_count;           // ceil64(total_spawn_count): logical init threads of this launch
     u32 properties_stride;           // bytes
+    u32 tile_rows;                   // rows per update tile of this launch (multiple of 32*K, <= 32*K*HNB_MAX_CHUNKS)
+    u32 _pad0;
+    unsigned long long* debug;       // 16 counters, written only by kernels compiled with HNB_PROFILE=1
 };
 
 }  // namespace hnb

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -164,6 +165,8 @@ struct hnb_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
     double update_ms = 0.0;
     uint64_t update_launches = 0;
+    uint32_t tile_chunks_override = 0;  // HNB_TILE_CHUNKS env: fixed sub-tile count per tile (tuning)
+    unsigned long long* d_debug = nullptr;  // 16 diagnostic counters (HNB_PROFILE kernels)
 
     hnb::FrameHeader* header() { return reinterpret_cast<hnb::FrameHeader*>(h_arena); }
     template <typename T> T* h_at(size_t off) { return reinterpret_cast<T*>(h_arena + off); }
@@ -400,7 +403,18 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     const hnb_batch_info& bi = c->h_at<hnb_batch_info>(c->lay.off_batch_infos)[lp.batch];
     if (uint64_t(bi.prefix_sum_offset) + bi.prefix_sum_count > c->E || uint64_t(bi.spawner_base) + bi.prefix_sum_count > c->E)
         fail(HNB_ERR_OUT_OF_RANGE, "batch references instances outside the uploaded spawner table");
-    const uint32_t tile = 256u * lp.fx->tile_k;
+    // Rows per warp tile: 32 lanes x K rows per lane x chunks. Larger tiles shorten the look-back chain
+    // and amortise per-tile work; the chunk count is picked so that the persistent grid still gets at
+    // least ~2 tiles per resident warp (small slabs get small tiles).
+    const uint32_t sub_tile = 32u * lp.fx->tile_k;
+    const uint32_t total_warps = uint32_t(lp.fx->km->update_blocks_per_sm) * uint32_t(c->sm_count) * 8u;
+    uint32_t chunks = c->tile_chunks_override;
+    if (chunks == 0) {
+        chunks = 1;
+        while (chunks < 8 && uint64_t(lp.slab->capacity) >= uint64_t(2) * total_warps * sub_tile * (chunks * 2)) chunks *= 2;
+    }
+    chunks = std::max(1u, std::min(chunks, kMaxRowsPerLane / lp.fx->tile_k));
+    const uint32_t tile = sub_tile * chunks;
     c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile;
 
     const bool consume = (lp.fx->flags & HNB_EFFECT_CONSUME_GPU_SPAWN_EVENTS) != 0;
@@ -453,9 +467,11 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
         }
     }
     P.init_thread_count = init_threads;
+    P.debug = c->d_debug;
+    P.tile_rows = tile;
     lp.init_blocks = ceil_div(init_threads, 256);
     uint32_t max_tiles = lp.slab->capacity / tile + bi.prefix_sum_count + 1;
-    lp.update_blocks = std::min<uint32_t>(max_tiles, uint32_t(lp.fx->km->update_blocks_per_sm) * uint32_t(c->sm_count));
+    lp.update_blocks = std::min<uint32_t>(ceil_div(max_tiles, 8), uint32_t(lp.fx->km->update_blocks_per_sm) * uint32_t(c->sm_count));
     if (lp.update_blocks == 0) lp.update_blocks = 1;
     if (lp.fx->props_size && !lp.fx->d_props) fail(HNB_ERR_NOT_READY, "effect uses properties but none were uploaded");
     return lp;
@@ -544,7 +560,10 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
             CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
             c->own_stream = true;
         }
+        if (const char* e = getenv("HNB_TILE_CHUNKS")) c->tile_chunks_override = (uint32_t)atoi(e);
         ensure_arena(c.get(), 0, 0);
+        CUDA_CHECK(cudaMalloc((void**)&c->d_debug, 16 * 8));
+        CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
         *out = c.release();
     });
 }
@@ -567,6 +586,7 @@ void hnb_ctx_destroy(hnb_ctx* c) {
     if (c->h_arena) cudaFreeHost(c->h_arena);
     if (c->d_arena) cudaFree(c->d_arena);
     cudaFree(c->d_metadata); cudaFree(c->d_draw_args); cudaFree(c->d_child_infos);
+    cudaFree(c->d_debug);
     cudaFree(c->d_tile_prefix); cudaFree(c->d_dispatch_args); cudaFree(c->d_batch_tiles); cudaFree(c->d_tickets);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -962,7 +982,7 @@ int32_t hnb_pass_prefix_sum(hnb_ctx* c) {
         c->header()->num_batches = c->B;
         // default tile size for batches never planned by a launch
         uint32_t* ts = c->h_at<uint32_t>(c->lay.off_tile_size);
-        for (uint32_t b = 0; b < c->B; ++b) if (ts[b] == 0) ts[b] = 1024;
+        for (uint32_t b = 0; b < c->B; ++b) if (ts[b] == 0) ts[b] = 128;
         flush_arena(c, false);
         CUDA_CHECK(hnb::launch_prefix_sum(static_tables(c), c->B, c->stream));
         c->launches += c->B ? 1 : 0;
@@ -1060,6 +1080,28 @@ void* hnb_host_alloc(size_t bytes) {
 }
 void hnb_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int32_t hnb_ctx_read_debug(hnb_ctx* c, uint64_t* out16, int32_t clear) {
+    return guarded([&] {
+        CUDA_CHECK(cudaMemcpyAsync(out16, c->d_debug, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (clear) CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_ctx_measure_sm_mhz(hnb_ctx* c, uint32_t window_us, double* mhz) {
+    return guarded([&] {
+        unsigned long long* d = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&d, 16));
+        CUDA_CHECK(hnb::launch_measure_sm_clock(d, (unsigned long long)window_us * 1000ull, c->stream));
+        c->launches++;
+        unsigned long long h[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+        if (mhz) *mhz = h[1] ? double(h[0]) / (double(h[1]) * 1e-3) : 0.0;
+    });
 }
 
 int32_t hnb_ctx_enable_kernel_timing(hnb_ctx* c, int32_t enabled) {

@@ -7,6 +7,7 @@
 #include "effect_source.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <stdexcept>
@@ -193,6 +194,20 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
     o << "// ---- generated by hanabi_b200 for effect '" << nz(d.name) << "' ----\n";
     o << kSrcWgsl << "\n" << kSrcTables << "\n";
     o << "namespace hnb {\n";
+    // Tuning hook for experiments: HNB_DEFINES="NAME=VALUE;NAME2=VALUE2" prepends #defines that the
+    // kernel templates honour through #ifndef guards (tile shape, look-back back-off, cache hints).
+    if (const char* env = getenv("HNB_DEFINES")) {
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t end = e.find(';', pos);
+            if (end == std::string::npos) end = e.size();
+            std::string item = e.substr(pos, end - pos);
+            size_t eq = item.find('=');
+            if (!item.empty()) o << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
+            pos = end + 1;
+        }
+    }
     o << "#define HNB_NUM_PLANES " << planes.size() << "\n";
     o << "#define HNB_TILE_K " << choose_tile_k(d) << "\n";
     o << "#define HNB_HAS_PROPERTIES " << (d.properties_size ? 1 : 0) << "\n";

@@ -170,6 +170,16 @@ class Context:
     def launch_count(self) -> int:
         return lib.hnb_ctx_launch_count(self._h)
 
+    def read_debug(self, clear: bool = True) -> list[int]:
+        out = (C.c_uint64 * 16)()
+        check(lib.hnb_ctx_read_debug(self._h, out, int(clear)))
+        return list(out)
+
+    def measure_sm_mhz(self, window_us: int = 50) -> float:
+        out = C.c_double(0)
+        check(lib.hnb_ctx_measure_sm_mhz(self._h, window_us, C.byref(out)))
+        return out.value
+
     def enable_kernel_timing(self, on: bool = True) -> None:
         check(lib.hnb_ctx_enable_kernel_timing(self._h, int(on)))
 

@@ -348,6 +348,12 @@ HNB_API void hnb_host_free(void* p);
 
 /** Time (ms) spent in the update kernels of the last `n` hnb_simulate calls is measured by CUDA
  *  events recorded around each update launch when enabled (bench roofline leg). */
+/** Effective SM clock (MHz) measured on the device over `window_us` microseconds (clock64 vs globaltimer),
+ *  enqueued on the context stream; blocks until done. Diagnostic for benchmarks. */
+/** Read (and optionally clear) the 16 diagnostic counters written by kernels compiled with HNB_PROFILE=1
+ *  (per-phase cycle totals of hnb_update; see hnb_particle_kernels.cuh). */
+HNB_API int32_t hnb_ctx_read_debug(hnb_ctx* ctx, uint64_t* out16, int32_t clear);
+HNB_API int32_t hnb_ctx_measure_sm_mhz(hnb_ctx* ctx, uint32_t window_us, double* mhz);
 HNB_API int32_t hnb_ctx_enable_kernel_timing(hnb_ctx* ctx, int32_t enabled);
 HNB_API int32_t hnb_ctx_kernel_time_ms(hnb_ctx* ctx, double* update_ms_total, uint64_t* update_launches);
 
