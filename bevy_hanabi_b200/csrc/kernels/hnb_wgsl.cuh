@@ -66,6 +66,14 @@ typedef vec2<u32> vec2u; typedef vec3<u32> vec3u; typedef vec4<u32> vec4u;
 template <typename T> HNB_DI vec3<T> xyz(const vec4<T>& v) { return vec3<T>(v.x, v.y, v.z); }
 template <typename T> HNB_DI vec2<T> xy(const vec4<T>& v) { return vec2<T>(v.x, v.y); }
 template <typename T> HNB_DI vec2<T> xy(const vec3<T>& v) { return vec2<T>(v.x, v.y); }
+template <typename T> HNB_DI vec3<T> xyz(const vec3<T>& v) { return v; }
+
+// WGSL's type-inferring constructors `vec2(a, b)`, `vec3(a, b, c)`, `vec4(xyz, w)` (BinaryOperator::Vec2 /
+// Vec4XyzW, TernaryOperator::Vec3 in src/graph/expr.rs): C++ cannot overload a class template's name with
+// a function, so generated code calls these instead.
+template <typename T> HNB_DI vec2<T> make_vec2(T x, T y) { return vec2<T>(x, y); }
+template <typename T> HNB_DI vec3<T> make_vec3(T x, T y, T z) { return vec3<T>(x, y, z); }
+template <typename T> HNB_DI vec4<T> make_vec4(const vec3<T>& xyz_, T w) { return vec4<T>(xyz_, w); }
 
 // Apply a scalar function / operator component-wise.
 #define HNB_VEC_UNARY(NAME, EXPR)                                                                     \
@@ -260,6 +268,7 @@ HNB_DI mat4x4f hnb_transform_from_rows(const f32* r0, const f32* r1, const f32* 
 // reference; generated code reaches it through the frand*() macros defined by the kernel template.
 // ---------------------------------------------------------------------------------------------
 #define HNB_TAU 6.283185307179586476925286766559f
+constexpr f32 tau = HNB_TAU;  // vfx_common.wgsl:262
 
 HNB_DI u32 pcg_hash(u32 input) {
     u32 state = input * 747796405u + 2891336453u;

@@ -530,6 +530,8 @@ void check_coverage(hnb_ctx* c, const std::vector<LaunchPlan>& plans) {
 extern "C" {
 
 const char* hnb_last_error(void) { return g_last_error.c_str(); }
+// shared with graph/graph_cabi.cpp (not part of the public ABI: hidden visibility)
+__attribute__((visibility("hidden"))) void hnb_set_last_error_(const char* msg) { g_last_error = msg ? msg : ""; }
 const char* hnb_version(void) { return "hanabi_b200 0.1.0 (sm_100a)"; }
 
 int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx** out) {

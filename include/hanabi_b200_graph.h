@@ -1,0 +1,124 @@
+/*
+ * hanabi_b200_graph.h — Level-2 C ABI: effect authoring and lowering to CUDA C.
+ *
+ * Replaces, for the simulation passes, the reference's src/graph (Module / Expr), src/modifier,
+ * src/attributes.rs (ParticleLayout), src/properties.rs (PropertyLayout) and
+ * EffectShaderSources::generate (src/lib.rs:805-1335). It exists in this library because the Rust
+ * toolchain is absent from the build image; the result of hnb_asset_generate() is an hnb_effect_desc
+ * that Level 1 (hanabi_b200.h, hnb_effect_compile) consumes. Pure CPU: no function here needs a GPU.
+ *
+ * Expression and property handles are 1-based; 0 means "invalid" and is returned on error together
+ * with a message in hnb_last_error().
+ */
+#ifndef HANABI_B200_GRAPH_H
+#define HANABI_B200_GRAPH_H
+
+#include "hanabi_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hnb_module hnb_module; /* Module, reference src/graph/expr.rs:337 */
+typedef struct hnb_asset hnb_asset;   /* EffectAsset, reference src/asset.rs:272 */
+typedef uint32_t hnb_expr;
+typedef uint32_t hnb_prop;
+
+/* BuiltInOperator (expr.rs:1580) */
+enum { HNB_BUILTIN_TIME = 0, HNB_BUILTIN_DELTA_TIME, HNB_BUILTIN_VIRTUAL_TIME, HNB_BUILTIN_VIRTUAL_DELTA_TIME, HNB_BUILTIN_REAL_TIME,
+       HNB_BUILTIN_REAL_DELTA_TIME, HNB_BUILTIN_RAND, HNB_BUILTIN_ALPHA_CUTOFF, HNB_BUILTIN_IS_ALIVE };
+/* UnaryOperator (expr.rs:1833), same order */
+enum { HNB_UN_ABS = 0, HNB_UN_ACOS, HNB_UN_ASIN, HNB_UN_ATAN, HNB_UN_ALL, HNB_UN_ANY, HNB_UN_CEIL, HNB_UN_COS, HNB_UN_EXP, HNB_UN_EXP2,
+       HNB_UN_FLOOR, HNB_UN_FRACT, HNB_UN_INV_SQRT, HNB_UN_LENGTH, HNB_UN_LOG, HNB_UN_LOG2, HNB_UN_NORMALIZE, HNB_UN_PACK4X8SNORM,
+       HNB_UN_PACK4X8UNORM, HNB_UN_ROUND, HNB_UN_SATURATE, HNB_UN_SIGN, HNB_UN_SIN, HNB_UN_SQRT, HNB_UN_TAN, HNB_UN_UNPACK4X8SNORM,
+       HNB_UN_UNPACK4X8UNORM, HNB_UN_W, HNB_UN_X, HNB_UN_Y, HNB_UN_Z };
+/* BinaryOperator (expr.rs:2079), same order */
+enum { HNB_BIN_ADD = 0, HNB_BIN_ATAN2, HNB_BIN_CROSS, HNB_BIN_DISTANCE, HNB_BIN_DIV, HNB_BIN_DOT, HNB_BIN_GT, HNB_BIN_GE, HNB_BIN_LT,
+       HNB_BIN_LE, HNB_BIN_MAX, HNB_BIN_MIN, HNB_BIN_MUL, HNB_BIN_REM, HNB_BIN_STEP, HNB_BIN_SUB, HNB_BIN_UNIFORM_RAND,
+       HNB_BIN_NORMAL_RAND, HNB_BIN_VEC2, HNB_BIN_VEC4_XYZ_W };
+/* TernaryOperator (expr.rs:2306) */
+enum { HNB_TER_MIX = 0, HNB_TER_CLAMP, HNB_TER_SMOOTHSTEP, HNB_TER_VEC3 };
+
+/* ---- Module --------------------------------------------------------------------------------- */
+HNB_API hnb_module* hnb_module_create(void);
+HNB_API void hnb_module_destroy(hnb_module* m);
+/** Literal of `value_type` (hnb_value_type); `words` holds its 32-bit lanes (bools: 0 / non-zero). */
+HNB_API hnb_expr hnb_module_lit(hnb_module* m, uint32_t value_type, const uint32_t* words);
+HNB_API hnb_expr hnb_module_attr(hnb_module* m, const char* attribute_name);
+HNB_API hnb_expr hnb_module_parent_attr(hnb_module* m, const char* attribute_name);
+HNB_API hnb_prop hnb_module_add_property(hnb_module* m, const char* name, uint32_t value_type, const uint32_t* default_words);
+HNB_API hnb_expr hnb_module_prop(hnb_module* m, hnb_prop property);
+/** `rand_value_type` is only read for HNB_BUILTIN_RAND. */
+HNB_API hnb_expr hnb_module_builtin(hnb_module* m, uint32_t op, uint32_t rand_value_type);
+HNB_API hnb_expr hnb_module_unary(hnb_module* m, uint32_t op, hnb_expr e);
+HNB_API hnb_expr hnb_module_binary(hnb_module* m, uint32_t op, hnb_expr left, hnb_expr right);
+HNB_API hnb_expr hnb_module_ternary(hnb_module* m, uint32_t op, hnb_expr a, hnb_expr b, hnb_expr c);
+HNB_API hnb_expr hnb_module_cast(hnb_module* m, hnb_expr e, uint32_t target_value_type);
+HNB_API int32_t hnb_module_is_const(const hnb_module* m, hnb_expr e);
+HNB_API int32_t hnb_module_has_side_effect(const hnb_module* m, hnb_expr e);
+/**
+ * Expr::eval in a fresh ShaderWriter of the given context (1 = init, 2 = update) with the module's
+ * own property layout and a layout made of every attribute: writes the expression text to `out`
+ * and the hoisted side-effect statements to `stmts` (either may be NULL). ≙ the reference's
+ * expression-text unit tests (src/graph/expr.rs:4219-4300).
+ */
+HNB_API int32_t hnb_module_eval(const hnb_module* m, hnb_expr e, uint32_t context, char* out, size_t out_cap, char* stmts, size_t stmts_cap);
+
+/* ---- Attributes / layouts ------------------------------------------------------------------- */
+HNB_API uint32_t hnb_attribute_count(void);
+/** Name / value type / default value lanes of built-in attribute `index` (reference attributes.rs:1338-1378 order). */
+HNB_API int32_t hnb_attribute_info(uint32_t index, const char** name, uint32_t* value_type, uint32_t default_words[4]);
+/** ParticleLayoutBuilder::build for a set of attribute names. `out` receives up to `cap` fields in offset order
+ *  (padding fields are named pad0..pad4 and included); *n = field count, *size = record bytes, *align. */
+HNB_API int32_t hnb_particle_layout_build(const char* const* attribute_names, uint32_t n_names, hnb_attr_layout* out, uint32_t cap,
+                                          uint32_t* n, uint32_t* size, uint32_t* align);
+/** f32 literal formatting (ToWgslString for f32, reference src/lib.rs:264-269, plus the C suffix). */
+HNB_API int32_t hnb_format_f32(float value, char* out, size_t cap);
+
+/* ---- Asset ---------------------------------------------------------------------------------- */
+enum { HNB_CONTEXT_INIT = 1, HNB_CONTEXT_UPDATE = 2 };
+/* Modifier kinds; operand order = field order of the reference struct (optional operands may be 0). */
+enum {
+    HNB_MOD_ACCEL = 1,             /* exprs: accel */
+    HNB_MOD_RADIAL_ACCEL,          /* origin, accel */
+    HNB_MOD_TANGENT_ACCEL,         /* origin, axis, accel */
+    HNB_MOD_CONFORM_TO_SPHERE,     /* origin, radius, influence_dist, attraction_accel, max_attraction_speed, [shell_half_thickness], [sticky_factor] */
+    HNB_MOD_LINEAR_DRAG,           /* drag */
+    HNB_MOD_KILL_SPHERE,           /* center, sqr_radius; params: kill_inside */
+    HNB_MOD_KILL_AABB,             /* center, half_size; params: kill_inside */
+    HNB_MOD_SET_ATTRIBUTE,         /* value; params: attribute index */
+    HNB_MOD_INHERIT_ATTRIBUTE,     /* params: attribute index */
+    HNB_MOD_SET_POSITION_CIRCLE,   /* center, axis, radius; params: dimension (0 surface, 1 volume) */
+    HNB_MOD_SET_POSITION_SPHERE,   /* center, radius; params: dimension */
+    HNB_MOD_SET_POSITION_CONE3D,   /* height, base_radius, top_radius; params: dimension */
+    HNB_MOD_SET_VELOCITY_CIRCLE,   /* center, axis, speed */
+    HNB_MOD_SET_VELOCITY_SPHERE,   /* center, speed */
+    HNB_MOD_SET_VELOCITY_TANGENT,  /* origin, axis, speed */
+    HNB_MOD_EMIT_SPAWN_EVENT       /* count; params: condition (0 always, 1 on die), child_index */
+};
+/** The module is copied into the asset (EffectAsset::new takes ownership of the Module). */
+HNB_API hnb_asset* hnb_asset_create(const char* name, uint32_t capacity, const hnb_module* module);
+HNB_API void hnb_asset_destroy(hnb_asset* a);
+HNB_API int32_t hnb_asset_set_simulation_space(hnb_asset* a, uint32_t local);        /* SimulationSpace */
+HNB_API int32_t hnb_asset_set_motion_integration(hnb_asset* a, uint32_t mode);       /* 0 none, 1 pre, 2 post */
+HNB_API int32_t hnb_asset_add_modifier(hnb_asset* a, uint32_t context, uint32_t kind, const hnb_expr* exprs, uint32_t n_exprs,
+                                       const uint32_t* params, uint32_t n_params);
+/** EffectAsset::particle_layout (asset.rs:605-626); same output convention as hnb_particle_layout_build. */
+HNB_API int32_t hnb_asset_particle_layout(const hnb_asset* a, hnb_attr_layout* out, uint32_t cap, uint32_t* n, uint32_t* size, uint32_t* align);
+/** PropertyLayout of the asset's module: entries in layout order; *size = bytes of one Properties record. */
+HNB_API int32_t hnb_asset_property_layout(const hnb_asset* a, hnb_attr_layout* out, uint32_t cap, uint32_t* n, uint32_t* size);
+/** EffectProperties::serialize: `names[i]` is set to the value lanes `words[i]` (others keep their default). */
+HNB_API int32_t hnb_asset_serialize_properties(const hnb_asset* a, const char* const* names, const uint32_t* const* words, uint32_t n,
+                                               void* blob, uint32_t blob_cap, uint32_t* blob_size);
+
+typedef struct hnb_generated hnb_generated; /* EffectShaderSources for the simulation passes */
+/** EffectShaderSources::generate. `parent` (or NULL) provides the parent particle layout of a GPU-event child. */
+HNB_API int32_t hnb_asset_generate(const hnb_asset* a, const hnb_asset* parent, uint32_t num_event_bindings, hnb_generated** out);
+/** Fill `desc` with pointers into `g` (valid until hnb_generated_destroy). */
+HNB_API int32_t hnb_generated_desc(const hnb_generated* g, hnb_effect_desc* desc);
+HNB_API void hnb_generated_destroy(hnb_generated* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANABI_B200_GRAPH_H */
