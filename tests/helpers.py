@@ -142,7 +142,9 @@ class RefWorld:
 class GpuWorld:
     """The same world on the GPU backend, driven through the C ABI only."""
 
-    def __init__(self, ctx, ref: RefWorld, lowered_effect):
+    def __init__(self, ctx, ref: RefWorld, lowered_effect, property_blobs=None):
+        """`property_blobs`: list (per instance) of serialized Properties records, uploaded at array index =
+        instance index; the metadata rows of `ref` must carry the same properties_array_index."""
         import bevy_hanabi_b200._native as N
         from bevy_hanabi_b200 import runtime as R
         self.N, self.R = N, R
@@ -151,6 +153,8 @@ class GpuWorld:
         self.stride = ref.stride_words * 4
         self.slab = ctx.slab_create(ref.slab_rows, self.stride)
         self.effect = ctx.effect_compile(lowered_effect)
+        for i, blob in enumerate(property_blobs or []):
+            ctx.upload_properties(self.effect, i, blob)
         ctx.slab_upload_aos(self.slab, 0, ref.particles)
         ctx.slab_upload_indirect(self.slab, 0, ref.indirect)
         for i in range(len(ref.instances)):

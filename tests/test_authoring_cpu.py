@@ -1,0 +1,371 @@
+"""CPU tests of the authoring / code-generation layer (no GPU): the counterpart of the reference's pure-CPU
+unit tests and of its naga "the generated shader parses" validation tests:
+
+  literal formatting        src/lib.rs:1925-1990
+  expression text           src/graph/expr.rs:4219-4300 (same structure; CUDA surface syntax)
+  particle layout packing   src/attributes.rs:2379-2521
+  property layout           src/properties.rs:1010-1165, :1395-1422
+  modifier validity         src/modifier/mod.rs:1066-1286 — here every modifier's generated translation
+                            unit is compiled for sm_100a by NVRTC
+  generated update body     src/lib.rs:2155-2308 / SURVEY.md Appendix E
+"""
+import re
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from bevy_hanabi_b200 import _native as N
+from bevy_hanabi_b200 import graph as G
+from bevy_hanabi_b200 import runtime as R
+from bevy_hanabi_b200._native import HanabiError
+
+A = G.Attribute
+
+
+# ---- literals -------------------------------------------------------------------------------------
+def test_f32_literal_formatting():
+    assert G.format_f32(1.0) == "1.f"
+    assert G.format_f32(-1.0) == "-1.f"
+    assert G.format_f32(1.5) == "1.5f"
+    assert G.format_f32(0.5) == "0.5f"
+    assert G.format_f32(0.12345678) == "0.123457f"  # 6 digits, like the reference
+    assert G.format_f32(1.0 / 3.0) == "0.333333f"
+    assert G.format_f32(4e-7) == "0.f"               # constants below 5e-7 vanish
+    assert G.format_f32(-9.8) == "-9.8f"
+
+
+def test_vector_literals():
+    m = G.Module()
+    assert m.eval(m.lit(G.Vec2(1., 2.)))[0] == "vec2<f32>(1.f,2.f)"
+    assert m.eval(m.lit(G.Vec3(1., 2., -1.)))[0] == "vec3<f32>(1.f,2.f,-1.f)"
+    assert m.eval(m.lit(G.Vec4(1., 2., -1., 2.)))[0] == "vec4<f32>(1.f,2.f,-1.f,2.f)"
+    assert m.eval(m.lit(G.U32(7)))[0] == "7u"
+    assert m.eval(m.lit(G.I32(-3)))[0] == "-3"
+    assert m.eval(m.lit(True))[0] == "true"
+    assert m.eval(m.lit(G.UVec(1, 2, 3)))[0] == "vec3<u32>(1u,2u,3u)"
+    assert m.eval(m.lit(G.IVec(1, -2)))[0] == "vec2<i32>(1,-2)"
+    assert m.eval(m.lit((True, False, True)))[0] == "vec3<bool>(true,false,true)"
+
+
+# ---- expressions ----------------------------------------------------------------------------------
+def test_writer_expression_text():
+    w = G.ExprWriter()
+    my_prop = w.add_property("my_prop", 3.0)
+    x = w.lit(3.).abs().max(w.attr(A.POSITION) * w.lit(2.)) + w.lit(-4.).min(w.prop(my_prop))
+    s, stmts = w.finish().eval(x.expr())
+    assert s == "(max(abs(3.f), (particle.position) * (2.f))) + (min(-4.f, properties[properties_array_index].my_prop))"
+    assert stmts == ""
+
+
+def test_binary_operator_formatting():
+    m = G.Module()
+    x = m.attr(A.POSITION)
+    y = m.lit(G.Vec3(1., 1., 1.))
+    for op, sym in [("add", "+"), ("sub", "-"), ("mul", "*"), ("div", "/"), ("lt", "<"), ("le", "<="), ("gt", ">"), ("ge", ">=")]:
+        assert m.eval(m.binary(op, x, y))[0] == f"(particle.position) {sym} (vec3<f32>(1.f,1.f,1.f))"
+    # `%` is WGSL's truncated remainder, also on floats: a function in C
+    assert m.eval(m.rem(x, y))[0] == "hnb_rem(particle.position, vec3<f32>(1.f,1.f,1.f))"
+    for op in ["max", "min", "dot", "cross", "distance", "step", "atan2"]:
+        assert m.eval(m.binary(op, x, y))[0] == f"{op}(particle.position, vec3<f32>(1.f,1.f,1.f))"
+
+
+def test_unary_ternary_cast_text():
+    m = G.Module()
+    x = m.attr(A.POSITION)
+    assert m.eval(m.normalize(x))[0] == "normalize(particle.position)"
+    assert m.eval(m.inverse_sqrt(m.lit(4.)))[0] == "inverseSqrt(4.f)"
+    assert m.eval(m.x(x))[0] == "particle.position.x"
+    a, b, c = m.lit(1.), m.lit(2.), m.lit(0.5)
+    assert m.eval(m.mix(a, b, c))[0] == "mix(1.f, 2.f, 0.5f)"
+    assert m.eval(m.clamp(a, b, c))[0] == "clamp(1.f, 2.f, 0.5f)"
+    assert m.eval(m.smoothstep(a, b, c))[0] == "smoothstep(1.f, 2.f, 0.5f)"
+    assert m.eval(m.vec3(a, b, c))[0] == "make_vec3(1.f, 2.f, 0.5f)"
+    assert m.eval(m.vec2(a, b))[0] == "make_vec2(1.f, 2.f)"
+    assert m.eval(m.vec4_xyz_w(x, a))[0] == "make_vec4(particle.position, 1.f)"
+    assert m.eval(m.cast(a, G.VEC3))[0] == "vec3<f32>(1.f)"
+    assert m.eval(m.cast(a, G.UINT))[0] == "u32(1.f)"
+    with pytest.raises(HanabiError):  # vector -> scalar is not a valid cast (expr.rs:1468-1490)
+        m.cast(x, G.FLOAT)
+
+
+def test_fluent_operand_order():
+    """x.step(edge) emits step(edge, x); x.smoothstep(lo, hi) emits smoothstep(lo, hi, x)."""
+    w = G.ExprWriter()
+    x = w.attr(A.AGE)
+    m = w.module
+    assert m.eval(x.step(0.5).expr())[0] == "step(0.5f, particle.age)"
+    assert m.eval(x.smoothstep(0., 1.).expr())[0] == "smoothstep(0.f, 1.f, particle.age)"
+    assert m.eval(x.mix(2., 0.25).expr())[0] == "mix(particle.age, 2.f, 0.25f)"
+
+
+def test_builtins_and_pseudo_attributes():
+    m = G.Module()
+    assert m.eval(m.builtin("time"))[0] == "sim_params.time"
+    assert m.eval(m.builtin("delta_time"))[0] == "sim_params.delta_time"
+    assert m.eval(m.builtin("virtual_delta_time"))[0] == "sim_params.virtual_delta_time"
+    assert m.eval(m.builtin("is_alive"))[0] == "is_alive"
+    assert m.eval(m.attr(A.ID))[0] == "particle_index"
+    assert m.eval(m.attr(A.PARTICLE_COUNTER))[0] == "particle_counter"
+    assert m.eval(m.parent_attr(A.POSITION))[0] == "parent_particle.position"
+    assert m.eval(m.parent_attr(A.ID))[0] == "parent_particle_index"
+
+
+def test_side_effect_hoisting():
+    """Rand expressions are hoisted once into a local (expr.rs:1812-1824) and cached per writer."""
+    m = G.Module()
+    r = m.builtin("rand", G.FLOAT)
+    assert m.has_side_effect(r) and not m.is_const(r)
+    e = m.add(m.mul(r, m.lit(2.)), r)
+    s, stmts = m.eval(e)
+    assert stmts == "const auto var0 = frand();\n"
+    assert s == "((var0) * (2.f)) + (var0)"
+    r3 = m.builtin("rand", G.VEC3)
+    assert m.eval(r3) == ("var0", "const auto var0 = frand3();\n")
+    u = m.uniform(m.lit(1.), m.lit(3.))
+    assert m.eval(u) == ("var0", "const auto var0 = rand_uniform_f(1.f, 3.f);\n")
+    uv = m.uniform(m.lit(G.Vec3(0, 0, 0)), m.lit(G.Vec3(1, 1, 1)))
+    assert m.eval(uv)[1] == "const auto var0 = rand_uniform_vec3(vec3<f32>(0.f,0.f,0.f), vec3<f32>(1.f,1.f,1.f));\n"
+    nv = m.normal(m.lit(0.), m.lit(1.))
+    assert m.eval(nv)[1] == "const auto var0 = rand_normal_f(0.f, 1.f);\n"
+    # operands of unknown type (a binary expression) are rejected like in the reference (expr.rs:1162-1198)
+    bad = m.uniform(m.add(m.lit(1.), m.lit(1.)), m.lit(3.))
+    with pytest.raises(HanabiError):
+        m.eval(bad)
+    with pytest.raises(HanabiError):  # mismatched operand types
+        m.eval(m.uniform(m.lit(1.), m.lit(G.Vec3(1, 1, 1))))
+    with pytest.raises(HanabiError):  # irand/urand/brand do not exist in vfx_common.wgsl
+        m.eval(m.builtin("rand", G.UINT))
+    assert m.is_const(m.add(m.lit(1.), m.lit(2.)))
+
+
+def test_invalid_handles():
+    m = G.Module()
+    with pytest.raises(HanabiError):
+        m.unary("abs", 12345)
+    with pytest.raises(HanabiError):
+        m.prop(3)
+
+
+# ---- layouts --------------------------------------------------------------------------------------
+def _lay(names):
+    fields, size, align = G.particle_layout_of(names)
+    return [(f.offset, f.name) for f in fields], size, align
+
+
+def test_particle_layout_goldens():
+    # [3, 1, 3, 2] -> [3 1 3 - 2 - -]   (attributes.rs:2464-2490)
+    fields, size, align = _lay(["f32_0", "f32x3_0", "f32x2_0", "f32x3_1"])
+    assert fields == [(0, "f32x3_0"), (12, "f32_0"), (16, "f32x3_1"), (28, "pad0"), (32, "f32x2_0"), (40, "pad1"), (44, "pad2")]
+    assert (size, align) == (48, 16)
+    # [1, 4, 3, 2, 2, 3] -> [4 3 1 2 2 3 -]   (attributes.rs:2491-2520)
+    fields, size, align = _lay(["f32_0", "f32x4_0", "f32x3_0", "f32x2_0", "f32x2_1", "f32x3_1"])
+    assert fields == [(0, "f32x4_0"), (16, "f32x3_0"), (28, "f32_0"), (32, "f32x2_0"), (40, "f32x2_1"), (48, "f32x3_1"), (60, "pad0")]
+    assert (size, align) == (64, 16)
+    # the default layout documented at attributes.rs:41-58
+    fields, size, align = _lay(["position", "velocity", "age", "lifetime"])
+    assert fields == [(0, "position"), (12, "age"), (16, "velocity"), (28, "lifetime")]
+    assert (size, align) == (32, 16)
+    # duplicates are removed; a lone scalar stays 4-byte aligned
+    assert _lay(["age", "age"]) == ([(0, "age")], 4, 4)
+    assert _lay(["size2"]) == ([(0, "size2")], 8, 8)
+    assert _lay(["position"]) == ([(0, "position"), (12, "pad0")], 16, 16)
+    # firework "trails": + color -> 48-byte stride
+    fields, size, _ = _lay(["position", "velocity", "age", "lifetime", "color"])
+    # scalars pair with the vec3s in alphabetical order: age, color, then lifetime alone + 3 pads
+    assert size == 48 and fields == [(0, "position"), (12, "age"), (16, "velocity"), (28, "color"), (32, "lifetime"),
+                                      (36, "pad0"), (40, "pad1"), (44, "pad2")]
+
+
+def test_attribute_table():
+    assert len(G.ATTRIBUTES) == 39
+    assert A.POSITION.vt == G.VEC3 and A.LIFETIME.default.floats() == [1.0]
+    assert A.COLOR.default.words == (0xFFFFFFFF,) and A.PREV.default.words == (0xFFFFFFFF,)
+    assert A.AXIS_Y.default.floats() == [0.0, 1.0, 0.0] and A.HDR_COLOR.vt == G.VEC4
+    assert A.SPRITE_INDEX.vt == G.INT and A.RIBBON_ID.vt == G.UINT
+    assert [a.name for a in G.ATTRIBUTES[:6]] == ["id", "particle_counter", "position", "velocity", "age", "lifetime"]
+
+
+def _asset_with_props(props):
+    w = G.ExprWriter()
+    for name, v in props:
+        w.add_property(name, v)
+    zero = w.lit(G.Vec3(0, 0, 0))
+    return G.EffectAsset(16, w.finish()).init(G.SetAttributeModifier(A.POSITION, zero))
+
+
+def test_property_layout_goldens():
+    # layout_valid (properties.rs:1010-1050)
+    a = _asset_with_props([("f32", 3.4), ("vec3", G.Vec3(0, 0, 0)), ("vec2", G.Vec2(0, -1)), ("vec4", G.Vec4(0, 1, 0, 0))])
+    fields, size = a.property_layout()
+    assert [(f.offset, f.name) for f in fields] == [(0, "vec4"), (16, "vec3"), (28, "f32"), (32, "vec2")]
+    assert size == 48  # min_binding_size; cpu_size is 40
+    # layout_padding_vec3 (properties.rs:1052-1090, regression #478)
+    a = _asset_with_props([("vec4a", G.Vec4(0, 1, 0, 0)), ("vec3b", G.Vec3(0, 0, 0)), ("vec3c", G.Vec3(1, 1, 1))])
+    fields, size = a.property_layout()
+    assert [(f.offset, f.name) for f in fields] == [(0, "vec4a"), (16, "vec3b"), (32, "vec3c")]
+    assert size == 48
+    # tails: 3/3/2, 3/2, 2/1 (properties.rs layout_tail_*)
+    a = _asset_with_props([("a", G.Vec3(0, 0, 0)), ("b", G.Vec3(0, 0, 0)), ("c", G.Vec2(0, 0))])
+    assert [(f.offset, f.name) for f in a.property_layout()[0]] == [(0, "a"), (16, "b"), (32, "c")]
+    a = _asset_with_props([("a", G.Vec3(0, 0, 0)), ("c", G.Vec2(0, 0))])
+    assert [(f.offset, f.name) for f in a.property_layout()[0]] == [(0, "a"), (16, "c")]
+    a = _asset_with_props([("c", G.Vec2(0, 0)), ("s", 1.0)])
+    assert [(f.offset, f.name) for f in a.property_layout()[0]] == [(0, "c"), (8, "s")]
+
+
+def test_property_serialize():
+    a = _asset_with_props([("f32", 3.4), ("vec3", G.Vec3(1, 2, 3)), ("vec4", G.Vec4(0, 1, 0, 0))])
+    blob = a.serialize_properties({"f32": 7.5})
+    assert len(blob) == 32  # vec4 | vec3 + f32
+    words = struct.unpack("<8f", blob)
+    assert words[0:4] == (0, 1, 0, 0) and words[4:7] == (1, 2, 3) and words[7] == 7.5
+    with pytest.raises(HanabiError):
+        a.serialize_properties({"nope": 1.0})
+
+
+# ---- code generation ------------------------------------------------------------------------------
+def _c5_asset():
+    w = G.ExprWriter()
+    accel, drag, zero = w.lit(G.Vec3(0., -9.8, 0.)), w.lit(0.5), w.lit(G.Vec3(0, 0, 0))
+    return (G.EffectAsset(1024, w.finish(), name="c5")
+            .init(G.SetAttributeModifier(A.POSITION, zero)).init(G.SetAttributeModifier(A.VELOCITY, zero))
+            .init(G.SetAttributeModifier(A.AGE, w.lit(0.))).init(G.SetAttributeModifier(A.LIFETIME, w.lit(1.)))
+            .update(G.AccelModifier(accel)).update(G.LinearDragModifier(drag)))
+
+
+def test_generated_update_body_matches_appendix_e():
+    fx = _c5_asset().generate()
+    assert fx.update_code == ("particle.velocity += (vec3<f32>(0.f,-9.8f,0.f)) * sim_params.delta_time;"
+                              "particle.velocity *= max(0.f, (1.f) - ((0.5f) * (sim_params.delta_time)));\n"
+                              "particle.position += particle.velocity * sim_params.delta_time;\n")
+    assert "particle.age = particle.age + sim_params.delta_time;" in fx.age_code
+    assert "is_alive = particle.age < particle.lifetime;" in fx.age_code
+    assert fx.reap_code == "is_alive = is_alive && (particle.age < particle.lifetime);"
+    assert fx.sim_space_code.strip() == "particle.position += xyz(transform[3]);"
+    assert fx.particle_stride == 32 and [(a.name, a.offset) for a in fx.attrs] == [("position", 0), ("age", 12), ("velocity", 16), ("lifetime", 28)]
+    pre = _c5_asset().with_motion_integration(G.MOTION_PRE_UPDATE).generate().update_code
+    assert pre.startswith("\nparticle.position += particle.velocity * sim_params.delta_time;\n")
+    none = _c5_asset().with_motion_integration(G.MOTION_NONE).generate().update_code
+    assert "particle.position +=" not in none
+    assert _c5_asset().with_simulation_space(G.LOCAL).generate().sim_space_code == ""
+
+
+def test_generate_validation_errors():
+    w = G.ExprWriter()
+    asset = G.EffectAsset(8, w.finish()).init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+    with pytest.raises(HanabiError) as e:  # POSITION is mandatory (lib.rs:836-843)
+        asset.generate()
+    assert "POSITION" in str(e.value)
+    w = G.ExprWriter()
+    with pytest.raises(HanabiError) as e:  # SetAttribute type check (attr.rs:97-113)
+        G.EffectAsset(8, w.finish()).init(G.SetAttributeModifier(A.POSITION, w.lit(1.))).generate()
+    assert "Mismatching expression type" in str(e.value)
+    w = G.ExprWriter()
+    with pytest.raises(HanabiError):  # ID is read-only (attr.rs:80-89)
+        G.EffectAsset(8, w.finish()).init(G.SetAttributeModifier(A.ID, w.lit(G.U32(1))))._native()
+    w = G.ExprWriter()
+    with pytest.raises(HanabiError):  # update-only modifier in the init context
+        G.EffectAsset(8, w.finish()).init(G.AccelModifier(w.lit(G.Vec3(0, 0, 0))))._native()
+
+
+def _all_modifier_assets():
+    """One asset per simulation modifier, operands exercising literals, properties, attributes and rand."""
+    def base(w):
+        return [G.SetAttributeModifier(A.POSITION, w.lit(G.Vec3(0, 0, 0))), G.SetAttributeModifier(A.VELOCITY, w.lit(G.Vec3(0, 1, 0))),
+                G.SetAttributeModifier(A.AGE, w.lit(0.)), G.SetAttributeModifier(A.LIFETIME, w.rand(G.FLOAT) * w.lit(2.) + w.lit(1.))]
+    out = {}
+    def mk(name, init_extra=(), update=()):
+        w = G.ExprWriter()
+        mods_i, mods_u = init_extra(w) if callable(init_extra) else [], update(w) if callable(update) else []
+        a = G.EffectAsset(64, w.module, name=name)
+        for m in base(w) + mods_i:
+            a.init(m)
+        for m in mods_u:
+            a.update(m)
+        out[name] = a
+    c = lambda w: w.lit(G.Vec3(0.5, -1., 2.))
+    mk("accel", update=lambda w: [G.AccelModifier(w.lit(G.Vec3(0, -9.8, 0)))])
+    mk("accel_prop", update=lambda w: [G.AccelModifier(w.prop(w.add_property("g", G.Vec3(0, -3, 0))) * w.time())])
+    mk("radial", update=lambda w: [G.RadialAccelModifier(c(w), w.lit(2.5))])
+    mk("tangent", update=lambda w: [G.TangentAccelModifier(c(w), w.lit(G.Vec3(0, 1, 0)), w.lit(1.5))])
+    mk("conform", update=lambda w: [G.ConformToSphereModifier(c(w), w.lit(1.5), w.lit(10.), w.lit(5.), w.lit(2.))])
+    mk("conform_full", update=lambda w: [G.ConformToSphereModifier(c(w), w.lit(1.5), w.lit(10.), w.lit(5.), w.lit(2.), w.lit(0.2), w.lit(3.))])
+    mk("drag", update=lambda w: [G.LinearDragModifier(w.lit(0.7))])
+    mk("kill_sphere", update=lambda w: [G.KillSphereModifier(c(w), w.lit(4.), False), G.KillSphereModifier(c(w), w.lit(0.01), True)])
+    mk("kill_aabb", update=lambda w: [G.KillAabbModifier(c(w), w.lit(G.Vec3(3, 2, 3)), False), G.KillAabbModifier(c(w), w.lit(G.Vec3(.1, .1, .1)), True)])
+    mk("set_attr_update", update=lambda w: [G.SetAttributeModifier(A.COLOR, w.attr(A.AGE).vec3(w.lit(0.), w.lit(1.)).vec4_xyz_w(w.lit(1.)).pack4x8unorm())])
+    mk("pos_circle", init_extra=lambda w: [G.SetPositionCircleModifier(c(w), w.lit(G.Vec3(0, 0, 1)), w.lit(2.), G.VOLUME),
+                                           G.SetPositionCircleModifier(c(w), w.lit(G.Vec3(0, 1, 0)), w.lit(2.), G.SURFACE)])
+    mk("pos_sphere", init_extra=lambda w: [G.SetPositionSphereModifier(c(w), w.lit(2.), G.VOLUME), G.SetPositionSphereModifier(c(w), w.rand() + w.lit(1.), G.SURFACE)])
+    mk("pos_cone", init_extra=lambda w: [G.SetPositionCone3dModifier(w.lit(3.), w.lit(1.), w.lit(0.2), G.VOLUME)])
+    mk("vel_circle", init_extra=lambda w: [G.SetVelocityCircleModifier(c(w), w.lit(G.Vec3(0, 0, 1)), w.lit(2.))])
+    mk("vel_sphere", init_extra=lambda w: [G.SetVelocitySphereModifier(c(w), w.rand() * w.lit(0.2) + w.lit(0.1))])
+    mk("vel_tangent", init_extra=lambda w: [G.SetVelocityTangentModifier(c(w), w.lit(G.Vec3(0, 0, 1)), w.lit(2.))])
+    mk("emit_events", update=lambda w: [G.EmitSpawnEventModifier(G.ON_DIE, w.lit(G.U32(3)), 0), G.EmitSpawnEventModifier(G.ALWAYS, w.lit(G.U32(1)), 1)])
+    mk("pos_sphere_update", update=lambda w: [G.SetPositionSphereModifier(c(w), w.lit(2.), G.SURFACE), G.SetPositionCone3dModifier(w.lit(3.), w.lit(1.), w.lit(0.2))])
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_all_modifier_assets().keys()))
+def test_every_modifier_compiles_for_sm100a(name):
+    """≙ validate_init / validate_update (modifier/mod.rs:1066-1286): the emitted code must be valid."""
+    asset = _all_modifier_assets()[name]
+    fx = asset.generate(num_event_bindings=2 if name == "emit_events" else 0)
+    src = fx.generate_source()
+    size, log = R.nvrtc_check(src)
+    assert size > 0
+    assert "error" not in log.lower()
+    assert "bytes spill stores" in log and " 0 bytes spill stores" in log
+
+
+def test_child_effect_compiles():
+    """GPU-event child: READ_PARENT_PARTICLE + CONSUME_GPU_SPAWN_EVENTS, InheritAttribute (attr.rs:173-186)."""
+    parent = _all_modifier_assets()["emit_events"]
+    w = G.ExprWriter()
+    child = (G.EffectAsset(256, w.module, name="child")
+             .init(G.InheritAttributeModifier(A.POSITION))
+             .init(G.SetAttributeModifier(A.VELOCITY, w.parent_attr(A.VELOCITY) * w.lit(0.5)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.))).init(G.SetAttributeModifier(A.LIFETIME, w.lit(1.))))
+    fx = child.generate(parent=parent)
+    assert fx.flags & N.EFFECT_READ_PARENT_PARTICLE and fx.flags & N.EFFECT_CONSUME_GPU_SPAWN_EVENTS
+    assert "particle.position = parent_particle.position;" in fx.init_code
+    size, log = R.nvrtc_check(fx.generate_source())
+    assert size > 0
+
+
+def test_generated_source_rejects_bad_layouts():
+    fx = R.LoweredEffect("bad", [R.AttrField("position", N.VEC3, 0), R.AttrField("age", N.FLOAT, 8)], 16)
+    with pytest.raises(HanabiError):  # overlapping fields
+        fx.generate_source()
+    with pytest.raises(HanabiError):
+        R.LoweredEffect("bad", [R.AttrField("position", N.VEC3, 0)], 14).generate_source()
+
+
+# ---- numpy oracle vs C oracle on the same effect (two independent restatements must agree) ----------
+def test_numpy_oracle_equals_c_oracle_on_c5(orc):
+    import ctypes as C
+    from oracle.hanabi_oracle import EffectOracle
+    from tests.helpers import Instance, RefWorld
+    rng = np.random.default_rng(11)
+    def world():
+        w = RefWorld(3000, 8, [Instance(0, 1500, alive=1200, seed=5), Instance(1500, 1500, alive=900, seed=6)])
+        for inst in w.instances:
+            n = inst.alive
+            p = np.zeros((n, 8), dtype=np.float32)
+            p[:, 0:3] = r.uniform(-1, 1, (n, 3)); p[:, 4:7] = r.uniform(-1, 1, (n, 3)); p[:, 7] = r.uniform(0.02, 0.3, n)
+            w.particles[inst.slab_offset:inst.slab_offset + n] = p.view(np.uint32)
+        return w
+    r = np.random.default_rng(11); a = world()
+    r = np.random.default_rng(11); b = world()
+    eo = EffectOracle(_c5_asset())
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    for step in range(15):
+        a.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        eo.frame(b, orc)
+        np.testing.assert_array_equal(a.particles, b.particles, err_msg=f"step {step}")
+        np.testing.assert_array_equal(a.indirect, b.indirect)
+        np.testing.assert_array_equal(a.metadata_rows(), b.metadata_rows())
+        np.testing.assert_array_equal(a.draw, b.draw)
+    assert a.metadata[0].alive_count < 1200

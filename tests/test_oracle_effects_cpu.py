@@ -1,0 +1,72 @@
+"""CPU-only sanity of the numpy oracle on the authored effects used by the GPU parity tests: structural
+invariants of the reference's bookkeeping must hold after every frame."""
+import numpy as np
+import pytest
+
+from bevy_hanabi_b200 import graph as G
+from oracle.hanabi_oracle import EffectOracle, pcg_hash
+from tests import test_gpu_effects as E
+from tests.helpers import Instance, RefWorld
+
+
+def _check_invariants(ref):
+    for i, inst in enumerate(ref.instances):
+        md = ref.metadata[i]
+        base, cap = inst.slab_offset, inst.capacity
+        assert md.alive_count == ref.draw[5 * md.indirect_render_index + 1]           # alive_count == instance_count
+        assert md.max_spawn == cap - md.alive_count
+        alive = ref.indirect[base:base + md.alive_count, md.indirect_write_index].astype(np.int64)
+        dead = ref.indirect[base + md.alive_count:base + cap, 2].astype(np.int64) - base
+        both = np.concatenate([alive, dead])
+        assert sorted(both.tolist()) == list(range(cap)), "alive list + dead stack must partition the instance's slots"
+
+
+@pytest.mark.parametrize("name", ["firework", "force_field"])
+def test_oracle_invariants(orc, name):
+    if name == "firework":
+        asset = E._firework_trails(2048)
+        ref = RefWorld(2048, 12, [Instance(0, 2048, alive=0)], dt=1.0 / 20.0)
+        spawns = lambda f: [700 if f % 12 == 0 else 0]
+        props = None
+    else:
+        asset = E._force_field(4096)
+        _, size, _ = asset.particle_layout()
+        ref = RefWorld(4096, size // 4, [Instance(0, 4096, alive=0, seed=77)])
+        spawns = lambda f: [3000 if f == 0 else 10]
+        props = {0: {"attraction_accel": 18.0, "repulsor_position": G.Vec3(0.25, 0.5, 0.1)}}
+    eo = EffectOracle(asset, props)
+    died = False
+    for f in range(40):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        ref.set_spawns(spawns(f), [int(pcg_hash(np.array([f], dtype=np.uint32))[0])])
+        before = ref.metadata[0].alive_count
+        eo.frame(ref, orc)
+        _check_invariants(ref)
+        died |= ref.metadata[0].alive_count < before + spawns(f)[0]
+    assert ref.metadata[0].particle_counter > 0
+    if name == "firework":
+        assert died, "the scenario must exercise kills and slot recycling"
+
+
+def test_oracle_runs_all_gpu_scenarios_shapes(orc):
+    """Every effect of the GPU parity suite is interpretable by the oracle (catches oracle bugs without a GPU)."""
+    w = G.ExprWriter()
+    axis, center = w.lit(G.Vec3(0., 0., 1.)), w.lit(G.Vec3(0.5, -0.25, 0.))
+    A = G.Attribute
+    asset = (G.EffectAsset(500, w.module, simulation_space=G.LOCAL)
+             .init(G.SetPositionCircleModifier(center, axis, w.lit(2.), G.VOLUME))
+             .init(G.SetVelocityTangentModifier(center, axis, w.lit(1.5)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.))).init(G.SetAttributeModifier(A.LIFETIME, w.lit(5.)))
+             .update(G.RadialAccelModifier(center, w.lit(-0.5))).update(G.TangentAccelModifier(center, axis, w.lit(0.25))))
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(500, size // 4, [Instance(0, 500, alive=0, seed=3)])
+    eo = EffectOracle(asset)
+    for f in range(3):
+        ref.set_spawns([200])
+        eo.frame(ref, orc)
+        _check_invariants(ref)
+    pos = ref.particles[:400, 0:3].view(np.float32)
+    assert np.all(np.isfinite(pos))
+    # circle of radius 2 around `center` in the z = 0 plane
+    d = pos[:, :2] - np.array([0.5, -0.25], dtype=np.float32)
+    assert np.all(np.abs(pos[:, 2]) < 0.2)
