@@ -158,6 +158,46 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T) {
     }
 }
 
+// Tile prefix of ONE batch for a given tile size, from the max_update values already published by the
+// indirect pass. Used by the stand-alone hnb_pass_update(), whose tile size (a property of the compiled
+// effect and of the launch) is unknown to a stand-alone prefix-sum pass.
+__global__ void __launch_bounds__(BK_THREADS) k_tile_prefix(StaticTables T, u32 batch_index, u32 tile) {
+    __shared__ u32 s_warp_t[BK_THREADS / 32];
+    __shared__ u32 s_carry_t;
+    const BatchInfo* bi = &T.batch_infos[batch_index];
+    const u32 offset = bi->prefix_sum_offset, count = bi->prefix_sum_count;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5u;
+    if (tid == 0) s_carry_t = 0u;
+    __syncthreads();
+    for (u32 chunk = 0; chunk < count; chunk += BK_THREADS) {
+        const u32 i = chunk + tid;
+        u32 t = 0u;
+        if (i < count) {
+            const Spawner* sp = &T.spawners[bi->spawner_base + i];
+            t = (T.metadata[sp->effect_metadata_index].max_update + tile - 1u) / tile;
+        }
+        u32 it = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 ut = __shfl_up_sync(0xffffffffu, it, d);
+            if (lane >= d) it += ut;
+        }
+        if (lane == 31) s_warp_t[warp] = it;
+        __syncthreads();
+        u32 wt = 0u;
+        for (u32 w = 0; w < warp; ++w) wt += s_warp_t[w];
+        const u32 carry_t = s_carry_t;
+        if (i < count) T.tile_prefix[offset + i] = carry_t + wt + it - t;
+        __syncthreads();
+        if (tid == BK_THREADS - 1) s_carry_t = carry_t + wt + it;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        T.batch_tiles[batch_index] = s_carry_t;
+        T.tickets[batch_index] = 0u;
+    }
+}
+
 // vfx_utils.wgsl:54-67
 __global__ void k_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
                                      u32 dst_stride, u32 count) {
@@ -278,6 +318,10 @@ cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t
 cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st) {
     if (num_batches == 0) return cudaSuccess;
     k_prefix_sum<<<blocks_for(num_batches, 64), 64, 0, st>>>(T);
+    return cudaGetLastError();
+}
+cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile, cudaStream_t st) {
+    k_tile_prefix<<<1, BK_THREADS, 0, st>>>(T, batch_index, tile);
     return cudaGetLastError();
 }
 cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, cudaStream_t st) {

@@ -35,6 +35,7 @@ struct PlaneSet {
 
 cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t st);
 cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st);
+cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile, cudaStream_t st);
 cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, cudaStream_t st);
 cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
                                       u32 dst_stride, u32 count, cudaStream_t st);

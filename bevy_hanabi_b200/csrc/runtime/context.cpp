@@ -982,10 +982,12 @@ int32_t hnb_pass_prefix_sum(hnb_ctx* c) {
     return guarded([&] {
         ensure_scratch(c);
         c->header()->num_batches = c->B;
-        // default tile size for batches never planned by a launch
+        // The tile prefix written by this stand-alone pass uses a nominal tile size; hnb_pass_update() rebuilds
+        // it for its own launch geometry (k_tile_prefix), so only the reference outputs matter here.
         uint32_t* ts = c->h_at<uint32_t>(c->lay.off_tile_size);
         for (uint32_t b = 0; b < c->B; ++b) if (ts[b] == 0) ts[b] = 128;
         flush_arena(c, false);
+        if (c->B) CUDA_CHECK(cudaMemcpyAsync(c->d_arena + c->lay.off_tile_size, ts, size_t(c->B) * 4, cudaMemcpyHostToDevice, c->stream));
         CUDA_CHECK(hnb::launch_prefix_sum(static_tables(c), c->B, c->stream));
         c->launches += c->B ? 1 : 0;
     });
@@ -998,6 +1000,8 @@ int32_t hnb_pass_update(hnb_ctx* c, const hnb_batch_launch* b) {
         LaunchPlan lp = plan_batch(c, *b, false);
         next_epoch(c);
         flush_arena(c, false);
+        CUDA_CHECK(hnb::launch_tile_prefix(static_tables(c), lp.batch, lp.params.tile_rows, c->stream));
+        c->launches++;
         launch_update(c, lp);
     });
 }

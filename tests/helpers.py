@@ -207,9 +207,10 @@ class GpuWorld:
         return out
 
 
-def assert_world_equal(ref: RefWorld, got: dict, float_words=None, rtol=0.0, what=""):
+def assert_world_equal(ref: RefWorld, got: dict, float_words=None, rtol=0.0, what="", float_attrs=None):
     """Bit-exact comparison of every buffer (integer bookkeeping AND particle words). When `float_words`
-    is given (boolean mask over the AoS words) those words are compared as fp32 within rtol instead."""
+    (boolean mask over the AoS words) and `float_attrs` ([(first_word, count)] of the fp32 attributes) are given,
+    those attributes are compared within rtol (see assert_float_attributes_close) instead."""
     np.testing.assert_array_equal(got["metadata"], ref.metadata_rows(), err_msg=f"{what}: effect metadata")
     np.testing.assert_array_equal(got["draw"], ref.draw, err_msg=f"{what}: draw indirect args")
     np.testing.assert_array_equal(got["prefix"], ref.prefix, err_msg=f"{what}: prefix sums")
@@ -224,6 +225,22 @@ def assert_world_equal(ref: RefWorld, got: dict, float_words=None, rtol=0.0, wha
     else:
         fw = np.asarray(float_words, dtype=bool)
         np.testing.assert_array_equal(got["particles"][:, ~fw], ref.particles[:, ~fw], err_msg=f"{what}: particle integer words")
-        a = got["particles"][:, fw].view(np.float32)
-        b = ref.particles[:, fw].view(np.float32)
-        np.testing.assert_allclose(a, b, rtol=rtol, atol=1e-6, err_msg=f"{what}: particle float words")
+        assert_float_attributes_close(got["particles"], ref.particles, float_attrs, rtol, what)
+
+
+def assert_float_attributes_close(got_words, ref_words, float_attrs, rtol, what=""):
+    """"fp32 attributes within `rtol` relative": the error of each component is measured against the magnitude of
+    the ATTRIBUTE it belongs to (the largest component of that vector in that particle), so that a component that
+    happens to be near zero (cos near pi/2 ...) is not held to an absolute precision fp32 cannot deliver.
+    `float_attrs` = [(first_word, component_count), ...]."""
+    for first, cnt in float_attrs:
+        a = np.ascontiguousarray(got_words[:, first:first + cnt]).view(np.float32)
+        b = np.ascontiguousarray(ref_words[:, first:first + cnt]).view(np.float32)
+        scale = np.max(np.abs(b), axis=1, keepdims=True)
+        err = np.abs(a.astype(np.float64) - b.astype(np.float64))
+        bound = rtol * scale.astype(np.float64) + 1e-7
+        bad = ~(err <= bound) & ~(np.isnan(a) & np.isnan(b))
+        if bad.any():
+            i = np.argwhere(bad)[0]
+            raise AssertionError(f"{what}: float attribute at words [{first},{first + cnt}): {bad.sum()} components exceed rtol={rtol}; "
+                                 f"first at row {i[0]}: got {a[i[0]]} want {b[i[0]]}")
