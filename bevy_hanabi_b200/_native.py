@@ -155,6 +155,7 @@ SIGNATURES = {
     "hnb_slab_download_indirect": (i32, [vp, u32, u32, u32, vp]),
     "hnb_slab_fill_c5": (i32, [vp, u32, u32, u32, u32, f32, f32]),
     "hnb_slab_checksum": (i32, [vp, u32, u32, u32, P(C.c_uint64)]),
+    "hnb_slab_checksum_indirect": (i32, [vp, u32, u32, u32, P(C.c_uint64)]),
     "hnb_effect_compile": (i32, [vp, P(EffectDesc), P(u32)]),
     "hnb_effect_destroy": (i32, [vp, u32]),
     "hnb_effect_generate_source": (i32, [P(EffectDesc), C.c_char_p, C.c_size_t, P(C.c_size_t)]),

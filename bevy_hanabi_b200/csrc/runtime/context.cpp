@@ -745,6 +745,30 @@ int32_t hnb_slab_checksum(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count
     });
 }
 
+int32_t hnb_slab_checksum_indirect(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint64_t* out) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        // hash the rows as the reference's interleaved IndirectEntry {ping, pong, dead}
+        hnb::PlaneSet ps{};
+        uint32_t* cols[3] = {s.ping, s.pong, s.dead};
+        for (int p = 0; p < 3; ++p) {
+            ps.ptr[p] = cols[p];
+            ps.words[p] = 1;
+            ps.word_off[p] = (uint32_t)p;
+            ps.word_to_plane[p] = (unsigned char)p;
+        }
+        unsigned long long* d = nullptr;
+        CUDA_CHECK(cudaMalloc((void**)&d, 8));
+        CUDA_CHECK(cudaMemsetAsync(d, 0, 8, c->stream));
+        CUDA_CHECK(hnb::launch_checksum(ps, first, count, 3, d, c->stream));
+        c->launches++;
+        CUDA_CHECK(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    });
+}
+
 // ---- effects --------------------------------------------------------------------------------
 int32_t hnb_effect_generate_source(const hnb_effect_desc* desc, char* out, size_t cap, size_t* len) {
     return guarded([&] {

@@ -227,6 +227,11 @@ class Context:
         check(lib.hnb_slab_checksum(self._h, slab, first, count, C.byref(out)))
         return out.value
 
+    def slab_checksum_indirect(self, slab: int, first: int, count: int) -> int:
+        out = C.c_uint64(0)
+        check(lib.hnb_slab_checksum_indirect(self._h, slab, first, count, C.byref(out)))
+        return out.value
+
     # -- effects
     def effect_compile(self, fx: LoweredEffect) -> int:
         d, _keep = fx.to_c()

@@ -203,6 +203,10 @@ HNB_API int32_t hnb_slab_fill_c5(hnb_ctx* ctx, hnb_slab slab, uint32_t first, ui
 HNB_API int32_t hnb_slab_checksum(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
                                   uint64_t* out);
 
+/** Same checksum over the interleaved {ping,pong,dead} rows of the slab's indirection columns. */
+HNB_API int32_t hnb_slab_checksum_indirect(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
+                                           uint64_t* out);
+
 /* ------------------------------------------------------------------------------------ */
 /* 4. Compiled effects ≙ pipeline specialisation (reference mod.rs:1758,1866;            */
 /*    templates vfx_init.wgsl / vfx_update.wgsl)                                          */

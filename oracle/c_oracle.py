@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     lib.orc_fill_c5.argtypes = [vp, vp, u32, u32, u32, f32, f32]
     lib.orc_update_c5_parallel.restype = u32
     lib.orc_update_c5_parallel.argtypes = [P(SimParams), P(u32), vp, vp, P(Spawner), P(EffectMetadata), P(f32), vp, C.c_int]
+    lib.orc_checksum.restype = C.c_uint64
+    lib.orc_checksum.argtypes = [vp, u32, u32, u32]
     lib.orc_max_threads.restype = C.c_int
     lib.orc_max_threads.argtypes = []
     return lib

@@ -422,6 +422,21 @@ ORC_API uint32_t orc_update_c5_parallel(const orc_sim_params* sim_params, uint32
     return alive_total;
 }
 
+/* Order-independent checksum of `count` rows of `stride_words` u32 each: same function as the device-side
+ * hnb_slab_checksum (sum over rows of a 64-bit mix of the row's words and its index). */
+ORC_API uint64_t orc_checksum(const uint32_t* words, uint32_t first, uint32_t count, uint32_t stride_words) {
+    uint64_t acc = 0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+    for (int64_t i = 0; i < (int64_t)count; ++i) {
+        uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)i;
+        const uint32_t* row = words + (size_t)(first + (uint32_t)i) * stride_words;
+        for (uint32_t w = 0; w < stride_words; ++w) h = (h ^ (uint64_t)row[w]) * 0x100000001b3ull;
+        h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+        acc += h;
+    }
+    return acc;
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
