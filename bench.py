@@ -214,11 +214,14 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = max(world, 1)
+    from bevy_hanabi_b200.sharding import shard_range
     if args.scaling == "strong":
-        per_rank = args.particles // n_gpus
+        first_row, end_row = shard_range(args.particles, rank, n_gpus)   # index-range shard of the logical instance
+        per_rank = end_row - first_row
+        total = args.particles
     else:
         per_rank = args.particles
-    total = per_rank * n_gpus
+        total = per_rank * n_gpus
 
     # all work goes on ONE explicit non-default stream shared by torch (events, barriers) and the backend
     stream = torch.cuda.Stream()
@@ -226,7 +229,8 @@ def run_b200(args):
     assert stream.cuda_stream != 0
     ctx = hb.Context(local_rank, stream.cuda_stream)
     slab = ctx.slab_create(per_rank, recipes.C5_STRIDE)
-    effect = ctx.effect_compile(recipes.c5_lowered())
+    # the C5 effect authored through the Module/Modifier/EffectAsset API and lowered to CUDA C by the library
+    effect = ctx.effect_compile(recipes.c5_asset(per_rank).generate())
     # shard `rank` owns rows [rank*per_rank, (rank+1)*per_rank) of the logical 64M instance: same
     # counter-based state as a 1-GPU run would hold for those rows (seed mixes the global row)
     ctx.slab_fill_c5(slab, 0, per_rank, 42 + rank, 1e9, 1e9)

@@ -45,3 +45,16 @@ def c5_lowered(relaxed_order: bool = False) -> LoweredEffect:
 
 def c5_generated_source() -> str:
     return c5_lowered().generate_source()
+
+
+def c5_asset(capacity: int):
+    """Config C5 authored through the public API (the path a Hanabi user takes): the generated code is
+    identical to `c5_lowered()` (tests/test_authoring_cpu.py)."""
+    from . import graph as G
+    w = G.ExprWriter()
+    A = G.Attribute
+    zero = w.lit(G.Vec3(0., 0., 0.))
+    return (G.EffectAsset(capacity, w.finish(), name="c5_accel_drag")
+            .init(G.SetAttributeModifier(A.POSITION, zero)).init(G.SetAttributeModifier(A.VELOCITY, zero))
+            .init(G.SetAttributeModifier(A.AGE, w.lit(0.))).init(G.SetAttributeModifier(A.LIFETIME, w.lit(1.)))
+            .update(G.AccelModifier(w.lit(G.Vec3(0., -9.8, 0.)))).update(G.LinearDragModifier(w.lit(0.5))))
