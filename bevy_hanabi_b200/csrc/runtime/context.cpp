@@ -107,6 +107,15 @@ struct EventBuffer {
     uint32_t* d = nullptr;
 };
 
+// Pinned staging slot of the per-frame upload (see flush_arena).
+constexpr int kStageSlots = 8;
+struct StageSlot {
+    char* h = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+
 struct ArenaLayout {
     size_t off_batch_infos, off_tile_size, off_spawners, off_range, off_spawn_prefix, off_prefix_sum, total;
     static ArenaLayout make(uint32_t E, uint32_t B) {
@@ -142,6 +151,8 @@ struct hnb_ctx {
     char* d_arena = nullptr;
     size_t arena_cap = 0;
     bool dirty_tables = true;  // spawners / batch infos / prefix sums changed since last flush
+    StageSlot stage[kStageSlots];  // pinned snapshots of the frame block, one per in-flight frame
+    uint32_t stage_next = 0;
     uint32_t epoch = 0;
 
     // persistent device tables
@@ -298,7 +309,21 @@ void flush_arena(hnb_ctx* c, bool with_ranges) {
     if (c->dirty_tables) bytes = c->lay.total;
     else if (with_ranges) bytes = c->lay.off_prefix_sum;  // everything but the GPU-rewritten prefix sums
     else bytes = sizeof(hnb::FrameHeader);
-    CUDA_CHECK(cudaMemcpyAsync(c->d_arena, c->h_arena, bytes, cudaMemcpyHostToDevice, c->stream));
+    // The copy executes when the stream reaches it, not now: the host arena (epoch, ranges, tables) will be
+    // rewritten for the NEXT frame long before that if the caller queues frames ahead. Snapshot the bytes into
+    // a pinned staging slot that is not reused until its copy has completed.
+    StageSlot& slot = c->stage[c->stage_next++ % kStageSlots];
+    if (slot.used) CUDA_CHECK(cudaEventSynchronize(slot.done));
+    if (slot.cap < bytes) {
+        if (slot.h) cudaFreeHost(slot.h);
+        slot.cap = std::max(bytes * 2, size_t(4096));
+        CUDA_CHECK(cudaMallocHost((void**)&slot.h, slot.cap));
+    }
+    if (!slot.done) CUDA_CHECK(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+    memcpy(slot.h, c->h_arena, bytes);
+    CUDA_CHECK(cudaMemcpyAsync(c->d_arena, slot.h, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaEventRecord(slot.done, c->stream));
+    slot.used = true;
     c->dirty_tables = false;
 }
 
@@ -585,6 +610,10 @@ void hnb_ctx_destroy(hnb_ctx* c) {
     for (auto p : c->d_tile_state) if (p) cudaFree(p);
     for (auto& ev : c->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : c->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& sl : c->stage) {
+        if (sl.h) cudaFreeHost(sl.h);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     if (c->h_arena) cudaFreeHost(c->h_arena);
     if (c->d_arena) cudaFree(c->d_arena);
     cudaFree(c->d_metadata); cudaFree(c->d_draw_args); cudaFree(c->d_child_infos);

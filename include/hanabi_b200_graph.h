@@ -118,6 +118,57 @@ HNB_API int32_t hnb_asset_generate(const hnb_asset* a, const hnb_asset* parent, 
 HNB_API int32_t hnb_generated_desc(const hnb_generated* g, hnb_effect_desc* desc);
 HNB_API void hnb_generated_destroy(hnb_generated* g);
 
+/* ---- CPU producers feeding the hot path ----------------------------------------- */
+/** SpawnerSettings (reference src/spawn.rs:219): CpuValue<f32> fields as [lo, hi] (lo == hi: Single). */
+typedef struct hnb_spawner_settings {
+    float count_lo, count_hi;
+    float spawn_duration_lo, spawn_duration_hi;
+    float period_lo, period_hi;
+    uint32_t cycle_count;   /* 0 = forever, 1 = once */
+    uint32_t starts_active;
+    uint32_t emit_on_start;
+} hnb_spawner_settings;
+typedef struct hnb_effect_spawner hnb_effect_spawner; /* EffectSpawner, spawn.rs:640 */
+typedef struct hnb_effect_spawner_state_t {
+    float cycle_time, cycle_spawn_duration, cycle_period, cycle_ratio, cycle_spawn_count;
+    uint32_t completed_cycle_count, active, has_completed, spawn_count;
+} hnb_effect_spawner_state_t;
+/** SpawnerSettings::try_new (spawn.rs:313-338): validates the period like the reference. */
+HNB_API int32_t hnb_spawner_settings_new(float count_lo, float count_hi, float duration_lo, float duration_hi, float period_lo,
+                                         float period_hi, uint32_t cycle_count, hnb_spawner_settings* out);
+HNB_API int32_t hnb_spawner_settings_once(float count, hnb_spawner_settings* out);                /* spawn.rs:349 */
+HNB_API int32_t hnb_spawner_settings_rate(float rate, hnb_spawner_settings* out);                 /* spawn.rs:367 */
+HNB_API int32_t hnb_spawner_settings_burst(float count, float period, hnb_spawner_settings* out); /* spawn.rs:381 */
+HNB_API hnb_effect_spawner* hnb_effect_spawner_create(const hnb_spawner_settings* settings, uint64_t rng_seed);
+HNB_API void hnb_effect_spawner_destroy(hnb_effect_spawner* s);
+/** EffectSpawner::tick (spawn.rs:838-921): number of particles to spawn this frame -> GpuSpawnerParams.spawn. */
+HNB_API int32_t hnb_effect_spawner_tick(hnb_effect_spawner* s, float dt, uint32_t* spawn_count);
+HNB_API void hnb_effect_spawner_reset(hnb_effect_spawner* s);
+HNB_API void hnb_effect_spawner_set_active(hnb_effect_spawner* s, uint32_t active);
+HNB_API int32_t hnb_effect_spawner_state(const hnb_effect_spawner* s, hnb_effect_spawner_state_t* out);
+
+/** What EffectBatch::try_merge compares (reference src/render/batch.rs:153-173). */
+typedef struct hnb_batch_key {
+    uint64_t asset_id;       /* handle */
+    uint32_t slab_id;
+    uint32_t pipeline_id;    /* init_and_update_pipeline_ids */
+    uint32_t property_key;
+    uint32_t parent_slab_id; /* 0xFFFFFFFF if none */
+    uint32_t uses_gpu_events;/* cached_effect_events.is_some() */
+    uint32_t is_cpu_spawner; /* spawn_info.is_cpu() */
+} hnb_batch_key;
+typedef struct hnb_batcher hnb_batcher; /* Batcher, batch.rs:197 */
+HNB_API hnb_batcher* hnb_batcher_create(void);
+HNB_API void hnb_batcher_destroy(hnb_batcher* b);
+HNB_API void hnb_batcher_clear(hnb_batcher* b);
+/** Batcher::push (batch.rs:348-386): *batch_index = index of the new batch, or -1 if merged into the last one. */
+HNB_API int32_t hnb_batcher_push(hnb_batcher* b, const hnb_batch_key* key, uint32_t spawner_base, uint32_t slab_offset,
+                                 uint32_t instance_spawn_count, int32_t* batch_index);
+/** Close the open batch and expose the tables to upload with hnb_upload_batches (pointers valid until the next
+ *  push/clear) plus each batch's CPU total spawn count (for hnb_batch_launch.total_spawn_count). */
+HNB_API int32_t hnb_batcher_finish(hnb_batcher* b, const hnb_batch_info** infos, uint32_t* n_batches, const uint32_t** prefix,
+                                   uint32_t* n_prefix, uint32_t* total_spawn_counts, uint32_t total_cap);
+
 #ifdef __cplusplus
 }
 #endif

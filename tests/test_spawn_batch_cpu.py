@@ -1,0 +1,127 @@
+"""CPU producers feeding the hot path: EffectSpawner::tick against the reference's own test sequences
+(src/spawn.rs:1046-1287) and Batcher::push / try_merge (src/render/batch.rs:153-188, :265-386)."""
+import pytest
+
+from bevy_hanabi_b200._native import HanabiError
+from bevy_hanabi_b200.spawn import BatchKey, Batcher, EffectSpawner, SpawnerSettings
+
+
+def test_new_sequence():
+    # spawn.rs test_new: count 3 over 3 s, period 10 s, 2 cycles
+    sp = EffectSpawner(SpawnerSettings(3.0, 3.0, 10.0, 2))
+    assert sp.tick(2.0) == 2
+    s = sp.state
+    assert (s.cycle_time, s.cycle_spawn_duration, s.cycle_period, s.cycle_spawn_count, s.completed_cycle_count) == (2.0, 3.0, 10.0, 3.0, 0)
+    assert s.cycle_ratio == pytest.approx(0.2, abs=0) or abs(s.cycle_ratio - 0.2) < 1e-7
+    assert sp.tick(5.0) == 1
+    assert sp.state.cycle_time == 7.0
+    assert sp.tick(8.0) == 3
+    s = sp.state
+    assert (s.cycle_time, s.completed_cycle_count) == (5.0, 1)
+    assert sp.tick(10.0) == 0
+    assert sp.state.completed_cycle_count == 2 and sp.active
+    assert sp.tick(0.1) == 0
+    assert sp.state.completed_cycle_count == 2
+
+
+def test_period_validation():
+    with pytest.raises(HanabiError):
+        SpawnerSettings(3.0, 1.0, (-1.0, 1.0), 0)       # negative period
+    with pytest.raises(HanabiError):
+        SpawnerSettings(3.0, 1.0, (0.0, 0.0), 0)        # cannot generate a positive period
+    with pytest.raises(HanabiError):
+        SpawnerSettings(3.0, 1.0, (0.0, float("inf")), 0)
+    SpawnerSettings(3.0, 1.0, (0.0, 0.0), 1)            # once(): period unchecked
+
+
+def test_once():
+    sp = EffectSpawner(SpawnerSettings.once(5.0))
+    assert sp.active
+    assert sp.tick(0.001) == 5
+    assert sp.tick(100.0) == 0
+    sp = EffectSpawner(SpawnerSettings.once(5.0))
+    sp.tick(1.0)
+    sp.reset()
+    assert sp.tick(1.0) == 5
+
+
+def test_once_start_inactive():
+    sp = EffectSpawner(SpawnerSettings.once(5.0).with_starts_active(False))
+    assert not sp.has_completed()
+    assert sp.tick(1.0) == 0 and not sp.has_completed()
+    sp.active = True
+    assert sp.tick(1.0) == 5 and sp.active and sp.has_completed()
+    assert sp.tick(1.0) == 0 and sp.has_completed()
+    sp.reset()
+    assert sp.active and not sp.has_completed()
+    assert sp.tick(1.0) == 5 and sp.has_completed()
+
+
+def test_rate():
+    sp = EffectSpawner(SpawnerSettings.rate(5.0))
+    assert sp.tick(1.01) == 5
+    assert sp.tick(0.4) == 2
+    sp = EffectSpawner(SpawnerSettings.rate(5.0))
+    sp.tick(1.01)
+    sp.active = False
+    assert sp.tick(0.4) == 0
+    sp.active = True
+    assert sp.tick(0.4) == 2
+    sp = EffectSpawner(SpawnerSettings.rate(5.0))
+    assert sum(sp.tick(1.0 / 60.0) for _ in range(13)) == 1
+
+
+def test_burst():
+    sp = EffectSpawner(SpawnerSettings.burst(5.0, 2.0))
+    assert sp.tick(1.0) == 5
+    assert sp.tick(4.0) == 10
+    assert sp.tick(0.1) == 0
+
+
+def test_with_active():
+    sp = EffectSpawner(SpawnerSettings.rate(5.0).with_starts_active(False))
+    assert not sp.active and sp.tick(1.0) == 0
+    sp.active = False
+    assert sp.tick(1.0) == 0
+    sp.active = True
+    assert sp.tick(1.0) == 5
+
+
+def test_c1_rate_1000_per_second():
+    # gpu_tests/single_particle.rs: rate 1000/s at dt=1/60 -> 16,17,17,16,...
+    sp = EffectSpawner(SpawnerSettings.rate(1000.0))
+    counts = [sp.tick(1.0 / 60.0) for _ in range(60)]
+    assert set(counts) <= {16, 17} and 999 <= sum(counts) <= 1000
+
+
+def _key(asset=1, slab=0, pipe=0, prop=0, parent=0xFFFFFFFF, events=0, cpu=1):
+    return BatchKey(asset, slab, pipe, prop, parent, events, cpu)
+
+
+def test_batcher_merges_same_asset_instances():
+    b = Batcher()
+    assert b.push(_key(), 0, 0, 10) == 0
+    assert b.push(_key(), 1, 512, 5) == -1          # merged
+    assert b.push(_key(), 2, 1024, 8) == -1
+    assert b.push(_key(asset=2, slab=1), 3, 0, 6) == 1
+    infos, prefix, totals = b.finish()
+    # headless_batching_tests.rs layout: batch 0 = 3 instances, batch 1 = 1 instance; CPU prefix of spawn counts
+    assert [(i.spawner_base, i.base_particle, i.prefix_sum_offset, i.prefix_sum_count) for i in infos] == [(0, 0, 0, 3), (3, 0, 3, 1)]
+    assert prefix == [0, 10, 15, 0]
+    assert totals == [23, 6]
+    assert all(i.total_spawn_count == 0 and i.total_update_count == 0 for i in infos)   # batch.rs:271-278
+
+
+def test_batcher_never_merges_event_effects_or_different_slabs():
+    b = Batcher()
+    assert b.push(_key(events=1, cpu=0), 0, 0, 0) == 0
+    assert b.push(_key(events=1, cpu=0), 1, 256, 0) == 1     # GPU-event effects stay alone (batch.rs:166-170)
+    assert b.push(_key(slab=3), 2, 0, 4) == 2
+    assert b.push(_key(slab=4), 3, 0, 4) == 3                # different slab
+    assert b.push(_key(slab=4, prop=9), 4, 64, 4) == 4       # different property buffer
+    assert b.push(_key(slab=4, prop=9), 5, 128, 4) == -1
+    infos, prefix, totals = b.finish()
+    assert [i.prefix_sum_count for i in infos] == [1, 1, 1, 1, 2]
+    assert prefix == [0, 0, 0, 0, 0, 4] and totals == [0, 0, 4, 4, 8]
+    b.clear()
+    assert b.finish() == ([], [], [])
