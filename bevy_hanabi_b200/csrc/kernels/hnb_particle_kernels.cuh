@@ -15,7 +15,9 @@
 // Design:
 //   * update is a persistent, single-pass "process + stable compaction" kernel with WARP-AUTONOMOUS
 //     tiles: every warp of the persistent grid takes tiles of tile_rows = 32*K*chunks rows of ONE effect
-//     instance from a ticket counter. Rows are read through the alive
+//     instance from a ticket counter. The compaction of a tile (look-back + index writes) is DEFERRED
+//     until the warp has streamed its next tile, by which time every predecessor has published its
+//     aggregate: nobody waits (see "deferred compaction" below). Rows are read through the alive
 //     list (coalesced u32), particles through float4 SoA planes, processed in registers and written
 //     back; survivors are compacted into the write list in row order with warp ballots inside the tile
 //     and a decoupled look-back chain (one 64-bit state word per tile) across the tiles of the same
@@ -34,9 +36,10 @@ namespace hnb {
 
 #define HNB_BLOCK 256
 #define HNB_WARPS (HNB_BLOCK / 32)
-// A tile is 1..HNB_MAX_CHUNKS sub-tiles of 32*K rows (BatchParams::tile_rows); at most 32 rows per
-// lane, i.e. 1024 rows per tile, so that the tile's alive-list entries fit a 4 KB per-warp stash.
-#define HNB_ROWS_PER_LANE 32
+// A tile is 1..HNB_MAX_CHUNKS sub-tiles of 32*K rows (BatchParams::tile_rows); at most 16 rows per
+// lane, i.e. 512 rows per tile, so that the alive-list entries of TWO tiles (the one being streamed and
+// the one whose compaction is deferred) fit a 2 x 2 KB per-warp stash.
+#define HNB_ROWS_PER_LANE 16
 #define HNB_MAX_CHUNKS (HNB_ROWS_PER_LANE / HNB_TILE_K)
 #ifndef HNB_LOOKBACK_GROUPS
 #define HNB_LOOKBACK_GROUPS 4  // predecessors examined per look-back round trip = 32 * groups
@@ -46,6 +49,9 @@ namespace hnb {
 #endif
 #ifndef HNB_MIN_BLOCKS
 #define HNB_MIN_BLOCKS 4
+#endif
+#ifndef HNB_DEFER_COMPACTION
+#define HNB_DEFER_COMPACTION (!HNB_RELAXED_ORDER)  // park a tile's compaction behind the warp's next pass 1
 #endif
 #ifndef HNB_PROFILE
 #define HNB_PROFILE 0  // 1: accumulate per-phase cycle counters into BatchParams::debug (diagnostics)
@@ -155,12 +161,123 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
 // ---------------------------------------------------------------------------------------------
 // update  ≙ vfx_update.wgsl main()
 // ---------------------------------------------------------------------------------------------
+// A tile whose rows have been simulated (pass 1) and whose compaction is still to be done. Lives in
+// shared memory (one per warp) so that it costs no registers while the next tile is being streamed.
+struct PendingTile {
+    u32 valid, tile, row0, tile_alive;
+    u32 base_particle, max_update, write_index, render_index;
+    u32 inst_first_tile, inst_end_tile, metadata_index, buffer;
+};
+
+// Compaction of one tile: exclusive prefix of survivors over the previous tiles of the instance
+// (decoupled look-back), then survivors -> write list, dead -> dead stack (vfx_update.wgsl:148-166).
+HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const u32* survivors, const u32 (*pidx_stash)[32],
+                             u32 chunks, u32 epoch, u32 lane, long long& prof_polls) {
+    u64* const states = P.tile_state;
+    const u32 tile = pt.tile, row0 = pt.row0, tile_alive = pt.tile_alive, max_update = pt.max_update;
+    const u32 base_particle = pt.base_particle, inst_first_tile = pt.inst_first_tile;
+    EffectMetadata* const md = &P.metadata[pt.metadata_index];
+    u32* __restrict__ write_col = P.slab.particle_index[pt.write_index] + base_particle;
+    (void)prof_polls;
+
+    u32 alive_before = 0u;
+#if HNB_RELAXED_ORDER
+    // Reference-style order (vfx_update.wgsl:164) with one warp-aggregated atomic per tile.
+    if (lane == 0) alive_before = atomicAdd(&P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * pt.render_index + 1u], tile_alive);
+    alive_before = __shfl_sync(0xffffffffu, alive_before, 0);
+#else
+    if (tile != inst_first_tile) {
+        // Walk back over the predecessors' states, HNB_LOOKBACK_GROUPS x 32 of them per round trip (lane l
+        // of group g examines tile pos - 32g - l), summing AGGREGATEs until the first PREFIX. Tiles before
+        // the instance's first tile count as a PREFIX of 0.
+        u32 pos = tile - 1u;  // newest predecessor not yet accounted for
+        for (;;) {
+            u64 s[HNB_LOOKBACK_GROUPS];
+#pragma unroll
+            for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
+                const u32 back = 32u * g + lane;
+                s[g] = (pos >= inst_first_tile + back) ? hnb_ld_state(&states[pos - back]) : hnb_pack_state(epoch, HNB_FLAG_PREFIX, 0u);
+            }
+            bool done = false, stalled = false;
+#pragma unroll
+            for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
+                if (!done && !stalled) {
+                    const u32 flag = (u32(s[g] >> 34) == epoch) ? (u32(s[g] >> 32) & 3u) : 0u;
+                    const u32 ready_mask = __ballot_sync(0xffffffffu, flag != 0u);
+                    const u32 prefix_mask = __ballot_sync(0xffffffffu, flag == u32(HNB_FLAG_PREFIX));
+                    const u32 first_p = prefix_mask ? (u32)(__ffs(prefix_mask) - 1) : 32u;
+                    const u32 need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
+                    if ((ready_mask & need) != need) {
+                        stalled = true;  // a needed predecessor has not published yet: poll again from here
+                    } else {
+                        u32 contrib = lane <= first_p ? u32(s[g]) : 0u;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                        alive_before += contrib;
+                        if (prefix_mask) done = true; else pos -= 32u;
+                    }
+                }
+            }
+            if (done) break;
+            if (stalled) {
+#if HNB_PROFILE
+                prof_polls++;
+#endif
+#if HNB_LOOKBACK_SLEEP_NS > 0
+                __nanosleep(HNB_LOOKBACK_SLEEP_NS);
+#endif
+            }
+        }
+        if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, alive_before + tile_alive));
+    }
+#endif
+
+    // survivors into the write list, the dead onto the dead stack, indices from the shared-memory stash
+    u32 alive_rank_base = alive_before;
+#pragma unroll 4
+    for (u32 jk = 0; jk < chunks * HNB_TILE_K; ++jk) {
+        const u32 row = row0 + jk * 32u + lane;
+        const u32 ballot = survivors[jk];
+        if (row < max_update) {
+            const u32 pidx = pidx_stash[jk][lane];
+            const u32 alive_rank = alive_rank_base + __popc(ballot & hnb_lanemask_lt());  // surviving rows before `row`
+            if ((ballot >> lane) & 1u) {
+                write_col[alive_rank] = pidx;
+            } else {
+#if HNB_RELAXED_ORDER
+                const u32 alive_index = atomicSub(&md->alive_count, 1u) - 1u;
+                P.slab.dead_index[base_particle + alive_index] = base_particle + pidx;
+                atomicAdd(&md->max_spawn, 1u);
+#else
+                // `row - alive_rank` dead rows precede this one: serial-order value of
+                // atomicSub(alive_count,1)-1 given alive_count == max_update at pass start.
+                const u32 alive_index = max_update - 1u - (row - alive_rank);
+                P.slab.dead_index[base_particle + alive_index] = base_particle + pidx;
+#endif
+            }
+        }
+        alive_rank_base += __popc(ballot);
+    }
+#if !HNB_RELAXED_ORDER
+    // the last tile of the instance publishes the totals (replaces the per-particle atomics on
+    // instance_count / alive_count / max_spawn)
+    if (lane == 0 && tile + 1u == pt.inst_end_tile) {
+        const u32 alive_total = alive_before + tile_alive;
+        const u32 dead_total = max_update - alive_total;
+        P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * pt.render_index + 1u] = alive_total;
+        md->alive_count = md->alive_count - dead_total;
+        md->max_spawn = md->max_spawn + dead_total;
+    }
+#endif
+}
+
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_update(const BatchParams P) {
     __shared__ u32 sh_tile_prefix[HNB_SMEM_EFFECTS + 1];
-    // survivor ballots of the tile a warp is working on (one word per 32 rows), pass 1 -> pass 2
-    __shared__ u32 sh_survivors[HNB_WARPS][HNB_ROWS_PER_LANE];
-    // alive-list entries of that tile (pass 1 reads them from global memory once, pass 2 from here)
-    __shared__ u32 sh_pidx[HNB_WARPS][HNB_ROWS_PER_LANE][32];
+    // double-buffered per warp: survivor ballots (one word per 32 rows) and alive-list entries of the tile
+    // being streamed and of the tile whose compaction is deferred
+    __shared__ u32 sh_survivors[HNB_WARPS][2][HNB_ROWS_PER_LANE];
+    __shared__ u32 sh_pidx[HNB_WARPS][2][HNB_ROWS_PER_LANE][32];
+    __shared__ PendingTile sh_pending[HNB_WARPS];
 #if HNB_HAS_PROPERTIES
     // per-warp staging slot of the current instance's Properties record
     __shared__ __align__(16) unsigned char sh_props[HNB_WARPS][(sizeof(Properties) + 15) / 16 * 16];
@@ -179,6 +296,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         for (u32 i = tid; i < n_effects; i += HNB_BLOCK) sh_tile_prefix[i] = g_tile_prefix[i];
         if (tid == 0) sh_tile_prefix[n_effects] = total_tiles;
     }
+    if (lane == 0) sh_pending[warp].valid = 0u;
     __syncthreads();  // the only block barrier of the kernel
 
     u64* const states = P.tile_state;
@@ -186,17 +304,16 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // host (and used by the bookkeeping kernel for the tile prefix), so it is a run-time value here
     const u32 tile_rows = P.tile_rows;
     const u32 chunks = tile_rows / (32u * HNB_TILE_K);
-    u32* const survivors = sh_survivors[warp];
-    u32(*const pidx_stash)[32] = sh_pidx[warp];
+    PendingTile& pending = sh_pending[warp];
+    u32 cur = 0u;  // buffer the tile being streamed uses
 
     // cached descriptor of the instance the current tile belongs to (reloaded when a tile leaves
     // [inst_first_tile, inst_end_tile))
     u32 inst_first_tile = 1u, inst_end_tile = 0u;  // empty range
     Spawner* spawner = nullptr;
-    EffectMetadata* md = nullptr;
+    u32 metadata_index = 0u;
     u32 base_particle = 0u, spawner_seed = 0u, max_update = 0u, write_index = 0u, render_index = 0u;
     const u32* __restrict__ read_col = nullptr;
-    u32* __restrict__ write_col = nullptr;
 
     Ctx hnb_ctx;
     hnb_ctx.sim = &P.frame->sim;
@@ -210,15 +327,15 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     }
 #endif
 
-    // Tiles are handed out by a ticket counter (so that every tile's predecessors in the look-back
-    // chain have already been taken by a running warp); the ticket of the NEXT tile is requested
-    // between the look-back and pass 2 of the current one (see below).
+    // Tiles are handed out by a ticket counter, so every tile's predecessors in the look-back chain have
+    // been taken by a running warp before it.
     u32 tile = 0u;
     if (lane == 0) tile = atomicAdd(P.ticket, 1u);
     tile = __shfl_sync(0xffffffffu, tile, 0);
+    long long prof_polls = 0;
 #if HNB_PROFILE
-    // per-warp cycle accounting of the three phases (diagnostics only)
-    long long prof_t0 = clock64(), prof_pass1 = 0, prof_lookback = 0, prof_pass2 = 0, prof_polls = 0, prof_tiles = 0;
+    // per-warp cycle accounting of the phases (diagnostics only)
+    long long prof_t0 = clock64(), prof_pass1 = 0, prof_compact = 0, prof_tiles = 0;
     const long long prof_start = prof_t0;
 #define HNB_PROF_MARK(acc) { const long long _t = clock64(); acc += _t - prof_t0; prof_t0 = _t; }
 #else
@@ -226,7 +343,6 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
 #endif
 
     while (tile < total_tiles) {
-
         if (tile < inst_first_tile || tile >= inst_end_tile) {
             // Which instance does this tile belong to? (per-warp replacement of the per-thread binary
             // search of vfx_update.wgsl:51-72; all lanes read the same words: broadcast)
@@ -243,13 +359,16 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             spawner = &P.spawners[bi.spawner_base + effect_index];
             base_particle = spawner->slab_offset;
             spawner_seed = spawner->seed;
-            md = &P.metadata[spawner->effect_metadata_index];
+            metadata_index = spawner->effect_metadata_index;
+            const EffectMetadata* md = &P.metadata[metadata_index];
             max_update = md->max_update;  // :119
             write_index = md->indirect_write_index;
             render_index = md->indirect_render_index;
             read_col = P.slab.particle_index[1u - write_index] + base_particle;
-            write_col = P.slab.particle_index[write_index] + base_particle;
             hnb_ctx.spawner = spawner;
+            hnb_ctx.transform = hnb_transform_from_rows(spawner->transform, spawner->transform + 4, spawner->transform + 8);
+            hnb_ctx.inverse_transform = hnb_transform_from_rows(spawner->inverse_transform, spawner->inverse_transform + 4,
+                                                                spawner->inverse_transform + 8);
 #if HNB_HAS_PROPERTIES
             {
                 const u32* src = (const u32*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
@@ -263,8 +382,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             hnb_ctx.base_child_index = md->base_child_index;
 #endif
         }
-        const u32 tile_in_effect = tile - inst_first_tile;
-        const u32 row0 = tile_in_effect * tile_rows;
+        const u32 row0 = (tile - inst_first_tile) * tile_rows;
+        u32* const survivors = sh_survivors[warp][cur];
+        u32(*const pidx_stash)[32] = sh_pidx[warp][cur];
 
         // ---- pass 1: stream the tile's rows in `chunks` sub-tiles of 32*K rows:
         //      alive-list entry -> particle record -> simulate -> write back; remember who survived.
@@ -317,125 +437,66 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                 tile_alive += __popc(ballot);
             }
         }
-        __syncwarp();  // ballots visible to all lanes for pass 2
-
+        // Publish this tile's survivor count right away: the first tile of an instance knows its prefix (0),
+        // the others publish an AGGREGATE that successors can sum over while this tile's own prefix is
+        // still unknown.
+#if !HNB_RELAXED_ORDER
+        if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, tile == inst_first_tile ? HNB_FLAG_PREFIX : HNB_FLAG_AGGREGATE, tile_alive));
+#endif
         HNB_PROF_MARK(prof_pass1)
-        // ---- exclusive prefix over the previous tiles of this instance
-        u32 alive_before = 0u;
-#if HNB_RELAXED_ORDER
-        // Reference-style order (vfx_update.wgsl:164) with one warp-aggregated atomic per tile.
-        if (lane == 0) alive_before = atomicAdd(&P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * render_index + 1u], tile_alive);
-        alive_before = __shfl_sync(0xffffffffu, alive_before, 0);
-#else
-        if (tile_in_effect == 0u) {
-            if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, tile_alive));
-        } else {
-            if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_AGGREGATE, tile_alive));
-            // Walk back over the predecessors' states, HNB_LOOKBACK_GROUPS x 32 of them per round trip
-            // (lane l of group g examines tile pos - 32g - l), summing AGGREGATEs until the first
-            // PREFIX. Tiles before the instance's first tile count as a PREFIX of 0.
-            u32 pos = tile - 1u;  // newest predecessor not yet accounted for
-            for (;;) {
-                u64 s[HNB_LOOKBACK_GROUPS];
-#pragma unroll
-                for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
-                    const u32 back = 32u * g + lane;
-                    s[g] = (pos >= inst_first_tile + back) ? hnb_ld_state(&states[pos - back])
-                                                           : hnb_pack_state(epoch, HNB_FLAG_PREFIX, 0u);
-                }
-                bool done = false, stalled = false;
-#pragma unroll
-                for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
-                    if (!done && !stalled) {
-                        const u32 flag = (u32(s[g] >> 34) == epoch) ? (u32(s[g] >> 32) & 3u) : 0u;
-                        const u32 ready_mask = __ballot_sync(0xffffffffu, flag != 0u);
-                        const u32 prefix_mask = __ballot_sync(0xffffffffu, flag == u32(HNB_FLAG_PREFIX));
-                        const u32 first_p = prefix_mask ? (u32)(__ffs(prefix_mask) - 1) : 32u;
-                        const u32 need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
-                        if ((ready_mask & need) != need) {
-                            stalled = true;  // a needed predecessor has not published yet: poll again from here
-                        } else {
-                            u32 contrib = lane <= first_p ? u32(s[g]) : 0u;
-#pragma unroll
-                            for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                            alive_before += contrib;
-                            if (prefix_mask) done = true; else pos -= 32u;
-                        }
-                    }
-                }
-                if (done) break;
-                if (stalled) {
-#if HNB_PROFILE
-                    prof_polls++;
-#endif
-#if HNB_LOOKBACK_SLEEP_NS > 0
-                    __nanosleep(HNB_LOOKBACK_SLEEP_NS);
-#endif
-                }
-            }
-            if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, alive_before + tile_alive));
-        }
-#endif
 
-        HNB_PROF_MARK(prof_lookback)
-        // Request the next tile now: pass 2 below never waits on anybody, so its duration hides the
-        // atomic's round trip. (Requesting it any earlier would park a taken-but-unstarted tile behind
-        // this warp's look-back wait, and later tiles wait for that tile's aggregate: a convoy.)
+        // Request the next tile now; the atomic's round trip hides behind the compaction below.
         u32 next_tile = 0u;
         if (lane == 0) next_tile = atomicAdd(P.ticket, 1u);
 
-        // ---- pass 2: compact. Survivors go to the write list, the dead onto the dead stack (:148-166).
-        //      The alive-list entries come back from the per-warp shared-memory stash.
-        {
-            u32 alive_rank_base = alive_before;
-#pragma unroll 4
-            for (u32 jk = 0; jk < chunks * HNB_TILE_K; ++jk) {
-                const u32 row = row0 + jk * 32u + lane;
-                const u32 ballot = survivors[jk];
-                if (row < max_update) {
-                    const u32 pidx = pidx_stash[jk][lane];
-                    // number of surviving rows before `row` in this instance
-                    const u32 alive_rank = alive_rank_base + __popc(ballot & hnb_lanemask_lt());
-                    if ((ballot >> lane) & 1u) {
-                        write_col[alive_rank] = pidx;
-                    } else {
-#if HNB_RELAXED_ORDER
-                        const u32 alive_index = atomicSub(&md->alive_count, 1u) - 1u;
-                        P.slab.dead_index[base_particle + alive_index] = base_particle + pidx;
-                        atomicAdd(&md->max_spawn, 1u);
+        // ---- deferred compaction. Resolving THIS tile now would mean waiting for every in-flight predecessor
+        // to finish its pass 1 (they started at about the same time, and pass-1 durations vary). Instead the
+        // tile is parked and the PREVIOUS tile of this warp is resolved: its predecessors published their
+        // aggregates a whole pass 1 ago, so the look-back finds them immediately.
+#if HNB_DEFER_COMPACTION
+        __syncwarp();
+        if (pending.valid) {
+            const PendingTile pt = pending;
+            hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            pending.valid = 1u; pending.tile = tile; pending.row0 = row0; pending.tile_alive = tile_alive;
+            pending.base_particle = base_particle; pending.max_update = max_update; pending.write_index = write_index;
+            pending.render_index = render_index; pending.inst_first_tile = inst_first_tile; pending.inst_end_tile = inst_end_tile;
+            pending.metadata_index = metadata_index; pending.buffer = cur;
+        }
+        cur ^= 1u;
+        __syncwarp();
 #else
-                        // `row - alive_rank` dead rows precede this one: serial-order value of
-                        // atomicSub(alive_count,1)-1 given alive_count == max_update at pass start.
-                        const u32 alive_index = max_update - 1u - (row - alive_rank);
-                        P.slab.dead_index[base_particle + alive_index] = base_particle + pidx;
-#endif
-                    }
-                }
-                alive_rank_base += __popc(ballot);
-            }
-        }
-#if !HNB_RELAXED_ORDER
-        // the last tile of the instance publishes the totals (replaces the per-particle atomics on
-        // instance_count / alive_count / max_spawn)
-        if (lane == 0 && tile + 1u == inst_end_tile) {
-            const u32 alive_total = alive_before + tile_alive;
-            const u32 dead_total = max_update - alive_total;
-            P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * render_index + 1u] = alive_total;
-            md->alive_count = md->alive_count - dead_total;
-            md->max_spawn = md->max_spawn + dead_total;
+        {
+            __syncwarp();
+            PendingTile pt;
+            pt.valid = 1u; pt.tile = tile; pt.row0 = row0; pt.tile_alive = tile_alive; pt.base_particle = base_particle;
+            pt.max_update = max_update; pt.write_index = write_index; pt.render_index = render_index;
+            pt.inst_first_tile = inst_first_tile; pt.inst_end_tile = inst_end_tile; pt.metadata_index = metadata_index; pt.buffer = cur;
+            hnb_compact_tile(P, pt, survivors, pidx_stash, chunks, epoch, lane, prof_polls);
+            __syncwarp();
         }
 #endif
+        HNB_PROF_MARK(prof_compact)
         tile = __shfl_sync(0xffffffffu, next_tile, 0);
 #if HNB_PROFILE
         prof_tiles++;
-        HNB_PROF_MARK(prof_pass2)
 #endif
     }
+#if HNB_DEFER_COMPACTION
+    __syncwarp();
+    if (pending.valid) {
+        const PendingTile pt = pending;
+        hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
+    }
+#endif
 #if HNB_PROFILE
+    HNB_PROF_MARK(prof_compact)
     if (lane == 0 && P.debug) {
         atomicAdd(&P.debug[0], (unsigned long long)prof_pass1);
-        atomicAdd(&P.debug[1], (unsigned long long)prof_lookback);
-        atomicAdd(&P.debug[2], (unsigned long long)prof_pass2);
+        atomicAdd(&P.debug[1], (unsigned long long)prof_compact);
         atomicAdd(&P.debug[3], (unsigned long long)prof_polls);
         atomicAdd(&P.debug[4], (unsigned long long)prof_tiles);
         atomicAdd(&P.debug[5], 1ull);  // warps

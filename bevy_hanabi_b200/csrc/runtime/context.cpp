@@ -436,7 +436,7 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     uint32_t chunks = c->tile_chunks_override;
     if (chunks == 0) {
         chunks = 1;
-        while (chunks < 8 && uint64_t(lp.slab->capacity) >= uint64_t(2) * total_warps * sub_tile * (chunks * 2)) chunks *= 2;
+        while (chunks < 4 && uint64_t(lp.slab->capacity) >= uint64_t(2) * total_warps * sub_tile * (chunks * 2)) chunks *= 2;
     }
     chunks = std::max(1u, std::min(chunks, kMaxRowsPerLane / lp.fx->tile_k));
     const uint32_t tile = sub_tile * chunks;

@@ -30,7 +30,7 @@ std::vector<Plane> cut_planes(uint32_t stride_bytes);
 
 // Update tiles are walked by one warp each: tile_rows = 32 lanes * k rows per lane * chunks. k is
 // chosen from the record size (register footprint) at compile time, the chunk count per launch.
-constexpr uint32_t kMaxRowsPerLane = 32;  // == HNB_ROWS_PER_LANE: tile_rows <= 32 * 32
+constexpr uint32_t kMaxRowsPerLane = 16;  // == HNB_ROWS_PER_LANE: tile_rows <= 32 * 16
 uint32_t choose_tile_k(const hnb_effect_desc& d);
 
 // The complete translation unit (throws std::invalid_argument on a bad description).

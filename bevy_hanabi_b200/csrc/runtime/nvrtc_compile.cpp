@@ -27,7 +27,7 @@ bool nvrtc_compile_sm100a(const std::string& source, const std::string& name, st
     }
     // -fmad=false: no FMA contraction, so add/mul sequences are bit-exact with the CPU oracle
     // (SURVEY.md §7 "fp parity"). No fast-math: IEEE division and square root.
-    const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-default-device", "-diag-suppress=550",
+    const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-default-device", "-diag-suppress=550", "-diag-suppress=177",
                           "--ptxas-options=-v"};
     r = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
     size_t log_size = 0;
