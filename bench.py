@@ -256,6 +256,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_rank_ms = []
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,10 +267,14 @@ def run_b200(args):
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        per_rank_ms.clear()
+        per_rank_ms.append(ms)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank_ms[:] = [float(x.item()) for x in allt]
+            ms = max(per_rank_ms)  # device time, MAX over ranks
         barrier()
         return ms
 
@@ -283,6 +289,7 @@ def run_b200(args):
         sampler.start()
     l0 = ctx.launch_count
     ms = timed(step_resident, args.steps)
+    value_per_rank_ms = [m / args.steps for m in per_rank_ms]
     gpu_launches = ctx.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     value = total * args.steps / (ms * 1e-3)
@@ -335,6 +342,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C5 synthetic 64M-particle SoA buffer, Accel+LinearDrag update, sharded by index range",
                        "particles_total": total, "particles_per_gpu": per_rank, "dt": DT, "steps_per_sec": args.steps / (ms * 1e-3),
+                       "ms_per_step_by_rank": value_per_rank_ms,
                        "l2": "inputs larger than L2 (per-GPU working set %.0f MB per step)" % (per_rank * 72 / 1e6),
                        "parallelism": f"index-range shards x{n_gpus}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,

@@ -108,7 +108,7 @@ struct EventBuffer {
 };
 
 // Pinned staging slot of the per-frame upload (see flush_arena).
-constexpr int kStageSlots = 8;
+constexpr int kStageSlots = 32;  // frames the host may queue ahead of the GPU before blocking
 struct StageSlot {
     char* h = nullptr;
     size_t cap = 0;
