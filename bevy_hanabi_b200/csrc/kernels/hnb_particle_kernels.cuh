@@ -39,16 +39,20 @@ namespace hnb {
 // A tile is 1..HNB_MAX_CHUNKS sub-tiles of 32*K rows (BatchParams::tile_rows); at most 16 rows per
 // lane, i.e. 512 rows per tile, so that the alive-list entries of TWO tiles (the one being streamed and
 // the one whose compaction is deferred) fit a 2 x 2 KB per-warp stash.
+#ifndef HNB_ROWS_PER_LANE
 #define HNB_ROWS_PER_LANE 16
+#endif
 #define HNB_MAX_CHUNKS (HNB_ROWS_PER_LANE / HNB_TILE_K)
 #ifndef HNB_LOOKBACK_GROUPS
-#define HNB_LOOKBACK_GROUPS 4  // predecessors examined per look-back round trip = 32 * groups
+#define HNB_LOOKBACK_GROUPS 1  // predecessors examined per look-back round trip = 32 * groups (with deferred
+                               // compaction the first window almost always holds a PREFIX: 1 beat 4 by 2.7 %)
 #endif
 #ifndef HNB_SMEM_EFFECTS
-#define HNB_SMEM_EFFECTS 2048  // tile_prefix entries staged in shared memory (8 KB)
+#define HNB_SMEM_EFFECTS 2047  // tile_prefix entries staged in shared memory (8 KB with the end sentinel)
 #endif
+#define HNB_SMEM_PREFIX_BYTES ((HNB_SMEM_EFFECTS + 1) * 4)
 #ifndef HNB_MIN_BLOCKS
-#define HNB_MIN_BLOCKS 4
+#define HNB_MIN_BLOCKS 3  // 3 CTAs x 85 registers measured 2.4 % faster than 4 x 64 on C5 (profiles/)
 #endif
 #ifndef HNB_DEFER_COMPACTION
 #define HNB_DEFER_COMPACTION (!HNB_RELAXED_ORDER)  // park a tile's compaction behind the warp's next pass 1
@@ -272,15 +276,19 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
 }
 
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_update(const BatchParams P) {
-    __shared__ u32 sh_tile_prefix[HNB_SMEM_EFFECTS + 1];
-    // double-buffered per warp: survivor ballots (one word per 32 rows) and alive-list entries of the tile
-    // being streamed and of the tile whose compaction is deferred
-    __shared__ u32 sh_survivors[HNB_WARPS][2][HNB_ROWS_PER_LANE];
-    __shared__ u32 sh_pidx[HNB_WARPS][2][HNB_ROWS_PER_LANE][32];
-    __shared__ PendingTile sh_pending[HNB_WARPS];
+    // Dynamic shared memory (size = hnb_update_smem_bytes, computed identically on the host):
+    //   tile-prefix table | per warp, double-buffered: alive-list entries [2][R][32] and survivor ballots [2][R] |
+    //   per warp: PendingTile | per warp: Properties staging slot
+    extern __shared__ __align__(16) unsigned char hnb_smem[];
+    u32* const sh_tile_prefix = (u32*)hnb_smem;
+    typedef u32 PidxBuf[HNB_ROWS_PER_LANE][32];
+    typedef u32 SurvBuf[HNB_ROWS_PER_LANE];
+    PidxBuf(*const sh_pidx)[2] = (PidxBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES);
+    SurvBuf(*const sh_survivors)[2] = (SurvBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES + sizeof(PidxBuf) * 2 * HNB_WARPS);
+    PendingTile* const sh_pending = (PendingTile*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * 2 * HNB_WARPS);
 #if HNB_HAS_PROPERTIES
-    // per-warp staging slot of the current instance's Properties record
-    __shared__ __align__(16) unsigned char sh_props[HNB_WARPS][(sizeof(Properties) + 15) / 16 * 16];
+    typedef unsigned char PropsBuf[(sizeof(Properties) + 15) / 16 * 16];
+    PropsBuf* const sh_props = (PropsBuf*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * 2 * HNB_WARPS + sizeof(PendingTile) * HNB_WARPS);
 #endif
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;

@@ -96,7 +96,8 @@ struct Effect {
     bool live = false;
     uint64_t hash = 0;
     KernelModule* km = nullptr;
-    uint32_t tile_k = 4, flags = 0, particle_stride = 0, parent_stride = 0;
+    uint32_t tile_k = 4, flags = 0, particle_stride = 0, parent_stride = 0, rows_per_lane = 16, update_smem = 0;
+    int update_blocks_per_sm = 1;
     uint32_t props_size = 0, props_stride = 0, props_rows = 0;
     char* d_props = nullptr;
     std::string name;
@@ -384,10 +385,7 @@ KernelModule* get_module(hnb_ctx* c, const std::string& source, const std::strin
     if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuModuleGetFunction(hnb_init): " + cu_error_string(c->drv, r));
     r = c->drv.ModuleGetFunction(&km->update, km->mod, "hnb_update");
     if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuModuleGetFunction(hnb_update): " + cu_error_string(c->drv, r));
-    int bps = 0;
-    r = c->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&bps, km->update, 256, 0);
-    if (r != CUDA_SUCCESS || bps < 1) bps = 1;
-    km->update_blocks_per_sm = bps;
+    km->update_blocks_per_sm = 1;  // per effect: depends on its dynamic shared memory (see hnb_effect_compile)
     KernelModule* out = km.get();
     c->modules.emplace(hash, std::move(km));
     return out;
@@ -432,13 +430,13 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     // and amortise per-tile work; the chunk count is picked so that the persistent grid still gets at
     // least ~2 tiles per resident warp (small slabs get small tiles).
     const uint32_t sub_tile = 32u * lp.fx->tile_k;
-    const uint32_t total_warps = uint32_t(lp.fx->km->update_blocks_per_sm) * uint32_t(c->sm_count) * 8u;
+    const uint32_t total_warps = uint32_t(lp.fx->update_blocks_per_sm) * uint32_t(c->sm_count) * 8u;
     uint32_t chunks = c->tile_chunks_override;
     if (chunks == 0) {
         chunks = 1;
-        while (chunks < 4 && uint64_t(lp.slab->capacity) >= uint64_t(2) * total_warps * sub_tile * (chunks * 2)) chunks *= 2;
+        while (chunks * 2 * lp.fx->tile_k <= lp.fx->rows_per_lane && uint64_t(lp.slab->capacity) >= uint64_t(2) * total_warps * sub_tile * (chunks * 2)) chunks *= 2;
     }
-    chunks = std::max(1u, std::min(chunks, kMaxRowsPerLane / lp.fx->tile_k));
+    chunks = std::max(1u, std::min(chunks, lp.fx->rows_per_lane / lp.fx->tile_k));
     const uint32_t tile = sub_tile * chunks;
     c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile;
 
@@ -496,15 +494,15 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     P.tile_rows = tile;
     lp.init_blocks = ceil_div(init_threads, 256);
     uint32_t max_tiles = lp.slab->capacity / tile + bi.prefix_sum_count + 1;
-    lp.update_blocks = std::min<uint32_t>(ceil_div(max_tiles, 8), uint32_t(lp.fx->km->update_blocks_per_sm) * uint32_t(c->sm_count));
+    lp.update_blocks = std::min<uint32_t>(ceil_div(max_tiles, 8), uint32_t(lp.fx->update_blocks_per_sm) * uint32_t(c->sm_count));
     if (lp.update_blocks == 0) lp.update_blocks = 1;
     if (lp.fx->props_size && !lp.fx->d_props) fail(HNB_ERR_NOT_READY, "effect uses properties but none were uploaded");
     return lp;
 }
 
-void launch_kernel(hnb_ctx* c, CUfunction f, uint32_t blocks, hnb::BatchParams& P) {
+void launch_kernel(hnb_ctx* c, CUfunction f, uint32_t blocks, hnb::BatchParams& P, uint32_t smem_bytes = 0) {
     void* args[] = {&P};
-    CUresult r = c->drv.LaunchKernel(f, blocks, 1, 1, 256, 1, 1, 0, (CUstream)c->stream, args, nullptr);
+    CUresult r = c->drv.LaunchKernel(f, blocks, 1, 1, 256, 1, 1, smem_bytes, (CUstream)c->stream, args, nullptr);
     if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuLaunchKernel: " + cu_error_string(c->drv, r));
     c->launches++;
 }
@@ -516,7 +514,7 @@ void launch_update(hnb_ctx* c, LaunchPlan& lp) {
         else { CUDA_CHECK(cudaEventCreate(&ev.first)); CUDA_CHECK(cudaEventCreate(&ev.second)); }
         CUDA_CHECK(cudaEventRecord(ev.first, c->stream));
     }
-    launch_kernel(c, lp.fx->km->update, lp.update_blocks, lp.params);
+    launch_kernel(c, lp.fx->km->update, lp.update_blocks, lp.params, lp.fx->update_smem);
     if (c->timing) {
         CUDA_CHECK(cudaEventRecord(ev.second, c->stream));
         c->ev_pending.push_back(ev);
@@ -831,6 +829,16 @@ int32_t hnb_effect_compile(hnb_ctx* c, const hnb_effect_desc* desc, hnb_effect* 
         fx.name = desc->name ? desc->name : "effect";
         fx.km = get_module(c, src, fx.name, fx.hash);
         fx.tile_k = choose_tile_k(*desc);
+        fx.rows_per_lane = rows_per_lane();
+        fx.update_smem = update_smem_bytes(*desc);
+        {
+            CUresult r = c->drv.FuncSetAttribute(fx.km->update, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)fx.update_smem);
+            if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem " + std::to_string(fx.update_smem) + "): " + cu_error_string(c->drv, r));
+            int bps = 0;
+            r = c->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&bps, fx.km->update, 256, fx.update_smem);
+            if (r != CUDA_SUCCESS || bps < 1) bps = 1;
+            fx.update_blocks_per_sm = bps;
+        }
         fx.flags = desc->flags;
         fx.particle_stride = desc->particle_stride;
         fx.parent_stride = desc->parent_particle_stride;

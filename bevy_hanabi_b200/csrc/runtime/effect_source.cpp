@@ -173,6 +173,25 @@ const char* nz(const char* s) { return s ? s : ""; }
 
 }  // namespace
 
+uint32_t rows_per_lane() {
+    // rows of a tile handled by one lane (tile <= 32 * rows_per_lane rows); HNB_ROWS_PER_LANE env for tuning
+    if (const char* e = getenv("HNB_ROWS_PER_LANE")) {
+        int v = atoi(e);
+        if (v >= 4 && v <= 64) return (uint32_t)v;
+    }
+    return 16;
+}
+
+uint32_t update_smem_bytes(const hnb_effect_desc& d) {
+    // must mirror the carve-up at the top of hnb_update (hnb_particle_kernels.cuh)
+    const uint32_t R = rows_per_lane(), warps = 8;
+    uint32_t bytes = (2047 + 1) * 4;
+    bytes += (R * 32 * 4 + R * 4) * 2 * warps;
+    bytes += 48 * warps;
+    if (d.properties_size) bytes += ((d.properties_size + 15) / 16 * 16) * warps;
+    return bytes;
+}
+
 uint32_t choose_tile_k(const hnb_effect_desc& d) {
     // rows per thread: keep (index + record) register footprint around 40 words
     uint32_t words = d.particle_stride / 4 + 1;
@@ -210,6 +229,7 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
     }
     o << "#define HNB_NUM_PLANES " << planes.size() << "\n";
     o << "#define HNB_TILE_K " << choose_tile_k(d) << "\n";
+    o << "#define HNB_ROWS_PER_LANE " << rows_per_lane() << "\n";
     o << "#define HNB_HAS_PROPERTIES " << (d.properties_size ? 1 : 0) << "\n";
     o << "#define HNB_CONSUME_EVENTS " << (consume ? 1 : 0) << "\n";
     o << "#define HNB_EMIT_EVENTS " << (emit ? 1 : 0) << "\n";

@@ -30,8 +30,11 @@ std::vector<Plane> cut_planes(uint32_t stride_bytes);
 
 // Update tiles are walked by one warp each: tile_rows = 32 lanes * k rows per lane * chunks. k is
 // chosen from the record size (register footprint) at compile time, the chunk count per launch.
-constexpr uint32_t kMaxRowsPerLane = 16;  // == HNB_ROWS_PER_LANE: tile_rows <= 32 * 16
+uint32_t rows_per_lane();  // == HNB_ROWS_PER_LANE of the generated kernels: tile_rows <= 32 * rows_per_lane()
 uint32_t choose_tile_k(const hnb_effect_desc& d);
+// Dynamic shared memory of hnb_update for this effect (tile-prefix table + per-warp double-buffered stash +
+// pending-tile records + Properties staging).
+uint32_t update_smem_bytes(const hnb_effect_desc& d);
 
 // The complete translation unit (throws std::invalid_argument on a bad description).
 std::string generate_effect_source(const hnb_effect_desc& d);
