@@ -114,7 +114,11 @@ class CpuC5:
         self.np, self.O = np, O
         self.orc = O.load()
         self.n = particles
-        self.threads = min(self.orc.orc_max_threads(), os.cpu_count() or 1)
+        try:
+            usable = len(os.sched_getaffinity(0))
+        except AttributeError:
+            usable = os.cpu_count() or 1
+        self.threads = max(1, min(self.orc.orc_max_threads(), usable))
         self.particles = np.empty((particles, 8), dtype=np.float32)
         self.indirect = np.zeros((particles, 3), dtype=np.uint32)
         self.indirect[:, 2] = np.arange(particles, dtype=np.uint32)

@@ -145,7 +145,6 @@ SIGNATURES = {
     "hnb_sync": (i32, [vp]),
     "hnb_ctx_stream": (C.c_size_t, [vp]),
     "hnb_ctx_launch_count": (C.c_uint64, [vp]),
-    "hnb_ctx_set_graphs": (i32, [vp, i32]),
     "hnb_slab_create": (i32, [vp, u32, u32, P(u32)]),
     "hnb_slab_destroy": (i32, [vp, u32]),
     "hnb_slab_reset_rows": (i32, [vp, u32, u32, u32]),

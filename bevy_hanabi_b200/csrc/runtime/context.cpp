@@ -143,7 +143,6 @@ struct hnb_ctx {
     bool own_stream = false;
     DriverApi drv;
     uint64_t launches = 0;
-    bool graphs = true;
 
     // per-frame arena (host pinned + device mirror), exact-size layout for (E, B)
     uint32_t E = 0, B = 0;
@@ -199,9 +198,6 @@ void ensure_arena(hnb_ctx* c, uint32_t E, uint32_t B) {
         char* nd = nullptr;
         CUDA_CHECK(cudaMalloc((void**)&nd, cap));
         CUDA_CHECK(cudaMemsetAsync(nd, 0, cap, c->stream));
-        if (c->h_arena) {
-            // repack below from the old arena
-        }
         // move: copy old host contents into the new buffer at the new offsets
         std::vector<char> old(c->h_arena ? c->lay.total : 0);
         if (c->h_arena) memcpy(old.data(), c->h_arena, c->lay.total);
@@ -626,10 +622,6 @@ int32_t hnb_sync(hnb_ctx* c) {
 }
 uintptr_t hnb_ctx_stream(hnb_ctx* c) { return (uintptr_t)c->stream; }
 uint64_t hnb_ctx_launch_count(hnb_ctx* c) { return c->launches; }
-int32_t hnb_ctx_set_graphs(hnb_ctx* c, int32_t enabled) {
-    c->graphs = enabled != 0;
-    return HNB_OK;
-}
 
 // ---- slabs ----------------------------------------------------------------------------------
 int32_t hnb_slab_create(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, hnb_slab* out) {

@@ -158,8 +158,6 @@ HNB_API int32_t hnb_sync(hnb_ctx* ctx);
 HNB_API uintptr_t hnb_ctx_stream(hnb_ctx* ctx);
 /** Number of kernels launched by this context since creation (for bench `gpu_launches`). */
 HNB_API uint64_t hnb_ctx_launch_count(hnb_ctx* ctx);
-/** Replay hnb_simulate through a captured CUDA graph when the launch list is unchanged (default 1). */
-HNB_API int32_t hnb_ctx_set_graphs(hnb_ctx* ctx, int32_t enabled);
 
 /* ------------------------------------------------------------------------------------ */
 /* 3. Particle slabs ≙ ParticleSlab::new (reference src/render/effect_cache.rs:246-356)  */
