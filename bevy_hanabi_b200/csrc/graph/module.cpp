@@ -9,6 +9,7 @@
 //   `let varN = e;`           -> `const auto varN = e;`
 //   `(a) % (b)`               -> `hnb_rem(a, b)`            (WGSL truncated remainder, also on floats)
 //   `vec2(a, b)` etc.         -> `make_vec2(a, b)`          (C++ cannot overload a class template name)
+//   `(a) * (b).x`             -> `((a) * (b)).x`            (swizzle of an infix operand: see Expr::Unary below)
 #include "hanabi_graph.h"
 
 namespace hnb_graph {
@@ -236,6 +237,11 @@ std::string Module::eval_expr(ExprHandle h, ShaderWriter& ctx) const {
             std::string inner = ctx.eval(*this, e.a);
             UnaryOperator op = (UnaryOperator)e.op;
             if (unary_is_functional(op)) return std::string(unary_name(op)) + "(" + inner + ")";
+            // Deliberate deviation: the reference pastes ".x" behind an infix operand's text ("(a) * (b).x",
+            // expr.rs:1146 with :1209), which binds the swizzle to the right operand only. The component of the
+            // whole operand is what the node's value_type() declares, so parenthesise.
+            const Expr& operand = expressions_[e.a - 1];
+            if (operand.kind == Expr::Binary && !binary_is_functional((BinaryOperator)operand.op)) inner = "(" + inner + ")";
             return inner + "." + unary_name(op);
         }
         case Expr::Binary: {

@@ -158,12 +158,17 @@ def _vt_count(vt):
     return 1 if vt < 4 else 2 + (vt - 4) % 3
 
 
-def literal_array(value, n):
-    """graph.Value -> broadcast array."""
+def literal_array(value, n, as_shader_text=True):
+    """graph.Value -> broadcast array. `as_shader_text`: the value is a literal embedded in shader code (properties
+    are uploaded as bytes and keep their exact bits)."""
     elem, cnt = _vt_elem(value.vt), _vt_count(value.vt)
     w = np.array(value.words, dtype=U32)
-    if elem == "f":
+    if elem == "f" and not as_shader_text:
         a = w.view(F32)
+    elif elem == "f":
+        # A float literal reaches the shader as TEXT with six decimals (ToWgslString for f32, src/lib.rs:264-269):
+        # the value the reference's GPU sees is the literal rounded to 1e-6, not the literal's own bits.
+        a = np.array([F32(float("%.6f" % float(x))) if np.isfinite(x) else x for x in w.view(F32)], dtype=F32)
     elif elem == "i":
         a = w.view(np.int32)
     elif elem == "b":
@@ -224,7 +229,7 @@ def ev(module, h: int, env: Env, wr: Writer):
             return env.parent_particle_index.astype(U32)
         return env.parent[node.attr.name]
     if k == "prop":
-        return literal_array(env.props[node.prop], n)
+        return literal_array(env.props[node.prop], n, as_shader_text=False)
     if k == "builtin":
         if node.op == "rand":
             if _vt_elem(node.vt) != "f":

@@ -369,3 +369,20 @@ def test_numpy_oracle_equals_c_oracle_on_c5(orc):
         np.testing.assert_array_equal(a.metadata_rows(), b.metadata_rows())
         np.testing.assert_array_equal(a.draw, b.draw)
     assert a.metadata[0].alive_count < 1200
+
+
+def test_swizzle_of_infix_expression_is_parenthesised():
+    """`(a * b).x`: the reference's text `(a) * (b).x` (expr.rs:1146 + :1209) swizzles only the right operand; the
+    CUDA lowering takes the component of the whole product, as the node's value type declares."""
+    w = G.ExprWriter()
+    e = (w.attr(G.Attribute.VELOCITY) * w.lit(0.5)).x()
+    asset = (G.EffectAsset(8, w.module).init(G.SetAttributeModifier(G.Attribute.POSITION, w.lit(G.Vec3(0, 0, 0))))
+             .update(G.SetAttributeModifier(G.Attribute.F32_0, e)))
+    code = asset.generate().update_code
+    assert "particle.f32_0 = ((particle.velocity) * (0.5f)).x;" in code
+    # swizzles of anything that is already a primary expression stay as the reference writes them
+    w2 = G.ExprWriter()
+    e2 = w2.attr(G.Attribute.VELOCITY).max(w2.attr(G.Attribute.POSITION)).y()
+    a2 = (G.EffectAsset(8, w2.module).init(G.SetAttributeModifier(G.Attribute.POSITION, w2.lit(G.Vec3(0, 0, 0))))
+          .update(G.SetAttributeModifier(G.Attribute.F32_0, e2)))
+    assert "particle.f32_0 = max(particle.velocity, particle.position).y;" in a2.generate().update_code

@@ -70,3 +70,22 @@ def test_oracle_runs_all_gpu_scenarios_shapes(orc):
     # circle of radius 2 around `center` in the z = 0 plane
     d = pos[:, :2] - np.array([0.5, -0.25], dtype=np.float32)
     assert np.all(np.abs(pos[:, 2]) < 0.2)
+
+
+def test_float_literals_are_seen_through_six_decimals():
+    """The reference embeds f32 literals as `{:.6}` text (src/lib.rs:264-269): both the generated CUDA code and the
+    oracle must evaluate with the rounded value; properties travel as bytes and keep every bit."""
+    from oracle.hanabi_oracle import literal_array
+    x = float(np.float32(1.018241286277771))
+    w = G.ExprWriter()
+    e = w.lit(x).fract()
+    asset = (G.EffectAsset(8, w.module).init(G.SetAttributeModifier(G.Attribute.POSITION, w.lit(G.Vec3(0, 0, 0))))
+             .update(G.SetAttributeModifier(G.Attribute.F32_0, e)))
+    assert "fract(1.018241f)" in asset.generate().update_code
+    lit = [nd for nd in w.module.nodes if nd.kind == "lit"][0]
+    assert literal_array(lit.value, 1)[0] == np.float32(1.018241)
+    assert literal_array(lit.value, 1)[0] != np.float32(x)
+    assert literal_array(lit.value, 1, as_shader_text=False)[0] == np.float32(x)
+    w.lit(-1e-8)
+    v = literal_array(w.module.nodes[-1].value, 1)[0]
+    assert v == 0 and np.signbit(v)  # "-0.f"
