@@ -122,6 +122,7 @@ EFFECT_CONSUME_GPU_SPAWN_EVENTS = 1 << 1
 EFFECT_EMIT_GPU_SPAWN_EVENTS = 1 << 2
 EFFECT_READ_PARENT_PARTICLE = 1 << 3
 EFFECT_RELAXED_ORDER = 1 << 4
+EFFECT_RIBBONS = 1 << 5
 
 
 def _load() -> C.CDLL:
@@ -174,6 +175,7 @@ SIGNATURES = {
     "hnb_pass_indirect": (i32, [vp]),
     "hnb_pass_prefix_sum": (i32, [vp]),
     "hnb_pass_update": (i32, [vp, P(BatchLaunch)]),
+    "hnb_pass_sort": (i32, [vp, P(BatchLaunch)]),
     "hnb_pass_fill_dispatch_args": (i32, [vp, P(u32), u32, u32, P(u32), u32, u32, u32, u32]),
     "hnb_read_metadata": (i32, [vp, u32, P(EffectMetadata)]),
     "hnb_read_draw_args": (i32, [vp, u32, P(DrawIndexedIndirectArgs)]),

@@ -366,6 +366,7 @@ EffectShaderSource EffectAsset::generate(const ParticleLayout* parent_layout, ui
     uint32_t flags = 0;
     if (simulation_space == SimulationSpace::Local) flags |= HNB_EFFECT_LOCAL_SPACE;
     if (parent_layout) flags |= HNB_EFFECT_READ_PARENT_PARTICLE;
+    if (out.particle_layout.contains(attr::RIBBON_ID)) flags |= HNB_EFFECT_RIBBONS;  // lib.rs:1018-1019
 
     // init (lib.rs:1026-1069)
     bool consume = false;

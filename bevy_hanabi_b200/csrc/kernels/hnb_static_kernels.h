@@ -33,6 +33,27 @@ struct PlaneSet {
     unsigned char word_to_plane[HNB_MAX_PLANES * 4];
 };
 
+// Ribbon sort of one batch (hnb_ribbon_sort.cu): every instance of the batch has its freshly written alive-list
+// column stably sorted by (particle[sort_key_offset], particle[sort_key2_offset]).
+#define HNB_RIBBON_SORT_SMALL_MAX 2048u
+struct RibbonSortArgs {
+    PlaneSet planes;            // particle planes of the slab
+    u32* ping;                  // alive-list columns of the slab (row 0 of the slab)
+    u32* pong;
+    const Spawner* spawners;
+    const EffectMetadata* metadata;
+    u32 spawner_base;           // first instance of the batch (BatchInfo::spawner_base)
+    u32 instance_count;         // BatchInfo::prefix_sum_count
+    // scratch of the large path (unused when every instance has <= HNB_RIBBON_SORT_SMALL_MAX rows)
+    u64* scratch_keys[2];
+    u32* scratch_vals[2];
+    u32* scratch_hist;          // ribbon_sort_hist_words(scratch_grid) words; the first 2*8*256 zero at launch
+    u32 scratch_rows;
+    u32 scratch_grid;
+};
+cudaError_t launch_ribbon_sort(const RibbonSortArgs& args, bool any_large, u32 sm_count, cudaStream_t st, u32* launches);
+size_t ribbon_sort_hist_words(u32 grid);
+
 cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t st);
 cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st);
 cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile, cudaStream_t st);

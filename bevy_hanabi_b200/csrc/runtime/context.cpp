@@ -176,6 +176,11 @@ struct hnb_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
     double update_ms = 0.0;
     uint64_t update_launches = 0;
+    // ribbon sort scratch (large path), sized to the largest ribbon slab seen so far
+    uint64_t* d_sort_keys[2] = {nullptr, nullptr};
+    uint32_t* d_sort_vals[2] = {nullptr, nullptr};
+    uint32_t* d_sort_hist = nullptr;
+    uint32_t sort_rows = 0;
     uint32_t tile_chunks_override = 0;  // HNB_TILE_CHUNKS env: fixed sub-tile count per tile (tuning)
     unsigned long long* d_debug = nullptr;  // 16 diagnostic counters (HNB_PROFILE kernels)
 
@@ -517,6 +522,43 @@ void launch_update(hnb_ctx* c, LaunchPlan& lp) {
     }
 }
 
+// Ribbon sort of one batch ("hanabi:sort" fill / sort / copy, mod.rs:7444-7610): every instance of the batch gets
+// the alive-list column the update pass just wrote stably sorted by (RIBBON_ID, AGE bits).
+void launch_ribbon_sort(hnb_ctx* c, const LaunchPlan& lp) {
+    const hnb_batch_info& bi = c->h_at<hnb_batch_info>(c->lay.off_batch_infos)[lp.batch];
+    const bool any_large = lp.slab->capacity > HNB_RIBBON_SORT_SMALL_MAX;
+    if (any_large && c->sort_rows < lp.slab->capacity) {
+        if (c->sort_rows) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->d_sort_keys[i]); cudaFree(c->d_sort_vals[i]);
+            c->d_sort_keys[i] = nullptr; c->d_sort_vals[i] = nullptr;
+        }
+        c->sort_rows = 0;
+        for (int i = 0; i < 2; ++i) {
+            CUDA_CHECK(cudaMalloc((void**)&c->d_sort_keys[i], size_t(lp.slab->capacity) * 8));
+            CUDA_CHECK(cudaMalloc((void**)&c->d_sort_vals[i], size_t(lp.slab->capacity) * 4));
+        }
+        if (!c->d_sort_hist) CUDA_CHECK(cudaMalloc((void**)&c->d_sort_hist, hnb::ribbon_sort_hist_words(uint32_t(c->sm_count)) * 4));
+        c->sort_rows = lp.slab->capacity;
+    }
+    hnb::RibbonSortArgs a{};
+    a.planes = plane_set(*lp.slab);
+    a.ping = lp.slab->ping;
+    a.pong = lp.slab->pong;
+    a.spawners = c->d_at<hnb::Spawner>(c->lay.off_spawners);
+    a.metadata = c->d_metadata;
+    a.spawner_base = bi.spawner_base;
+    a.instance_count = bi.prefix_sum_count;
+    for (int i = 0; i < 2; ++i) { a.scratch_keys[i] = (u64*)c->d_sort_keys[i]; a.scratch_vals[i] = c->d_sort_vals[i]; }
+    a.scratch_hist = c->d_sort_hist;
+    a.scratch_rows = c->sort_rows;
+    a.scratch_grid = uint32_t(c->sm_count);
+    if (any_large) CUDA_CHECK(cudaMemsetAsync(c->d_sort_hist, 0, size_t(2 * 8 * 256) * 4, c->stream));
+    uint32_t launched = 0;
+    CUDA_CHECK(hnb::launch_ribbon_sort(a, any_large, uint32_t(c->sm_count), c->stream, &launched));
+    c->launches += launched;
+}
+
 void check_coverage(hnb_ctx* c, const std::vector<LaunchPlan>& plans) {
     // the fused bookkeeping kernel visits instances batch by batch: the launched batches must tile
     // [0, num_effects) exactly (Batcher::push allocates spawners and prefix entries in sync)
@@ -612,6 +654,8 @@ void hnb_ctx_destroy(hnb_ctx* c) {
     if (c->d_arena) cudaFree(c->d_arena);
     cudaFree(c->d_metadata); cudaFree(c->d_draw_args); cudaFree(c->d_child_infos);
     cudaFree(c->d_debug);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_sort_keys[i]); cudaFree(c->d_sort_vals[i]); }
+    cudaFree(c->d_sort_hist);
     cudaFree(c->d_tile_prefix); cudaFree(c->d_dispatch_args); cudaFree(c->d_batch_tiles); cudaFree(c->d_tickets);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1004,6 +1048,26 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         c->launches += 1 + (c->child_rows ? 1 : 0);
         // pass "hanabi:update" (mod.rs:7280-7370)
         for (auto& lp : plans) launch_update(c, lp);
+        // ribbons: passes "hanabi:sort_prefix_sum" (the reference re-runs vfx_prefix_sum over every batch,
+        // mod.rs:7393-7428) and "hanabi:sort" (mod.rs:7444-7610)
+        bool needs_sort = false;
+        for (auto& lp : plans) needs_sort |= (lp.fx->flags & HNB_EFFECT_RIBBONS) != 0;
+        if (needs_sort) {
+            CUDA_CHECK(hnb::launch_prefix_sum(static_tables(c), c->B, c->stream));
+            c->launches += c->B ? 1 : 0;
+            for (auto& lp : plans)
+                if (lp.fx->flags & HNB_EFFECT_RIBBONS) launch_ribbon_sort(c, lp);
+        }
+    });
+}
+
+int32_t hnb_pass_sort(hnb_ctx* c, const hnb_batch_launch* b) {
+    return guarded([&] {
+        if (!b) fail(HNB_ERR_INVALID_ARG, "batch is NULL");
+        ensure_scratch(c);
+        LaunchPlan lp = plan_batch(c, *b, false);
+        flush_arena(c, false);
+        launch_ribbon_sort(c, lp);
     });
 }
 

@@ -318,6 +318,10 @@ class Context:
     def pass_update(self, launch: BatchLaunch) -> None:
         check(lib.hnb_pass_update(self._h, C.byref(launch)))
 
+    def pass_sort(self, launch: BatchLaunch) -> None:
+        """Ribbon sort of every instance of the batch (vfx_sort_fill / vfx_sort / vfx_sort_copy)."""
+        check(lib.hnb_pass_sort(self._h, C.byref(launch)))
+
     def pass_fill_dispatch_args(self, src: Sequence[int], src_offset: int, src_stride: int, dst: Sequence[int],
                                 dst_offset: int, dst_stride: int, count: int) -> list[int]:
         s = (N.u32 * max(1, len(src)))(*src)

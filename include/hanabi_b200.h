@@ -233,8 +233,10 @@ enum {
     HNB_EFFECT_CONSUME_GPU_SPAWN_EVENTS = 1u << 1,
     HNB_EFFECT_EMIT_GPU_SPAWN_EVENTS = 1u << 2,
     HNB_EFFECT_READ_PARENT_PARTICLE = 1u << 3,
-    HNB_EFFECT_RELAXED_ORDER = 1u << 4         /* alive/dead lists in atomic order (sets exact,
+    HNB_EFFECT_RELAXED_ORDER = 1u << 4,        /* alive/dead lists in atomic order (sets exact,
                                                   order scheduling-dependent like the reference) */
+    HNB_EFFECT_RIBBONS = 1u << 5               /* LayoutFlags::RIBBONS (lib.rs:1018-1019): the layout has RIBBON_ID;
+                                                  hnb_simulate() sorts the alive list by (RIBBON_ID, AGE) after the update */
 };
 
 /**
@@ -319,7 +321,8 @@ typedef struct hnb_batch_launch {
 
 /**
  * Enqueue one simulation frame: init (per batch with spawns) → indirect + prefix-sum (one fused
- * bookkeeping kernel) → update (per batch). Asynchronous on the context stream.
+ * bookkeeping kernel) → update (per batch) → for HNB_EFFECT_RIBBONS batches the second prefix-sum pass and
+ * the ribbon sort. Asynchronous on the context stream.
  */
 HNB_API int32_t hnb_simulate(hnb_ctx* ctx, const hnb_batch_launch* batches, uint32_t n);
 
@@ -329,6 +332,10 @@ HNB_API int32_t hnb_pass_init(hnb_ctx* ctx, const hnb_batch_launch* batch);
 HNB_API int32_t hnb_pass_indirect(hnb_ctx* ctx);                       /* vfx_indirect.wgsl */
 HNB_API int32_t hnb_pass_prefix_sum(hnb_ctx* ctx);                     /* vfx_prefix_sum.wgsl */
 HNB_API int32_t hnb_pass_update(hnb_ctx* ctx, const hnb_batch_launch* batch); /* vfx_update.wgsl */
+/** vfx_sort_fill.wgsl + vfx_sort.wgsl + vfx_sort_copy.wgsl for every instance of the batch (mod.rs:7444-7610):
+ *  the alive-list column `indirect_write_index` of each instance is stably sorted by the particle words
+ *  (sort_key_offset, sort_key2_offset) of its metadata row — RIBBON_ID, then AGE bits, compared as u32. */
+HNB_API int32_t hnb_pass_sort(hnb_ctx* ctx, const hnb_batch_launch* batch);
 /** vfx_utils.wgsl::fill_dispatch_args over host-provided arrays (round-trips through the GPU). */
 HNB_API int32_t hnb_pass_fill_dispatch_args(hnb_ctx* ctx, const uint32_t* src, uint32_t src_offset,
                                             uint32_t src_stride, uint32_t* dst, uint32_t dst_len,

@@ -76,6 +76,12 @@ def load() -> C.CDLL:
     lib.orc_prefix_sum.argtypes = [P(BatchInfo), u32, P(u32), P(u32)]
     lib.orc_fill_dispatch_args.restype = None
     lib.orc_fill_dispatch_args.argtypes = [P(u32), P(u32), u32, u32, u32, u32, u32]
+    lib.orc_sort_fill.restype = None
+    lib.orc_sort_fill.argtypes = [P(C.c_int32), vp, vp, vp, P(EffectMetadata), P(Spawner), u32]
+    lib.orc_sort.restype = None
+    lib.orc_sort.argtypes = [P(C.c_int32), vp]
+    lib.orc_sort_copy.restype = None
+    lib.orc_sort_copy.argtypes = [vp, vp, P(EffectMetadata), P(Spawner), u32]
     lib.orc_update.restype = None
     lib.orc_update.argtypes = [P(SimParams), P(u32), vp, u32, vp, P(Spawner), P(u32), P(BatchInfo), P(EffectMetadata),
                                u32, vp, vp]

@@ -659,10 +659,12 @@ class EffectOracle:
             self.last_emitted = env.emitted
 
     def frame(self, world, orc_c):
-        """init -> indirect -> prefix sum -> update, bookkeeping passes by the C oracle."""
+        """init -> indirect -> prefix sum -> update [-> ribbon sort], bookkeeping passes by the C oracle."""
         for b in range(len(world.batches)):
             self.init_pass(world, b)
         world.oracle_indirect(orc_c)
         world.oracle_prefix_sum(orc_c)
         for b in range(len(world.batches)):
             self.update_pass(world, b)
+        if "ribbon_id" in self.names:  # LayoutFlags::RIBBONS (lib.rs:1018-1019) -> sort passes (mod.rs:7372-7610)
+            world.oracle_sort_ribbons(orc_c)

@@ -11,6 +11,7 @@
  *     vfx_indirect main                       src/render/vfx_indirect.wgsl:31-90
  *     vfx_prefix_sum main                     src/render/vfx_prefix_sum.wgsl:14-43
  *     fill_dispatch_args                      src/render/vfx_utils.wgsl:54-67
+ *     ribbon sort: fill / sort / copy         src/render/vfx_sort_fill.wgsl, vfx_sort.wgsl, vfx_sort_copy.wgsl
  *     vfx_init main (structure)               src/render/vfx_init.wgsl:101-196
  *     vfx_update main (structure)             src/render/vfx_update.wgsl:106-167
  *     the generated update body of config C5  src/lib.rs:1223-1281, src/modifier/accel.rs:79-86,
@@ -200,6 +201,65 @@ ORC_API void orc_fill_dispatch_args(const uint32_t* src_buffer, uint32_t* dst_bu
         dst_buffer[dst] = (thread_count + 63u) >> 6u;
         dst_buffer[dst + 1u] = 1u;
         dst_buffer[dst + 2u] = 1u;
+    }
+}
+
+/* ---- ribbon sort (vfx_sort_fill.wgsl:38-57, vfx_sort.wgsl:18-55, vfx_sort_copy.wgsl:30-46) --------------
+ * Three dispatches per ribbon effect instance, run after the update pass (mod.rs:7444-7610). The sort
+ * buffer is `count` followed by {key, key2, value} triples (HAS_DUAL_KEY is always defined, sort.rs:163,:364).
+ * Fill threads run in ascending thread index (canonical order; the reference appends with an atomic).
+ * "parity unpinned": no reference test executes these shaders. */
+typedef struct {
+    uint32_t key, key2, value;
+} orc_key_value_pair;
+
+ORC_API void orc_sort_fill(int32_t* sort_count, orc_key_value_pair* pairs, const uint32_t* particle_buffer,
+                           const uint32_t* indirect_index_buffer, const orc_effect_metadata* effect_metadata,
+                           const orc_spawner* spawner, uint32_t thread_count) {
+    for (uint32_t thread_index = 0; thread_index < thread_count; ++thread_index) {
+        uint32_t count = effect_metadata->alive_count;
+        if (thread_index >= count) continue;
+        uint32_t base_particle = spawner->slab_offset;
+        uint32_t read_index = effect_metadata->indirect_write_index;
+        uint32_t particle_index = indirect_index_buffer[(base_particle + thread_index) * 3u + read_index];
+        uint32_t particle_offset = (base_particle + particle_index) * effect_metadata->particle_stride;
+        uint32_t key_offset = particle_offset + effect_metadata->sort_key_offset;
+        uint32_t key2_offset = particle_offset + effect_metadata->sort_key2_offset;
+        int32_t pair_index = (*sort_count)++;
+        pairs[pair_index].key = particle_buffer[key_offset];
+        pairs[pair_index].key2 = particle_buffer[key2_offset];
+        pairs[pair_index].value = particle_index;
+    }
+}
+
+static int compare_greater(orc_key_value_pair kv1, orc_key_value_pair kv2) {
+    if (kv1.key > kv2.key) return 1;
+    if (kv1.key == kv2.key) return kv1.key2 > kv2.key2;
+    return 0;
+}
+
+ORC_API void orc_sort(int32_t* sort_count, orc_key_value_pair* pairs) {
+    int32_t num_items = *sort_count;
+    for (int32_t i = 1; i < num_items; ++i) {
+        orc_key_value_pair kv = pairs[i];
+        int32_t j = i;
+        while (j > 0 && compare_greater(pairs[j - 1], kv)) {
+            pairs[j] = pairs[j - 1];
+            j -= 1;
+        }
+        pairs[j] = kv;
+    }
+    *sort_count = 0;
+}
+
+ORC_API void orc_sort_copy(uint32_t* indirect_index_buffer, const orc_key_value_pair* pairs,
+                           const orc_effect_metadata* effect_metadata, const orc_spawner* spawner, uint32_t thread_count) {
+    for (uint32_t row_index = 0; row_index < thread_count; ++row_index) {
+        uint32_t count = effect_metadata->alive_count;
+        if (row_index >= count) continue;
+        uint32_t base_particle = spawner->slab_offset;
+        uint32_t write_index = effect_metadata->indirect_write_index;
+        indirect_index_buffer[(base_particle + row_index) * 3u + write_index] = pairs[row_index].value;
     }
 }
 

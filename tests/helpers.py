@@ -125,6 +125,39 @@ class RefWorld:
                        self.prefix.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(self.batch_infos[b]), self.metadata,
                        threads, body, user)
 
+    def set_sort_keys(self, fields):
+        """Ribbon effects: sort_key_offset / sort_key2_offset = word offsets of RIBBON_ID / AGE (mod.rs:6037-6046).
+        `fields`: the (name, offset, ...) records of asset.particle_layout()."""
+        off = {f.name: f.offset // 4 for f in fields}
+        for m in self.metadata:
+            m.sort_key_offset = off["ribbon_id"]
+            m.sort_key2_offset = off["age"]
+
+    def oracle_sort_ribbons(self, orc, literal: bool | None = None):
+        """Passes "hanabi:sort_prefix_sum" + per instance fill / sort / copy (mod.rs:7372-7610). `literal` runs
+        the restated insertion sort (O(n^2)); otherwise a stable numpy sort of the same (key, key2) pairs."""
+        self.oracle_prefix_sum(orc)  # the reference re-runs vfx_prefix_sum over every batch before sorting
+        flat = self.indirect.reshape(-1)
+        for i in range(len(self.instances)):
+            md, sp = self.metadata[i], self.spawners[i]
+            n = md.alive_count
+            use_literal = literal if literal is not None else n <= 3000
+            if use_literal:
+                count = C.c_int32(0)
+                pairs = np.zeros((max(n, 1), 3), dtype=np.uint32)
+                threads = (n + 63) // 64 * 64
+                orc.orc_sort_fill(C.byref(count), O.ptr(pairs), O.ptr(self.particles), O.ptr(flat), C.byref(md), C.byref(sp), threads)
+                assert count.value == n
+                orc.orc_sort(C.byref(count), O.ptr(pairs))
+                orc.orc_sort_copy(O.ptr(flat), O.ptr(pairs), C.byref(md), C.byref(sp), threads)
+            else:
+                col, base = md.indirect_write_index, sp.slab_offset
+                e = self.indirect[base:base + n, col].astype(np.int64)
+                key = self.particles[base + e, md.sort_key_offset]
+                key2 = self.particles[base + e, md.sort_key2_offset]
+                order = np.lexsort((key2, key))  # stable, last key is the primary one
+                self.indirect[base:base + n, col] = e[order].astype(np.uint32)
+
     def oracle_frame(self, orc, update_body, update_user=None, init_body=None, init_user=None):
         """init -> indirect -> prefix sum -> update (simulate(), mod.rs:7025-7370)."""
         if init_body is not None:

@@ -89,3 +89,36 @@ def test_float_literals_are_seen_through_six_decimals():
     w.lit(-1e-8)
     v = literal_array(w.module.nodes[-1].value, 1)[0]
     assert v == 0 and np.signbit(v)  # "-0.f"
+
+
+def test_ribbon_sort_restatement_equals_stable_sort(orc):
+    """The literal restatement of vfx_sort_fill / vfx_sort (insertion sort) / vfx_sort_copy and the vectorised
+    stable sort used for large instances are the same function (ties keep the alive list's order)."""
+    rng = np.random.default_rng(5)
+    for n, cap, base in ((0, 8, 0), (1, 8, 3), (2, 8, 0), (257, 400, 16), (1500, 1600, 5)):
+        worlds = []
+        for literal in (True, False):
+            ref = RefWorld(base + cap, 6, [Instance(base, cap, alive=n)])
+            r2 = np.random.default_rng(n)
+            ref.particles[:] = r2.integers(0, 2**32, ref.particles.shape, dtype=np.uint32)
+            ref.particles[:, 4] = r2.integers(0, 4, base + cap, dtype=np.uint32)                      # key: few ribbons
+            ref.particles[:, 1] = r2.choice(np.array([0.0, 0.5, 1.0], dtype=np.float32), base + cap).view(np.uint32)  # key2: ties
+            ref.indirect[:] = r2.integers(0, 2**32, ref.indirect.shape, dtype=np.uint32)
+            ref.indirect[base:base + n, 1] = r2.permutation(cap)[:n]
+            ref.metadata[0].indirect_write_index = 1
+            ref.metadata[0].sort_key_offset, ref.metadata[0].sort_key2_offset = 4, 1
+            before = ref.indirect.copy()
+            ref.oracle_sort_ribbons(orc, literal=literal)
+            untouched = np.ones_like(before, dtype=bool)
+            untouched[base:base + n, 1] = False
+            np.testing.assert_array_equal(ref.indirect[untouched], before[untouched])
+            assert sorted(ref.indirect[base:base + n, 1].tolist()) == sorted(before[base:base + n, 1].tolist())
+            worlds.append(ref.indirect.copy())
+        np.testing.assert_array_equal(worlds[0], worlds[1], err_msg=f"n={n}")
+
+
+def test_ribbon_layout_sets_the_ribbons_flag():
+    from bevy_hanabi_b200 import _native as N
+    from tests.test_gpu_ribbons import _ribbon_asset
+    assert _ribbon_asset(16).generate().flags & N.EFFECT_RIBBONS
+    assert not E._firework_trails(16).generate().flags & N.EFFECT_RIBBONS
