@@ -293,6 +293,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
     const u32 warp = tid >> 5u;
+#if HNB_PROFILE
+    if (lane == 0 && P.debug) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&P.debug[8], ~_g); }
+#endif
 
     const BatchInfo bi = *P.batch_info;
     const u32 n_effects = bi.prefix_sum_count;
@@ -346,6 +349,11 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     long long prof_t0 = clock64(), prof_pass1 = 0, prof_compact = 0, prof_tiles = 0;
     const long long prof_start = prof_t0;
 #define HNB_PROF_MARK(acc) { const long long _t = clock64(); acc += _t - prof_t0; prof_t0 = _t; }
+    // timeline (ns, %globaltimer): [8] = ~(earliest warp start) [9] latest first ticket [10] latest end of a warp's
+    // first pass 1 [11] latest warp end [12] = ~(earliest end of a first pass 1) [13] = ~(earliest warp end)
+#define HNB_PROF_TIME(slot, invert) if (lane == 0 && P.debug) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&P.debug[slot], (invert) ? ~_g : _g); }
+    bool prof_first = true;
+    HNB_PROF_TIME(9, false)
 #else
 #define HNB_PROF_MARK(acc)
 #endif
@@ -452,6 +460,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, tile == inst_first_tile ? HNB_FLAG_PREFIX : HNB_FLAG_AGGREGATE, tile_alive));
 #endif
         HNB_PROF_MARK(prof_pass1)
+#if HNB_PROFILE
+        if (prof_first) { HNB_PROF_TIME(10, false) HNB_PROF_TIME(12, true) prof_first = false; }
+#endif
 
         // Request the next tile now; the atomic's round trip hides behind the compaction below.
         u32 next_tile = 0u;
@@ -510,6 +521,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         atomicAdd(&P.debug[5], 1ull);  // warps
         atomicMax(&P.debug[6], (unsigned long long)(clock64() - prof_start));  // longest-lived warp (cycles)
     }
+    HNB_PROF_TIME(11, false) HNB_PROF_TIME(13, true)
 #endif
 }
 

@@ -176,6 +176,11 @@ struct hnb_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
     double update_ms = 0.0;
     uint64_t update_launches = 0;
+    // side streams: the update (and independent init) launches of a multi-batch frame run concurrently
+    std::vector<cudaStream_t> side_streams;
+    std::vector<cudaEvent_t> side_done;
+    cudaEvent_t fork_event = nullptr;
+    uint32_t max_side_streams = 7;  // HNB_SIDE_STREAMS env (0 = everything on the context stream)
     // ribbon sort scratch (large path), sized to the largest ribbon slab seen so far
     uint64_t* d_sort_keys[2] = {nullptr, nullptr};
     uint32_t* d_sort_vals[2] = {nullptr, nullptr};
@@ -501,26 +506,62 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     return lp;
 }
 
-void launch_kernel(hnb_ctx* c, CUfunction f, uint32_t blocks, hnb::BatchParams& P, uint32_t smem_bytes = 0) {
+void launch_kernel(hnb_ctx* c, CUfunction f, uint32_t blocks, hnb::BatchParams& P, uint32_t smem_bytes = 0, cudaStream_t st = nullptr) {
     void* args[] = {&P};
-    CUresult r = c->drv.LaunchKernel(f, blocks, 1, 1, 256, 1, 1, smem_bytes, (CUstream)c->stream, args, nullptr);
+    CUresult r = c->drv.LaunchKernel(f, blocks, 1, 1, 256, 1, 1, smem_bytes, (CUstream)(st ? st : c->stream), args, nullptr);
     if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuLaunchKernel: " + cu_error_string(c->drv, r));
     c->launches++;
 }
 
-void launch_update(hnb_ctx* c, LaunchPlan& lp) {
+void launch_update(hnb_ctx* c, LaunchPlan& lp, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
     std::pair<cudaEvent_t, cudaEvent_t> ev{};
     if (c->timing) {
         if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); }
         else { CUDA_CHECK(cudaEventCreate(&ev.first)); CUDA_CHECK(cudaEventCreate(&ev.second)); }
-        CUDA_CHECK(cudaEventRecord(ev.first, c->stream));
+        CUDA_CHECK(cudaEventRecord(ev.first, st));
     }
-    launch_kernel(c, lp.fx->km->update, lp.update_blocks, lp.params, lp.fx->update_smem);
+    launch_kernel(c, lp.fx->km->update, lp.update_blocks, lp.params, lp.fx->update_smem, st);
     if (c->timing) {
-        CUDA_CHECK(cudaEventRecord(ev.second, c->stream));
+        CUDA_CHECK(cudaEventRecord(ev.second, st));
         c->ev_pending.push_back(ev);
     }
 }
+
+// Fork / join of the context stream for the independent launches of one pass. The reference records one
+// dispatch per batch into a single compute pass (mod.rs:7280-7370) and leaves the overlap to the driver; here
+// launch k goes to lane k % lanes (lane 0 = the context stream itself). Small batches are latency-bound
+// (a few microseconds of work behind ~10 of launch and pipeline ramp), so concurrency is what fills the GPU.
+struct Fork {
+    hnb_ctx* c;
+    uint32_t lanes = 1;
+    Fork(hnb_ctx* ctx, uint32_t launches) : c(ctx) {
+        if (c->max_side_streams == 0 || launches < 2) return;
+        lanes = std::min<uint32_t>(launches, c->max_side_streams + 1);
+        while (c->side_streams.size() < lanes - 1) {
+            cudaStream_t s = nullptr;
+            cudaEvent_t e = nullptr;
+            CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->side_streams.push_back(s);
+            c->side_done.push_back(e);
+        }
+        if (!c->fork_event) CUDA_CHECK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(c->fork_event, c->stream));
+        for (uint32_t i = 0; i + 1 < lanes; ++i) CUDA_CHECK(cudaStreamWaitEvent(c->side_streams[i], c->fork_event, 0));
+    }
+    cudaStream_t lane(uint32_t k) const {
+        const uint32_t l = k % lanes;
+        return l == 0 ? c->stream : c->side_streams[l - 1];
+    }
+    void join() {
+        for (uint32_t i = 0; i + 1 < lanes; ++i) {
+            CUDA_CHECK(cudaEventRecord(c->side_done[i], c->side_streams[i]));
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->side_done[i], 0));
+        }
+        lanes = 1;
+    }
+};
 
 // Ribbon sort of one batch ("hanabi:sort" fill / sort / copy, mod.rs:7444-7610): every instance of the batch gets
 // the alive-list column the update pass just wrote stably sorted by (RIBBON_ID, AGE bits).
@@ -624,6 +665,7 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
             c->own_stream = true;
         }
         if (const char* e = getenv("HNB_TILE_CHUNKS")) c->tile_chunks_override = (uint32_t)atoi(e);
+        if (const char* e = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::min(atoi(e), 31);
         ensure_arena(c.get(), 0, 0);
         CUDA_CHECK(cudaMalloc((void**)&c->d_debug, 16 * 8));
         CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
@@ -654,6 +696,9 @@ void hnb_ctx_destroy(hnb_ctx* c) {
     if (c->d_arena) cudaFree(c->d_arena);
     cudaFree(c->d_metadata); cudaFree(c->d_draw_args); cudaFree(c->d_child_infos);
     cudaFree(c->d_debug);
+    for (auto st : c->side_streams) cudaStreamDestroy(st);
+    for (auto e : c->side_done) cudaEventDestroy(e);
+    if (c->fork_event) cudaEventDestroy(c->fork_event);
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_sort_keys[i]); cudaFree(c->d_sort_vals[i]); }
     cudaFree(c->d_sort_hist);
     cudaFree(c->d_tile_prefix); cudaFree(c->d_dispatch_args); cudaFree(c->d_batch_tiles); cudaFree(c->d_tickets);
@@ -1040,14 +1085,32 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         check_coverage(c, plans);  // nothing has been enqueued yet: a bad frame is skipped as a whole
         next_epoch(c);
         flush_arena(c, true);
-        // pass "hanabi:init" (mod.rs:7025-7179)
-        for (auto& lp : plans)
-            if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params);
+        // pass "hanabi:init" (mod.rs:7025-7179). Batches write disjoint slab rows and table rows; the only
+        // cross-batch access is a child reading its parent's records, so frames with event-driven children keep
+        // the reference's serial order.
+        {
+            uint32_t inits = 0;
+            bool reads_parent = false;
+            for (auto& lp : plans) {
+                inits += lp.init_blocks ? 1 : 0;
+                reads_parent |= (lp.fx->flags & (HNB_EFFECT_READ_PARENT_PARTICLE | HNB_EFFECT_CONSUME_GPU_SPAWN_EVENTS)) != 0;
+            }
+            Fork fork(c, reads_parent ? 1 : inits);
+            uint32_t k = 0;
+            for (auto& lp : plans)
+                if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params, 0, fork.lane(k++));
+            fork.join();
+        }
         // passes "hanabi:indirect_dispatch" + "hanabi:update_prefix_sum" (mod.rs:7182-7275), fused
         CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, c->stream));
         c->launches += 1 + (c->child_rows ? 1 : 0);
-        // pass "hanabi:update" (mod.rs:7280-7370)
-        for (auto& lp : plans) launch_update(c, lp);
+        // pass "hanabi:update" (mod.rs:7280-7370): batches are independent (event appends are atomic)
+        {
+            Fork fork(c, uint32_t(plans.size()));
+            uint32_t k = 0;
+            for (auto& lp : plans) launch_update(c, lp, fork.lane(k++));
+            fork.join();
+        }
         // ribbons: passes "hanabi:sort_prefix_sum" (the reference re-runs vfx_prefix_sum over every batch,
         // mod.rs:7393-7428) and "hanabi:sort" (mod.rs:7444-7610)
         bool needs_sort = false;

@@ -1,0 +1,215 @@
+"""Performance matrix beyond the headline bench line: the same kernels on the other BASELINE configurations.
+
+Every row reports the hnb_update launch time (CUDA events inside the context, as in bench.py), the algorithmic
+traffic (8 + 2*stride bytes per UPDATED particle) and the fraction of the measured HBM peak; init
+rows report whole frames (init + bookkeeping + update of the newly spawned particles) because the init kernel is
+not timed separately.  Usage: python tools/perf_matrix.py [scenario ...]
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, "/root/repo")
+import numpy as np
+import torch
+
+import bevy_hanabi_b200 as hb
+from bevy_hanabi_b200 import _native as N, graph as G, recipes, runtime as R
+
+A = G.Attribute
+PEAK = 6581.9
+try:
+    PEAK = float(json.load(open("/root/repo/MEASURED_PEAKS.json"))["hbm_gbs"])
+except Exception:
+    pass
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+
+
+def report(name, ms, bytes_, extra=""):
+    gbs = bytes_ / (ms * 1e-3) / 1e9
+    print(f"{name:44s} {ms:8.4f} ms  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f} % of {PEAK:.0f}  {extra}", flush=True)
+
+
+def timed_update(ctx, launches, steps):
+    ctx.sync()
+    ctx.enable_kernel_timing(True)
+    ctx.kernel_time_ms()
+    for _ in range(steps):
+        ctx.simulate(launches)
+    ms, k = ctx.kernel_time_ms()
+    ctx.enable_kernel_timing(False)
+    return ms / k
+
+
+def frame_ms(ctx, launches, steps=1):
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.simulate(launches)
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def single_instance(ctx, capacity, stride, alive=0, spawn=0, seed=42):
+    md = R.initial_metadata(capacity, 0, stride // 4)
+    md.alive_count, md.max_spawn = alive, capacity - alive
+    ctx.metadata_insert(0, md)
+    ctx.draw_args_insert(0)
+    ctx.upload_spawners([R.make_spawner(spawn=spawn, seed=seed)])
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+    ctx.set_sim_params(1 / 60, 0.0, 1)
+
+
+def c5_update():
+    P = 64 << 20
+    ctx = hb.Context(0, stream.cuda_stream)
+    slab = ctx.slab_create(P, 32)
+    ctx.slab_fill_c5(slab, 0, P, 42, 1e9, 1e9)
+    single_instance(ctx, P, 32, alive=P)
+    la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered()), slab, 0, 0)]
+    for _ in range(5):
+        ctx.simulate(la)
+    ms = timed_update(ctx, la, 30)
+    report("C5 64Mi update, nobody dies", ms, 72 * P)
+    ctx.close()
+
+
+def c5_dying():
+    """Lifetimes U(0, 0.5 s): ~3 % of the survivors die every step; dead-stack pushes + compaction at work."""
+    P = 64 << 20
+    ctx = hb.Context(0, stream.cuda_stream)
+    slab = ctx.slab_create(P, 32)
+    ctx.slab_fill_c5(slab, 0, P, 42, 0.0, 0.5)
+    single_instance(ctx, P, 32, alive=P)
+    la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered()), slab, 0, 0)]
+    alive = P
+    for step in range(12):
+        ms = timed_update(ctx, la, 1)
+        after = ctx.read_metadata(0).alive_count
+        if step in (0, 1, 5, 11):
+            report(f"C5 64Mi dying, step {step}: {alive >> 10} Ki -> {after >> 10} Ki", ms, 72 * alive, f"{100 * (alive - after) / max(alive, 1):.1f} % died")
+        alive = after
+    ctx.close()
+
+
+def c4_topology():
+    n_inst, cap = 1024, 65536
+    P = n_inst * cap
+    ctx = hb.Context(0, stream.cuda_stream)
+    slab = ctx.slab_create(P, 32)
+    sp = []
+    for i in range(n_inst):
+        ctx.slab_fill_c5(slab, i * cap, cap, 7000 + i, 1e9, 1e9)
+        m = R.initial_metadata(cap, i, 8)
+        m.alive_count, m.max_spawn = cap, 0
+        ctx.metadata_insert(i, m)
+        ctx.draw_args_insert(i)
+        sp.append(R.make_spawner(seed=i, effect_metadata_index=i, draw_indirect_index=i, slab_offset=i * cap))
+    ctx.upload_spawners(sp)
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, n_inst)], [0] * n_inst)
+    ctx.set_sim_params(1 / 60, 0.0, n_inst)
+    la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered()), slab, 0, 0)]
+    for _ in range(5):
+        ctx.simulate(la)
+    ms = timed_update(ctx, la, 30)
+    report("C4 shape: 1024 instances x 65536, one batch", ms, 72 * P, f"frame {frame_ms(ctx, la, 20):.4f} ms")
+    # the same with one spawn per instance per frame (init + update): needs free slots -> kill a few first
+    ctx.close()
+
+
+def _burst(name, asset, P, spawn, props=None, steps=10):
+    ctx = hb.Context(0, stream.cuda_stream)
+    fx = asset.generate()
+    stride = fx.particle_stride
+    slab = ctx.slab_create(P, stride)
+    effect = ctx.effect_compile(fx)
+    if props is not None:
+        ctx.upload_properties(effect, 0, props)
+    md = R.initial_metadata(P, 0, stride // 4, properties_array_index=0 if props is not None else N.INVALID)
+    ctx.metadata_insert(0, md)
+    ctx.draw_args_insert(0)
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+    ctx.set_sim_params(1 / 60, 0.0, 1)
+    # warm the kernels on a throw-away frame pair, then reset the instance
+    ctx.upload_spawners([R.make_spawner(spawn=1024, seed=1)])
+    ctx.simulate([N.BatchLaunch.make(effect, slab, 0, 1024)])
+    ctx.sync()
+    ctx.slab_reset_rows(slab, 0, P)
+    ctx.metadata_insert(0, md)
+    ctx.upload_spawners([R.make_spawner(spawn=spawn, seed=7)])
+    t_burst = frame_ms(ctx, [N.BatchLaunch.make(effect, slab, 0, spawn)])
+    alive = ctx.read_metadata(0).alive_count
+    ctx.upload_spawners([R.make_spawner(spawn=0, seed=8)])
+    la = [N.BatchLaunch.make(effect, slab, 0, 0)]
+    for _ in range(3):
+        ctx.simulate(la)
+    ms = timed_update(ctx, la, steps)
+    alive2 = ctx.read_metadata(0).alive_count
+    upd_bytes = (8 + 2 * stride) * alive
+    report(f"{name}: update, {alive2 >> 10} Ki alive, stride {stride}", ms, (8 + 2 * stride) * alive2)
+    t_plain = frame_ms(ctx, la, 5)
+    init_bytes = (stride + 8) * alive
+    report(f"{name}: burst frame (init {alive >> 10} Ki + update)", t_burst, init_bytes + upd_bytes, f"init alone ~{t_burst - t_plain:.4f} ms = {init_bytes / max(t_burst - t_plain, 1e-6) / 1e6:.0f} GB/s")
+    ctx.close()
+
+
+def c5_init_burst():
+    w = G.ExprWriter()
+    asset = (G.EffectAsset(64 << 20, w.module, name="c5_spawned")
+             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(2.) - w.lit(1.)))
+             .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) * w.lit(2.) - w.lit(1.)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+             .init(G.SetAttributeModifier(A.LIFETIME, w.lit(1e9)))
+             .update(G.AccelModifier(w.lit(G.Vec3(0., -9.8, 0.))))
+             .update(G.LinearDragModifier(w.lit(0.5))))
+    _burst("C5 recipe, 32Mi burst", asset, 64 << 20, 32 << 20)
+
+
+def c2_trails():
+    from tests.test_gpu_effects import _firework_trails
+    _burst("C2 trails, 32Mi burst", _firework_trails(40 << 20), 40 << 20, 32 << 20)
+
+
+def c3_force_field():
+    from tests.test_gpu_effects import _force_field
+    for P in (1 << 20, 16 << 20):
+        asset = _force_field(P)
+        _burst(f"C3 force field, {P >> 20}Mi burst", asset, P, P, props=asset.serialize_properties())
+
+
+def many_batches():
+    """Typical game frame: many effect assets -> many batches -> one init/update launch each."""
+    for nb, cap in ((64, 16 << 10), (64, 256 << 10), (256, 4 << 10)):
+        ctx = hb.Context(0, stream.cuda_stream)
+        effect = ctx.effect_compile(recipes.c5_lowered())
+        sp, bis, la = [], [], []
+        for b in range(nb):
+            slab = ctx.slab_create(cap, 32)
+            ctx.slab_fill_c5(slab, 0, cap, 100 + b, 1e9, 1e9)
+            m = R.initial_metadata(cap, b, 8)
+            m.alive_count, m.max_spawn = cap, 0
+            ctx.metadata_insert(b, m)
+            ctx.draw_args_insert(b)
+            sp.append(R.make_spawner(seed=b, effect_metadata_index=b, draw_indirect_index=b, slab_offset=0))
+            bis.append(N.BatchInfo(0, 0, b, 0, b, 1))
+            la.append(N.BatchLaunch.make(effect, slab, b, 0))
+        ctx.upload_spawners(sp)
+        ctx.upload_batches(bis, [0] * nb)
+        ctx.set_sim_params(1 / 60, 0.0, nb)
+        for _ in range(5):
+            ctx.simulate(la)
+        ms = frame_ms(ctx, la, 30)
+        report(f"{nb} batches x {cap >> 10} Ki particles: frame", ms, 72 * nb * cap, f"{ms * 1e3 / nb:.1f} us per batch")
+        ctx.close()
+
+
+SCENARIOS = {"many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field}
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(SCENARIOS)):
+        try:
+            SCENARIOS[name]()
+        except Exception as e:  # keep going: one scenario must not hide the others
+            print(f"{name}: FAILED {type(e).__name__}: {str(e)[:400]}", flush=True)
