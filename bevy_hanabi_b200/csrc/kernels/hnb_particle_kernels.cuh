@@ -308,6 +308,10 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         if (tid == 0) sh_tile_prefix[n_effects] = total_tiles;
     }
     if (lane == 0) sh_pending[warp].valid = 0u;
+    // First tiles: one ticket request per CTA for its eight warps (all warps of the grid start within a few
+    // microseconds of each other; this keeps 7/8 of those same-address atomics off the start of the kernel).
+    __shared__ u32 sh_first_ticket;
+    if (tid == 0) sh_first_ticket = atomicAdd(P.ticket, HNB_WARPS);
     __syncthreads();  // the only block barrier of the kernel
 
     u64* const states = P.tile_state;
@@ -340,9 +344,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
 
     // Tiles are handed out by a ticket counter, so every tile's predecessors in the look-back chain have
     // been taken by a running warp before it.
-    u32 tile = 0u;
-    if (lane == 0) tile = atomicAdd(P.ticket, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
+    u32 tile = sh_first_ticket + warp;
     long long prof_polls = 0;
 #if HNB_PROFILE
     // per-warp cycle accounting of the phases (diagnostics only)

@@ -432,15 +432,17 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     const hnb_batch_info& bi = c->h_at<hnb_batch_info>(c->lay.off_batch_infos)[lp.batch];
     if (uint64_t(bi.prefix_sum_offset) + bi.prefix_sum_count > c->E || uint64_t(bi.spawner_base) + bi.prefix_sum_count > c->E)
         fail(HNB_ERR_OUT_OF_RANGE, "batch references instances outside the uploaded spawner table");
-    // Rows per warp tile: 32 lanes x K rows per lane x chunks. Larger tiles shorten the look-back chain
-    // and amortise per-tile work; the chunk count is picked so that the persistent grid still gets at
-    // least ~2 tiles per resident warp (small slabs get small tiles).
+    // Rows per warp tile: 32 lanes x K rows per lane x chunks. Larger tiles shorten the look-back chain and
+    // amortise the per-tile work (ticket, state word, instance lookup); smaller tiles spread a small slab over more
+    // warps. Thresholds in units of W = one sub-tile per resident warp, from tools/sweep_small.py on C5
+    // (W = 444 Ki rows): 4 chunks win from 2 Mi rows up, 2 chunks from 256 Ki up, below that the launch is
+    // latency-bound and the tile size does not matter.
     const uint32_t sub_tile = 32u * lp.fx->tile_k;
     const uint32_t total_warps = uint32_t(lp.fx->update_blocks_per_sm) * uint32_t(c->sm_count) * 8u;
     uint32_t chunks = c->tile_chunks_override;
     if (chunks == 0) {
-        chunks = 1;
-        while (chunks * 2 * lp.fx->tile_k <= lp.fx->rows_per_lane && uint64_t(lp.slab->capacity) >= uint64_t(2) * total_warps * sub_tile * (chunks * 2)) chunks *= 2;
+        const uint64_t wave = uint64_t(total_warps) * sub_tile;
+        chunks = uint64_t(lp.slab->capacity) >= 4 * wave ? 4u : (uint64_t(lp.slab->capacity) * 4 >= wave ? 2u : 1u);
     }
     chunks = std::max(1u, std::min(chunks, lp.fx->rows_per_lane / lp.fx->tile_k));
     const uint32_t tile = sub_tile * chunks;

@@ -6,7 +6,7 @@ import torch
 import bevy_hanabi_b200 as hb
 from bevy_hanabi_b200 import _native as N, recipes, runtime as R
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-PS = [int(x) << 20 for x in os.environ.get("SWEEP_PS", "4,8,16,32").split(",")]
+PS = [int(float(x) * (1 << 20)) for x in os.environ.get("SWEEP_PS", "4,8,16,32").split(",")]
 CH = os.environ.get("SWEEP_CHUNKS", "0,1,2,4").split(",")
 variants = sys.argv[1:] or [""]
 for P in PS:
@@ -33,5 +33,5 @@ for P in PS:
             ctx.enable_kernel_timing(True); ctx.kernel_time_ms()
             for _ in range(40): ctx.simulate_raw(la,1)
             ms,k = ctx.kernel_time_ms()
-            print(f"P={P>>20:3d}Mi chunks={ch} {defs[:50]:50s} update {ms/k:.4f} ms {72*P/(ms/k*1e-3)/1e9:5.0f} GB/s  step {step:.4f} ms", flush=True)
+            print(f"P={P/(1<<20):8.4f}Mi chunks={ch} {defs[:50]:50s} update {ms/k:.4f} ms {72*P/(ms/k*1e-3)/1e9:5.0f} GB/s  step {step:.4f} ms", flush=True)
             ctx.close()
