@@ -94,72 +94,95 @@ template <typename Ptr> HNB_DI u32 hnb_find_effect(Ptr prefix, u32 lo, u32 hi, u
 // ---------------------------------------------------------------------------------------------
 // init  ≙ vfx_init.wgsl main()
 // ---------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchParams P) {
-    const u32 thread_index = blockIdx.x * HNB_BLOCK + threadIdx.x;  // global_invocation_id.x
-    if (thread_index >= P.init_thread_count) return;
-
-    const BatchInfo bi = *P.batch_info;
-    // Location in the packed init space of this batch (CPU prefix sums of spawn counts, batch.rs:358-383)
-    const u32 slot = hnb_find_effect(P.spawn_prefix, bi.prefix_sum_offset, bi.prefix_sum_offset + bi.prefix_sum_count, thread_index);
-    const u32 effect_index = slot - bi.prefix_sum_offset;
-    const u32 update_index = thread_index - P.spawn_prefix[slot];
-    const Spawner* spawner = &P.spawners[bi.spawner_base + effect_index];
-    const u32 base_particle = spawner->slab_offset;
-    const EffectMetadata* md = &P.metadata[spawner->effect_metadata_index];
-
-    // Cap to the number of dead particles (vfx_init.wgsl:115-119)
-    const u32 max_spawn = md->max_spawn;
-    if (update_index >= max_spawn) return;
-#if HNB_CONSUME_EVENTS
-    const u32 event_index = update_index;
-    const i32 event_count = P.child_infos[md->global_child_index].event_count;
-    if (event_index >= u32(event_count)) return;
-#else
-    const u32 spawn_count = u32(spawner->spawn);
-    if (update_index >= spawn_count) return;
+// Each CUDA thread runs HNB_INIT_ITEMS of the reference's init threads (logical thread index = CTA base +
+// k*HNB_BLOCK + threadIdx, so every k is a coalesced row of the dead stack / alive list). One spawn per thread is
+// latency-bound: the work is a chain broadcast loads -> dead-slot load -> PRNG -> stores, so a thread lives ~2 us
+// for 40 bytes of traffic; with the items' chains issued together the launch is bandwidth-bound instead.
+#ifndef HNB_INIT_ITEMS
+#define HNB_INIT_ITEMS 4
 #endif
+extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchParams P) {
+    const BatchInfo bi = *P.batch_info;
+    struct Item {
+        const Spawner* spawner;
+        const EffectMetadata* md;
+        u32 update_index, alive_index, dead;
+        bool ok;
+    } items[HNB_INIT_ITEMS];
 
-    // Recycle a dead slot. Serial-order equivalent of `atomicAdd(alive_count, 1)` (:141): every thread
-    // with a smaller update_index also passed the caps above, so this thread's rank IS update_index.
-    const u32 alive_index = md->alive_count + update_index;
-    const u32 slab_particle_dead_index = P.slab.dead_index[base_particle + alive_index];
-    const u32 particle_index = slab_particle_dead_index - base_particle;
-
-    Ctx hnb_ctx;
-    hnb_ctx.particle_index = particle_index;
-    hnb_ctx.particle_counter = md->particle_counter + update_index;  // atomicAdd(particle_counter, 1) (:151)
-    hnb_ctx.seed = pcg_hash(particle_index ^ spawner->seed);         // :154
-    hnb_ctx.sim = &P.frame->sim;
-    hnb_ctx.spawner = spawner;
-    hnb_ctx.transform = hnb_transform_from_rows(spawner->transform, spawner->transform + 4, spawner->transform + 8);
-    hnb_ctx.inverse_transform = hnb_transform_from_rows(spawner->inverse_transform, spawner->inverse_transform + 4,
-                                                        spawner->inverse_transform + 8);
-    hnb_ctx.is_alive = true;
-#if HNB_HAS_PROPERTIES
-    hnb_ctx.props = (const Properties*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
+    // ---- locate, apply the caps, pop the dead slot (all loads of all items in flight together)
+#pragma unroll
+    for (int k = 0; k < HNB_INIT_ITEMS; ++k) {
+        Item& it = items[k];
+        const u32 thread_index = (blockIdx.x * HNB_INIT_ITEMS + k) * HNB_BLOCK + threadIdx.x;  // global_invocation_id.x
+        it.ok = thread_index < P.init_thread_count;
+        it.dead = 0u;
+        if (!it.ok) continue;
+        // Location in the packed init space of this batch (CPU prefix sums of spawn counts, batch.rs:358-383)
+        const u32 slot = hnb_find_effect(P.spawn_prefix, bi.prefix_sum_offset, bi.prefix_sum_offset + bi.prefix_sum_count, thread_index);
+        const u32 effect_index = slot - bi.prefix_sum_offset;
+        it.update_index = thread_index - P.spawn_prefix[slot];
+        it.spawner = &P.spawners[bi.spawner_base + effect_index];
+        it.md = &P.metadata[it.spawner->effect_metadata_index];
+        // Cap to the number of dead particles (vfx_init.wgsl:115-119)
+        it.ok = it.update_index < it.md->max_spawn;
+#if HNB_CONSUME_EVENTS
+        it.ok = it.ok && it.update_index < u32(P.child_infos[it.md->global_child_index].event_count);  // event_index = update_index
 #else
-    hnb_ctx.props = nullptr;
+        it.ok = it.ok && it.update_index < u32(it.spawner->spawn);
+#endif
+        if (!it.ok) continue;
+        // Recycle a dead slot. Serial-order equivalent of `atomicAdd(alive_count, 1)` (:141): every thread
+        // with a smaller update_index also passed the caps above, so this thread's rank IS update_index.
+        it.alive_index = it.md->alive_count + it.update_index;
+        it.dead = P.slab.dead_index[it.spawner->slab_offset + it.alive_index];
+    }
+
+    // ---- initialise and store
+#pragma unroll
+    for (int k = 0; k < HNB_INIT_ITEMS; ++k) {
+        const Item& it = items[k];
+        if (!it.ok) continue;
+        const Spawner* spawner = it.spawner;
+        const EffectMetadata* md = it.md;
+        const u32 base_particle = spawner->slab_offset;
+        const u32 particle_index = it.dead - base_particle;
+
+        Ctx hnb_ctx;
+        hnb_ctx.particle_index = particle_index;
+        hnb_ctx.particle_counter = md->particle_counter + it.update_index;  // atomicAdd(particle_counter, 1) (:151)
+        hnb_ctx.seed = pcg_hash(particle_index ^ spawner->seed);            // :154
+        hnb_ctx.sim = &P.frame->sim;
+        hnb_ctx.spawner = spawner;
+        hnb_ctx.transform = hnb_transform_from_rows(spawner->transform, spawner->transform + 4, spawner->transform + 8);
+        hnb_ctx.inverse_transform = hnb_transform_from_rows(spawner->inverse_transform, spawner->inverse_transform + 4,
+                                                            spawner->inverse_transform + 8);
+        hnb_ctx.is_alive = true;
+#if HNB_HAS_PROPERTIES
+        hnb_ctx.props = (const Properties*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
+#else
+        hnb_ctx.props = nullptr;
 #endif
 #if HNB_READ_PARENT
-    {
-        const u32 parent_base_particle = spawner->parent_slab_offset;
-        hnb_ctx.parent_particle_index = P.consume_events[event_index];
-        ParentRawParticle praw;
-        hnb_parent_load_raw(praw, P.parent_slab, parent_base_particle + hnb_ctx.parent_particle_index);
-        hnb_parent_unpack(praw, hnb_ctx.parent_particle);
-    }
+        {
+            const u32 parent_base_particle = spawner->parent_slab_offset;
+            hnb_ctx.parent_particle_index = P.consume_events[it.update_index];
+            ParentRawParticle praw;
+            hnb_parent_load_raw(praw, P.parent_slab, parent_base_particle + hnb_ctx.parent_particle_index);
+            hnb_parent_unpack(praw, hnb_ctx.parent_particle);
+        }
 #endif
 
-    Particle particle = Particle();
-    hnb_init_body(particle, hnb_ctx);
+        Particle particle = Particle();
+        hnb_init_body(particle, hnb_ctx);
 
-    // Append to the alive list (:191-192) and write the particle back (:195)
-    const u32 write_index = md->indirect_write_index;
-    P.slab.particle_index[write_index][base_particle + alive_index] = particle_index;
-    RawParticle raw;
-    hnb_raw_zero(raw);
-    hnb_pack<true>(particle, raw);  // init also stores PREV/NEXT (vfx_init.wgsl:175-181)
-    hnb_store_raw(raw, P.slab, base_particle + particle_index);
+        // Append to the alive list (:191-192) and write the particle back (:195)
+        P.slab.particle_index[md->indirect_write_index][base_particle + it.alive_index] = particle_index;
+        RawParticle raw;
+        hnb_raw_zero(raw);
+        hnb_pack<true>(particle, raw);  // init also stores PREV/NEXT (vfx_init.wgsl:175-181)
+        hnb_store_raw(raw, P.slab, base_particle + particle_index);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

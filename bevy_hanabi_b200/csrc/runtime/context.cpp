@@ -500,7 +500,7 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     P.init_thread_count = init_threads;
     P.debug = c->d_debug;
     P.tile_rows = tile;
-    lp.init_blocks = ceil_div(init_threads, 256);
+    lp.init_blocks = ceil_div(init_threads, 256 * hnb_rt::kInitItems);  // HNB_INIT_ITEMS logical init threads per CUDA thread
     uint32_t max_tiles = lp.slab->capacity / tile + bi.prefix_sum_count + 1;
     lp.update_blocks = std::min<uint32_t>(ceil_div(max_tiles, 8), uint32_t(lp.fx->update_blocks_per_sm) * uint32_t(c->sm_count));
     if (lp.update_blocks == 0) lp.update_blocks = 1;

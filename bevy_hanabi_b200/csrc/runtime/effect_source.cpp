@@ -230,6 +230,7 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
     o << "#define HNB_NUM_PLANES " << planes.size() << "\n";
     o << "#define HNB_TILE_K " << choose_tile_k(d) << "\n";
     o << "#define HNB_ROWS_PER_LANE " << rows_per_lane() << "\n";
+    o << "#define HNB_INIT_ITEMS " << kInitItems << "\n";
     o << "#define HNB_HAS_PROPERTIES " << (d.properties_size ? 1 : 0) << "\n";
     o << "#define HNB_CONSUME_EVENTS " << (consume ? 1 : 0) << "\n";
     o << "#define HNB_EMIT_EVENTS " << (emit ? 1 : 0) << "\n";

@@ -30,6 +30,8 @@ std::vector<Plane> cut_planes(uint32_t stride_bytes);
 
 // Update tiles are walked by one warp each: tile_rows = 32 lanes * k rows per lane * chunks. k is
 // chosen from the record size (register footprint) at compile time, the chunk count per launch.
+// logical init threads (vfx_init.wgsl invocations) per CUDA thread of hnb_init == HNB_INIT_ITEMS of the generated kernels
+constexpr uint32_t kInitItems = 4;
 uint32_t rows_per_lane();  // == HNB_ROWS_PER_LANE of the generated kernels: tile_rows <= 32 * rows_per_lane()
 uint32_t choose_tile_k(const hnb_effect_desc& d);
 // Dynamic shared memory of hnb_update for this effect (tile-prefix table + per-warp double-buffered stash +
