@@ -123,6 +123,7 @@ EFFECT_EMIT_GPU_SPAWN_EVENTS = 1 << 2
 EFFECT_READ_PARENT_PARTICLE = 1 << 3
 EFFECT_RELAXED_ORDER = 1 << 4
 EFFECT_RIBBONS = 1 << 5
+EFFECT_FAST_MATH = 1 << 6
 
 
 def _load() -> C.CDLL:

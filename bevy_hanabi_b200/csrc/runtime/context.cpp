@@ -378,11 +378,11 @@ void check_rows(const Slab& s, uint32_t first, uint32_t count) {
 // Staging through a device buffer in chunks (AoS <-> planes transposes run on the device).
 constexpr size_t kChunkBytes = size_t(64) << 20;
 
-KernelModule* get_module(hnb_ctx* c, const std::string& source, const std::string& name, uint64_t hash) {
+KernelModule* get_module(hnb_ctx* c, const std::string& source, const std::string& name, uint64_t hash, bool fast_math) {
     auto it = c->modules.find(hash);
     if (it != c->modules.end()) return it->second.get();
     std::string cubin, log;
-    if (!nvrtc_compile_sm100a(source, name + ".cu", cubin, log)) fail(HNB_ERR_NVRTC, log);
+    if (!nvrtc_compile_sm100a(source, name + ".cu", cubin, log, fast_math)) fail(HNB_ERR_NVRTC, log);
     auto km = std::make_unique<KernelModule>();
     km->log = log;
     CUresult r = c->drv.ModuleLoadData(&km->mod, cubin.data());
@@ -896,7 +896,9 @@ int32_t hnb_effect_generate_source(const hnb_effect_desc* desc, char* out, size_
 int32_t hnb_nvrtc_check(const char* source, size_t* cubin_size) {
     return guarded([&] {
         std::string cubin, log;
-        if (!nvrtc_compile_sm100a(source, "check.cu", cubin, log)) fail(HNB_ERR_NVRTC, log);
+        // generated sources state their own compile mode (effect_source.cpp)
+        const bool fast_math = std::string(source).find("#define HNB_FAST_MATH 1") != std::string::npos;
+        if (!nvrtc_compile_sm100a(source, "check.cu", cubin, log, fast_math)) fail(HNB_ERR_NVRTC, log);
         g_last_error = log;  // compiler log (ptxas -v) available to the caller even on success
         if (cubin_size) *cubin_size = cubin.size();
     });
@@ -910,7 +912,7 @@ int32_t hnb_effect_compile(hnb_ctx* c, const hnb_effect_desc* desc, hnb_effect* 
         Effect fx;
         fx.hash = fnv1a64(src);
         fx.name = desc->name ? desc->name : "effect";
-        fx.km = get_module(c, src, fx.name, fx.hash);
+        fx.km = get_module(c, src, fx.name, fx.hash, (desc->flags & HNB_EFFECT_FAST_MATH) != 0);  // the flag is part of the source (hash)
         fx.tile_k = choose_tile_k(*desc);
         fx.rows_per_lane = rows_per_lane();
         fx.update_smem = update_smem_bytes(*desc);

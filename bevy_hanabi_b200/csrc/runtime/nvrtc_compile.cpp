@@ -18,7 +18,7 @@ uint64_t fnv1a64(const std::string& s) {
     return h;
 }
 
-bool nvrtc_compile_sm100a(const std::string& source, const std::string& name, std::string& cubin, std::string& log) {
+bool nvrtc_compile_sm100a(const std::string& source, const std::string& name, std::string& cubin, std::string& log, bool fast_math) {
     nvrtcProgram prog = nullptr;
     nvrtcResult r = nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) {
@@ -27,9 +27,18 @@ bool nvrtc_compile_sm100a(const std::string& source, const std::string& name, st
     }
     // -fmad=false: no FMA contraction, so add/mul sequences are bit-exact with the CPU oracle
     // (SURVEY.md §7 "fp parity"). No fast-math: IEEE division and square root.
-    const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-default-device", "-diag-suppress=550", "-diag-suppress=177",
-                          "--ptxas-options=-v"};
-    r = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    // HNB_EFFECT_FAST_MATH: contraction and approximate div/sqrt, but NOT --use_fast_math (its sin/cos/exp
+    // intrinsics have absolute, not relative, error bounds and would break the 1e-5 relative tolerance).
+    std::vector<const char*> opts = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-diag-suppress=550", "-diag-suppress=177",
+                                     "--ptxas-options=-v"};
+    if (fast_math) {
+        opts.push_back("-fmad=true");
+        opts.push_back("-prec-div=false");
+        opts.push_back("-prec-sqrt=false");
+    } else {
+        opts.push_back("-fmad=false");
+    }
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     size_t log_size = 0;
     nvrtcGetProgramLogSize(prog, &log_size);
     if (log_size > 1) {

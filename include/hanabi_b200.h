@@ -235,8 +235,12 @@ enum {
     HNB_EFFECT_READ_PARENT_PARTICLE = 1u << 3,
     HNB_EFFECT_RELAXED_ORDER = 1u << 4,        /* alive/dead lists in atomic order (sets exact,
                                                   order scheduling-dependent like the reference) */
-    HNB_EFFECT_RIBBONS = 1u << 5               /* LayoutFlags::RIBBONS (lib.rs:1018-1019): the layout has RIBBON_ID;
+    HNB_EFFECT_RIBBONS = 1u << 5,              /* LayoutFlags::RIBBONS (lib.rs:1018-1019): the layout has RIBBON_ID;
                                                   hnb_simulate() sorts the alive list by (RIBBON_ID, AGE) after the update */
+    HNB_EFFECT_FAST_MATH = 1u << 6             /* compile the effect with FMA contraction and approximate division /
+                                                  square root — the latitude a WGSL compiler has. fp32 results stay within
+                                                  the 1e-5 relative bound but are no longer bit-identical to the oracle;
+                                                  integer bookkeeping is unaffected. Pays off for ALU-bound effects. */
 };
 
 /**

@@ -30,7 +30,7 @@ def _float_word_mask(asset):
     return mask, attrs
 
 
-def _run(ctx, orc, asset, ref, frames, spawns, rtol=0.0, props=None, seeds=None, check_every=1, relaxed=False):
+def _run(ctx, orc, asset, ref, frames, spawns, rtol=0.0, props=None, seeds=None, check_every=1, relaxed=False, fast_math=False):
     """spawns: callable frame -> list of per-instance spawn counts. props: per-instance dict of property values."""
     blobs = None
     if props is not None:
@@ -38,7 +38,7 @@ def _run(ctx, orc, asset, ref, frames, spawns, rtol=0.0, props=None, seeds=None,
         for i in range(len(ref.instances)):
             ref.metadata[i].properties_array_index = i
     eo = EffectOracle(asset, {i: p for i, p in enumerate(props)} if props else None)
-    gpu = GpuWorld(ctx, ref, asset.generate(relaxed_order=relaxed), property_blobs=blobs)
+    gpu = GpuWorld(ctx, ref, asset.generate(relaxed_order=relaxed, fast_math=fast_math), property_blobs=blobs)
     mask, fattrs = _float_word_mask(asset)
     for f in range(frames):
         ref.sim.time = np.float32(f) * ref.sim.delta_time
@@ -144,6 +144,21 @@ def test_c3_force_field(ctx, orc):
     ref = RefWorld(8192, size // 4, [Instance(0, 8192, alive=0, seed=77)])
     props = [{"attraction_accel": 18.0, "repulsor_position": G.Vec3(0.25, 0.5, 0.1)}]
     _run(ctx, orc, asset, ref, 25, lambda f: [5000 if f == 0 else (30 if f % 5 == 0 else 0)], rtol=1e-5, props=props)
+
+
+def test_fast_math_effects_stay_within_tolerance(ctx, orc):
+    """HNB_EFFECT_FAST_MATH (FMA contraction, approximate division / square root): fp32 attributes within the 1e-5
+    per-step bound of BASELINE.json, every integer structure still exact."""
+    from bevy_hanabi_b200 import _native as N
+    asset = _force_field(8192)
+    assert asset.generate(fast_math=True).flags & N.EFFECT_FAST_MATH
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(8192, size // 4, [Instance(0, 8192, alive=0, seed=77)])
+    props = [{"attraction_accel": 18.0, "repulsor_position": G.Vec3(0.25, 0.5, 0.1)}]
+    _run(ctx, orc, asset, ref, 25, lambda f: [5000 if f == 0 else (30 if f % 5 == 0 else 0)], rtol=1e-5, props=props, fast_math=True)
+    asset = _firework_trails(4096)
+    ref = RefWorld(4096, 12, [Instance(0, 4096, alive=0)], dt=1.0 / 20.0)
+    _run(ctx, orc, asset, ref, 30, lambda f: [1000 if f % 20 == 0 else 0], rtol=1e-5, fast_math=True)
 
 
 def test_many_instances_properties_transforms(ctx, orc):

@@ -120,9 +120,9 @@ def c4_topology():
     ctx.close()
 
 
-def _burst(name, asset, P, spawn, props=None, steps=10):
+def _burst(name, asset, P, spawn, props=None, steps=10, fast_math=False):
     ctx = hb.Context(0, stream.cuda_stream)
-    fx = asset.generate()
+    fx = asset.generate(fast_math=fast_math)
     stride = fx.particle_stride
     slab = ctx.slab_create(P, stride)
     effect = ctx.effect_compile(fx)
@@ -180,6 +180,12 @@ def c3_force_field():
         _burst(f"C3 force field, {P >> 20}Mi burst", asset, P, P, props=asset.serialize_properties())
 
 
+def c3_fast_math():
+    from tests.test_gpu_effects import _force_field
+    asset = _force_field(16 << 20)
+    _burst("C3 force field FAST_MATH, 16Mi burst", asset, 16 << 20, 16 << 20, props=asset.serialize_properties(), fast_math=True)
+
+
 def many_batches():
     """Typical game frame: many effect assets -> many batches -> one init/update launch each."""
     for nb, cap in ((64, 16 << 10), (64, 256 << 10), (256, 4 << 10)):
@@ -206,7 +212,7 @@ def many_batches():
         ctx.close()
 
 
-SCENARIOS = {"many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field}
+SCENARIOS = {"many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
