@@ -169,6 +169,45 @@ HNB_API int32_t hnb_batcher_push(hnb_batcher* b, const hnb_batch_key* key, uint3
 HNB_API int32_t hnb_batcher_finish(hnb_batcher* b, const hnb_batch_info** infos, uint32_t* n_batches, const uint32_t** prefix,
                                    uint32_t* n_prefix, uint32_t* total_spawn_counts, uint32_t total_cap);
 
+/* ------------------------------------------------------------------------------------ */
+/* Placement of effect instances into slabs ≙ ParticleSlab / EffectCache bookkeeping      */
+/* (reference src/render/effect_cache.rs:484-607, :843-930). Host only: the caller owns  */
+/* the device storage (hnb_slab_create / _destroy / _reset_rows in hanabi_b200.h).        */
+/* ------------------------------------------------------------------------------------ */
+#define HNB_SLAB_MIN_CAPACITY 65536u /* ParticleSlab::MIN_CAPACITY, effect_cache.rs:234 */
+enum { HNB_SLAB_USED = 0, HNB_SLAB_FREE = 1 }; /* SlabState */
+
+/** Slice allocator of one slab: ParticleSlab::{allocate, free_slice} (effect_cache.rs:540-607). */
+typedef struct hnb_slice_allocator hnb_slice_allocator;
+HNB_API hnb_slice_allocator* hnb_slice_allocator_create(uint32_t capacity); /* capacity = max(capacity, 65536) */
+HNB_API void hnb_slice_allocator_destroy(hnb_slice_allocator* s);
+HNB_API uint32_t hnb_slice_allocator_capacity(const hnb_slice_allocator* s);
+HNB_API uint32_t hnb_slice_allocator_used_size(const hnb_slice_allocator* s);
+HNB_API uint32_t hnb_slice_allocator_free_count(const hnb_slice_allocator* s);
+HNB_API int32_t hnb_slice_allocator_free_range(const hnb_slice_allocator* s, uint32_t index, uint32_t* start, uint32_t* end);
+/** 0 and [*start, *end) on success, -1 when the slab has no room (allocate() -> None). */
+HNB_API int32_t hnb_slice_allocator_allocate(hnb_slice_allocator* s, uint32_t size, uint32_t* start, uint32_t* end);
+/** HNB_SLAB_FREE when this was the last allocated slice, else HNB_SLAB_USED. */
+HNB_API int32_t hnb_slice_allocator_free(hnb_slice_allocator* s, uint32_t start, uint32_t end);
+
+/** CachedEffect (effect_cache.rs:624-632) plus what the caller needs to create the storage. */
+typedef struct hnb_cached_effect {
+    uint32_t slab_index;     /* SlabId */
+    uint32_t range_start;    /* slice.range: rows of the slab = spawner.slab_offset .. */
+    uint32_t range_end;
+    uint32_t slab_capacity;  /* rows of the slab (for hnb_slab_create when `created`) */
+    uint32_t created;        /* 1: a new slab was opened for this instance */
+} hnb_cached_effect;
+typedef struct hnb_effect_cache hnb_effect_cache;
+HNB_API hnb_effect_cache* hnb_effect_cache_create(void);
+HNB_API void hnb_effect_cache_destroy(hnb_effect_cache* c);
+HNB_API uint32_t hnb_effect_cache_slab_count(const hnb_effect_cache* c);   /* slots, live or not */
+HNB_API int32_t hnb_effect_cache_slab_is_live(const hnb_effect_cache* c, uint32_t slab_index);
+/** EffectCache::insert (effect_cache.rs:843-914). */
+HNB_API int32_t hnb_effect_cache_insert(hnb_effect_cache* c, uint64_t asset_id, uint32_t capacity, hnb_cached_effect* out);
+/** EffectCache::remove (:918-938): HNB_SLAB_FREE when the slab became empty (destroy its storage), -1 on a bad handle. */
+HNB_API int32_t hnb_effect_cache_remove(hnb_effect_cache* c, const hnb_cached_effect* effect);
+
 #ifdef __cplusplus
 }
 #endif

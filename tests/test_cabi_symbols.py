@@ -34,8 +34,9 @@ def test_symbol_exported(header, name):
 def test_python_binding_covers_every_symbol():
     from bevy_hanabi_b200 import _native as N
     from bevy_hanabi_b200 import graph as G
+    from bevy_hanabi_b200 import cache as K
     from bevy_hanabi_b200 import spawn as S
-    bound = set(N.SIGNATURES) | set(G.GRAPH_SIGNATURES) | set(S.SPAWN_SIGNATURES)
+    bound = set(N.SIGNATURES) | set(G.GRAPH_SIGNATURES) | set(S.SPAWN_SIGNATURES) | set(K.CACHE_SIGNATURES)
     declared = {n for _, n in _declared()}
     assert declared <= bound, f"unbound: {sorted(declared - bound)}"
 
