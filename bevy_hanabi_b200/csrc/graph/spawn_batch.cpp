@@ -263,3 +263,90 @@ int32_t hnb_batcher_finish(hnb_batcher* b, const hnb_batch_info** infos, uint32_
 }
 
 }  // extern "C"
+
+// ---- EffectSorter (batch.rs:476-637) ------------------------------------------------------------
+// Order in which batch_effects() walks the instances: dependency level first (children get level 0, an effect
+// sits one level above its deepest child — so children come BEFORE their parents, as the reference's own test
+// pins, batch.rs:776-826), then slab, then position in the slab, which puts mergeable instances next to each other.
+struct hnb_effect_sorter {
+    struct Entry {
+        uint64_t entity;
+        uint32_t slab_id, base_instance;
+    };
+    std::vector<Entry> effects;
+    std::vector<std::pair<uint64_t, uint64_t>> child_to_parent;  // (child, parent); a child has at most one parent
+
+    bool sort() {
+        const size_t n = effects.size();
+        auto index_of = [&](uint64_t e) -> size_t {
+            for (size_t i = 0; i < n; ++i)
+                if (effects[i].entity == e) return i;
+            return n;
+        };
+        std::vector<std::vector<size_t>> parents(n);
+        for (auto& cp : child_to_parent) {
+            const size_t kid = index_of(cp.first), parent = index_of(cp.second);
+            if (kid == n || parent == n) return false;
+            parents[kid].push_back(parent);
+        }
+        // depth-first topological order: an effect is emitted after the parents it points to
+        std::vector<size_t> ordering;
+        std::vector<uint8_t> state(n, 0);  // 0 new, 1 visiting, 2 done
+        bool cycle = false;
+        struct Frame { size_t node, next; };
+        for (size_t root = 0; root < n; ++root) {
+            if (state[root]) continue;
+            std::vector<Frame> stack{{root, 0}};
+            state[root] = 1;
+            while (!stack.empty()) {
+                Frame& f = stack.back();
+                if (f.next < parents[f.node].size()) {
+                    const size_t p = parents[f.node][f.next++];
+                    if (state[p] == 1) cycle = true;
+                    if (state[p] == 0) { state[p] = 1; stack.push_back({p, 0}); }
+                } else {
+                    state[f.node] = 2;
+                    ordering.push_back(f.node);
+                    stack.pop_back();
+                }
+            }
+        }
+        if (cycle) return false;
+        std::vector<uint32_t> levels(n, 0);
+        for (size_t k = ordering.size(); k-- > 0;) {
+            const size_t e = ordering[k];
+            for (size_t p : parents[e]) levels[p] = std::max(levels[p], levels[e] + 1);
+        }
+        std::vector<size_t> perm(n);
+        for (size_t i = 0; i < n; ++i) perm[i] = i;
+        std::sort(perm.begin(), perm.end(), [&](size_t a, size_t b) {
+            if (levels[a] != levels[b]) return levels[a] < levels[b];
+            if (effects[a].slab_id != effects[b].slab_id) return effects[a].slab_id < effects[b].slab_id;
+            return effects[a].base_instance < effects[b].base_instance;
+        });
+        std::vector<Entry> sorted(n);
+        for (size_t i = 0; i < n; ++i) sorted[i] = effects[perm[i]];
+        effects.swap(sorted);
+        return true;
+    }
+};
+
+extern "C" {
+hnb_effect_sorter* hnb_effect_sorter_create(void) { return new hnb_effect_sorter(); }
+void hnb_effect_sorter_destroy(hnb_effect_sorter* s) { delete s; }
+void hnb_effect_sorter_insert(hnb_effect_sorter* s, uint64_t entity, uint32_t slab_id, uint32_t base_instance, uint64_t parent) {
+    s->effects.push_back({entity, slab_id, base_instance});
+    if (parent != HNB_NO_ENTITY) {
+        for (auto& cp : s->child_to_parent)
+            if (cp.first == entity) { cp.second = parent; return; }
+        s->child_to_parent.push_back({entity, parent});
+    }
+}
+int32_t hnb_effect_sorter_sort(hnb_effect_sorter* s) {
+    if (s->sort()) return 0;
+    hnb_set_last_error_("EffectSorter: unknown parent entity or cyclic parent-child relation");
+    return -1;
+}
+uint32_t hnb_effect_sorter_len(const hnb_effect_sorter* s) { return (uint32_t)s->effects.size(); }
+uint64_t hnb_effect_sorter_get(const hnb_effect_sorter* s, uint32_t index) { return index < s->effects.size() ? s->effects[index].entity : HNB_NO_ENTITY; }
+}

@@ -36,6 +36,12 @@ SPAWN_SIGNATURES = {
     "hnb_effect_spawner_reset": (None, [C.c_void_p]),
     "hnb_effect_spawner_set_active": (None, [C.c_void_p, u32]),
     "hnb_effect_spawner_state": (C.c_int32, [C.c_void_p, P(SpawnerState)]),
+    "hnb_effect_sorter_create": (C.c_void_p, []),
+    "hnb_effect_sorter_destroy": (None, [C.c_void_p]),
+    "hnb_effect_sorter_insert": (None, [C.c_void_p, C.c_uint64, u32, u32, C.c_uint64]),
+    "hnb_effect_sorter_sort": (C.c_int32, [C.c_void_p]),
+    "hnb_effect_sorter_len": (u32, [C.c_void_p]),
+    "hnb_effect_sorter_get": (C.c_uint64, [C.c_void_p, u32]),
     "hnb_batcher_create": (C.c_void_p, []),
     "hnb_batcher_destroy": (None, [C.c_void_p]),
     "hnb_batcher_clear": (None, [C.c_void_p]),
@@ -152,3 +158,30 @@ class Batcher:
         check(lib.hnb_batcher_finish(self._h, C.byref(infos), C.byref(nb), C.byref(prefix), C.byref(np_), totals, 4096))
         bi = [N.BatchInfo.from_buffer_copy(bytes(infos[i])) for i in range(nb.value)]
         return bi, [prefix[i] for i in range(np_.value)], list(totals[:nb.value])
+
+
+NO_ENTITY = 0xFFFFFFFFFFFFFFFF
+
+
+class EffectSorter:
+    """EffectSorter (batch.rs:476-637): children before parents, then by slab, then by row offset."""
+
+    def __init__(self):
+        self._h = lib.hnb_effect_sorter_create()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.hnb_effect_sorter_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def insert(self, entity: int, slab_id: int, base_instance: int, parent: int | None = None):
+        lib.hnb_effect_sorter_insert(self._h, entity, slab_id, base_instance, NO_ENTITY if parent is None else parent)
+
+    def sort(self):
+        check(lib.hnb_effect_sorter_sort(self._h))
+
+    def entities(self) -> list[int]:
+        return [lib.hnb_effect_sorter_get(self._h, i) for i in range(lib.hnb_effect_sorter_len(self._h))]

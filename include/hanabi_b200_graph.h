@@ -169,6 +169,18 @@ HNB_API int32_t hnb_batcher_push(hnb_batcher* b, const hnb_batch_key* key, uint3
 HNB_API int32_t hnb_batcher_finish(hnb_batcher* b, const hnb_batch_info** infos, uint32_t* n_batches, const uint32_t** prefix,
                                    uint32_t* n_prefix, uint32_t* total_spawn_counts, uint32_t total_cap);
 
+/** EffectSorter (reference src/render/batch.rs:476-637): the order in which batch_effects() visits the instances —
+ *  dependency level (children before their parents, pinned by batch.rs:776-826), then slab, then row offset. */
+#define HNB_NO_ENTITY 0xFFFFFFFFFFFFFFFFull
+typedef struct hnb_effect_sorter hnb_effect_sorter;
+HNB_API hnb_effect_sorter* hnb_effect_sorter_create(void);
+HNB_API void hnb_effect_sorter_destroy(hnb_effect_sorter* s);
+HNB_API void hnb_effect_sorter_insert(hnb_effect_sorter* s, uint64_t entity, uint32_t slab_id, uint32_t base_instance,
+                                      uint64_t parent /* HNB_NO_ENTITY if none */);
+HNB_API int32_t hnb_effect_sorter_sort(hnb_effect_sorter* s); /* -1: unknown parent or cycle */
+HNB_API uint32_t hnb_effect_sorter_len(const hnb_effect_sorter* s);
+HNB_API uint64_t hnb_effect_sorter_get(const hnb_effect_sorter* s, uint32_t index);
+
 /* ------------------------------------------------------------------------------------ */
 /* Placement of effect instances into slabs ≙ ParticleSlab / EffectCache bookkeeping      */
 /* (reference src/render/effect_cache.rs:484-607, :843-930). Host only: the caller owns  */

@@ -125,3 +125,43 @@ def test_batcher_never_merges_event_effects_or_different_slabs():
     assert prefix == [0, 0, 0, 0, 0, 4] and totals == [0, 0, 4, 4, 8]
     b.clear()
     assert b.finish() == ([], [], [])
+
+
+def test_effect_sorter_toposort_batches():
+    """batch.rs:776-826 `toposort_batches`: children first, then by slab and offset."""
+    from bevy_hanabi_b200.spawn import EffectSorter
+    s = EffectSorter()
+    s.insert(1, 42, 0)                 # some parent effect
+    s.insert(2, 5, 30, parent=1)       # a child in a different buffer
+    assert s.entities() == [1, 2]
+    s.sort()
+    assert s.entities() == [2, 1]      # child first, parent after
+    s.insert(3, 42, 20, parent=1)      # a child in the same buffer as its parent
+    assert s.entities() == [2, 1, 3]   # simply appended
+    s.sort()
+    assert s.entities() == [2, 3, 1]   # child, other child (same buffer as the parent), finally the parent
+
+
+def test_effect_sorter_levels_slabs_and_errors():
+    from bevy_hanabi_b200.spawn import EffectSorter
+    from bevy_hanabi_b200._native import HanabiError
+    s = EffectSorter()
+    # grandparent 10 <- parent 11 <- child 12; unrelated effects 20, 21 in slab 1, 22 in slab 0
+    s.insert(10, 3, 0)
+    s.insert(11, 3, 100, parent=10)
+    s.insert(12, 4, 0, parent=11)
+    s.insert(20, 1, 500)
+    s.insert(21, 1, 0)
+    s.insert(22, 0, 7)
+    s.sort()
+    # level 0: 12 (slab 4), 20/21 (slab 1), 22 (slab 0) ordered by (slab, offset); level 1: 11; level 2: 10
+    assert s.entities() == [22, 21, 20, 12, 11, 10]
+    bad = EffectSorter()
+    bad.insert(1, 0, 0, parent=99)
+    with pytest.raises(HanabiError):
+        bad.sort()
+    cyc = EffectSorter()
+    cyc.insert(1, 0, 0, parent=2)
+    cyc.insert(2, 0, 8, parent=1)
+    with pytest.raises(HanabiError):
+        cyc.sort()
