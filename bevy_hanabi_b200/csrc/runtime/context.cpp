@@ -336,7 +336,13 @@ void flush_arena(hnb_ctx* c, bool with_ranges) {
 
 void next_epoch(hnb_ctx* c) {
     c->epoch = (c->epoch + 1u) & 0x3fffffffu;
-    if (c->epoch == 0) c->epoch = 1;  // 0 = "never written" in tile states
+    if (c->epoch == 0) {
+        // 30-bit wrap (207 days at 60 frames/s): a tile state left untouched since the same epoch of the previous
+        // cycle would look current, so drop them all. 0 = "never written".
+        c->epoch = 1;
+        for (size_t b = 0; b < c->d_tile_state.size(); ++b)
+            if (c->d_tile_state[b]) CUDA_CHECK(cudaMemsetAsync(c->d_tile_state[b], 0, size_t(c->tile_state_cap[b]) * 8, c->stream));
+    }
     c->header()->epoch = c->epoch;
     c->header()->num_batches = c->B;
 }
@@ -667,6 +673,7 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
             c->own_stream = true;
         }
         if (const char* e = getenv("HNB_TILE_CHUNKS")) c->tile_chunks_override = (uint32_t)atoi(e);
+        if (const char* e = getenv("HNB_EPOCH_START")) c->epoch = uint32_t(strtoul(e, nullptr, 0)) & 0x3fffffffu;  // tests: start near the wrap
         if (const char* e = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::min(atoi(e), 31);
         ensure_arena(c.get(), 0, 0);
         CUDA_CHECK(cudaMalloc((void**)&c->d_debug, 16 * 8));

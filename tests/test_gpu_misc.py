@@ -153,6 +153,49 @@ def test_batch_with_more_instances_than_the_shared_memory_table(ctx, orc):
             assert_world_equal(ref, gpu.pull(), what=f"step {step}")
 
 
+def test_empty_frames(ctx):
+    """No effects at all, then an instance that is empty and asks for nothing: frames must be no-ops."""
+    ctx.set_sim_params(1 / 60, 0.0, 0)
+    ctx.simulate([])
+    ctx.sync()
+    fx = ctx.effect_compile(recipes.c5_lowered())
+    slab = ctx.slab_create(256, 32)
+    ctx.metadata_insert(0, R.initial_metadata(256, 0, 8))
+    ctx.draw_args_insert(0)
+    ctx.upload_spawners([R.make_spawner(seed=1)])
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+    ctx.set_sim_params(1 / 60, 0.0, 1)
+    for _ in range(3):
+        ctx.simulate([N.BatchLaunch.make(fx, slab, 0, 0)])
+    md = ctx.read_metadata(0)
+    assert (md.alive_count, md.max_update, md.max_spawn, md.particle_counter) == (0, 0, 256, 0)
+    assert ctx.read_draw_args(0).instance_count == 0
+    assert ctx.read_batch_info(0).total_update_count == 0
+    ind = ctx.slab_download_indirect(slab, 0, 256)
+    np.testing.assert_array_equal(ind[:, 2], np.arange(256))
+
+
+def test_epoch_wrap(native, orc, monkeypatch):
+    """The look-back's tile states carry a 30-bit frame epoch; frames across the wrap must stay exact."""
+    monkeypatch.setenv("HNB_EPOCH_START", str(0x3fffffff - 3))
+    c = native.Context(0)
+    try:
+        rng = np.random.default_rng(3)
+        n = 200_000
+        ref = RefWorld(n, 8, [Instance(0, n, alive=n, seed=9)])
+        p = np.zeros((n, 8), dtype=np.float32)
+        p[:, 0:3] = rng.uniform(-1, 1, (n, 3)); p[:, 4:7] = rng.uniform(-1, 1, (n, 3)); p[:, 7] = rng.uniform(0.01, 0.2, n)
+        ref.particles[:] = p.view(np.uint32)
+        gpu = GpuWorld(c, ref, recipes.c5_lowered())
+        k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+        for step in range(8):
+            ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+            gpu.frame()
+            assert_world_equal(ref, gpu.pull(), what=f"step {step}")
+    finally:
+        c.close()
+
+
 # ---- randomised expression graphs ---------------------------------------------------------------------
 hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, Phase, given, settings, strategies as st  # noqa: E402
