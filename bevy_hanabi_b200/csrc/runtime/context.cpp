@@ -268,7 +268,10 @@ template <typename T> void grow_device(T*& p, uint32_t& rows, uint32_t need, cud
 
 void ensure_scratch(hnb_ctx* c) {
     if (c->E > c->scratch_E) {
-        if (c->d_tile_prefix) cudaFree(c->d_tile_prefix);
+        if (c->d_tile_prefix) {
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));  // earlier frames may still read the old table
+            cudaFree(c->d_tile_prefix);
+        }
         uint32_t cap = std::max<uint32_t>(c->E * 2, 64);
         CUDA_CHECK(cudaMalloc((void**)&c->d_tile_prefix, size_t(cap) * 4));
         CUDA_CHECK(cudaMemsetAsync(c->d_tile_prefix, 0, size_t(cap) * 4, c->stream));
@@ -305,11 +308,12 @@ hnb::StaticTables static_tables(hnb_ctx* c) {
     T.metadata = c->d_metadata;
     T.draw_args = c->d_draw_args;
     T.child_infos = c->d_child_infos;
-    T.num_child_infos = c->child_rows ? c->child_rows : 0;
+    T.num_child_infos = c->child_rows;
     return T;
 }
 
-// One host->device copy of the frame block. `with_tables` false: only the 64-byte header.
+// One host->device copy of the frame block: everything when the tables changed, else the header + per-frame
+// ranges (`with_ranges`), else only the 64-byte header.
 void flush_arena(hnb_ctx* c, bool with_ranges) {
     if (!c->h_arena) ensure_arena(c, c->E, c->B);
     size_t bytes;
@@ -732,9 +736,7 @@ int32_t hnb_slab_create(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, hnb
         s.planes = cut_planes(stride);
         for (size_t p = 0; p < s.planes.size(); ++p) {
             CUDA_CHECK(cudaMalloc(&s.d_planes[p], size_t(capacity_rows) * s.planes[p].width));
-#ifndef NDEBUG
-            // debug builds of the reference poison particle buffers (effect_cache.rs:284-296)
-#endif
+            // zero-filled (debug builds of the reference poison the particle buffer instead, effect_cache.rs:284-296)
             CUDA_CHECK(cudaMemsetAsync(s.d_planes[p], 0, size_t(capacity_rows) * s.planes[p].width, c->stream));
         }
         CUDA_CHECK(cudaMalloc((void**)&s.ping, size_t(capacity_rows) * 4));
