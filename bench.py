@@ -58,22 +58,57 @@ def parse_args():
 # clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region. NVML in a thread (a query takes microseconds,
+    so even a 40 ms timed region gets dozens of samples); `nvidia-smi -lms` as a fallback when pynvml is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.samples = []
+        self.samples = []          # nvidia-smi csv lines (fallback)
+        self.sm, self.reason_bits = [], 0
+        self.sm_max = None
         self.proc = None
         self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
         try:
+            nv, h = self._nvml_handle()
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+            self.nv = nv
+            self.source = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
+        self.source = "nvidia-smi"
         def pump():
             for line in self.proc.stdout:
                 self.samples.append(line.strip())
@@ -81,8 +116,17 @@ class ClockSampler:
         self.thread.start()
 
     def stop(self):
+        if self.source == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv, bits = self.nv, self.reason_bits
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(n for n, b in names if bits & b), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -101,7 +145,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
