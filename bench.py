@@ -186,10 +186,17 @@ class CpuC5:
     def calibrate(self):
         """Pick the OpenMP thread count that is actually fastest on this host: "all logical CPUs" can be far from it
         (hyper-threads, or a container CPU quota below the affinity mask makes spinning OpenMP barriers collapse).
-        Times two frames for max, max/2 and max/4 threads and keeps the best."""
+        Times two frames for max, max/2, ... max/16 threads (and the cgroup CPU quota) and keeps the best."""
         best_t, best_threads = None, self.threads
         top = self.threads
-        for threads in sorted({top, max(1, top // 2), max(1, top // 4)}, reverse=True):
+        candidates = {max(1, top >> k) for k in range(5)}  # max, max/2, ..., max/16
+        try:  # cgroup v2 CPU quota, e.g. "1600000 100000" = 16 CPUs worth of time
+            quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if quota != "max":
+                candidates.add(max(1, min(top, int(quota) // int(period))))
+        except Exception:
+            pass
+        for threads in sorted(candidates, reverse=True):
             self.threads = threads
             self.step()
             t0 = time.perf_counter()
@@ -224,7 +231,7 @@ def cpu_baseline(seconds: float, sample: int = 8 * 1024 * 1024):
             break
     return {"value": sample * steps / el, "unit": UNIT, "cores": arm.threads, "kind": "port",
             "sample": f"{steps} full frames (indirect+prefix-sum+update) of a {sample}-particle C5 instance, {el:.1f} s wall, "
-                      f"oracle/vfx_oracle.c OpenMP x{arm.threads} (fastest of max, max/2, max/4 threads)",
+                      f"oracle/vfx_oracle.c OpenMP x{arm.threads} (fastest of max, max/2 ... max/16 threads)",
             "gbps": BYTES_PER_PARTICLE_STEP * sample * steps / el / 1e9}
 
 
@@ -253,7 +260,7 @@ def run_reference(args):
                    "particles_per_step": sample, "dt": DT},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": "port",
                          "sample": f"one full frame (indirect+prefix-sum+update) of an {sample}-particle C5 instance per step, {steps} steps, OpenMP x{arm.threads} "
-                                   "(fastest of max, max/2, max/4 threads; oracle port: the Rust/wgpu reference cannot be built in this image)"},
+                                   "(fastest of max, max/2 ... max/16 threads; oracle port: the Rust/wgpu reference cannot be built in this image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
