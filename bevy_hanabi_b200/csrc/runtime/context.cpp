@@ -676,9 +676,9 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
             CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
             c->own_stream = true;
         }
-        if (const char* e = getenv("HNB_TILE_CHUNKS")) c->tile_chunks_override = (uint32_t)atoi(e);
-        if (const char* e = getenv("HNB_EPOCH_START")) c->epoch = uint32_t(strtoul(e, nullptr, 0)) & 0x3fffffffu;  // tests: start near the wrap
-        if (const char* e = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::min(atoi(e), 31);
+        if (const char* env = getenv("HNB_TILE_CHUNKS")) c->tile_chunks_override = (uint32_t)atoi(env);
+        if (const char* env = getenv("HNB_EPOCH_START")) c->epoch = uint32_t(strtoul(env, nullptr, 0)) & 0x3fffffffu;  // tests: start near the wrap
+        if (const char* env = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::max(0, std::min(atoi(env), 31));
         ensure_arena(c.get(), 0, 0);
         CUDA_CHECK(cudaMalloc((void**)&c->d_debug, 16 * 8));
         CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
