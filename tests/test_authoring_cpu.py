@@ -386,3 +386,16 @@ def test_swizzle_of_infix_expression_is_parenthesised():
     a2 = (G.EffectAsset(8, w2.module).init(G.SetAttributeModifier(G.Attribute.POSITION, w2.lit(G.Vec3(0, 0, 0))))
           .update(G.SetAttributeModifier(G.Attribute.F32_0, e2)))
     assert "particle.f32_0 = max(particle.velocity, particle.position).y;" in a2.generate().update_code
+
+
+def test_effect_properties_serialize_reference_vector():
+    """properties.rs:1395-1421 `effect_properties_serialize`: {a: 3.0, b: Vec3::ONE} -> blob of cpu_size bytes with
+    each value at its layout offset."""
+    a = _asset_with_props([("a", 3.0), ("b", G.Vec3(1, 1, 1))])
+    fields, size = a.property_layout()
+    off = {f.name: f.offset for f in fields}
+    assert off == {"b": 0, "a": 12} and size == 16   # vec3 first, the f32 pairs into its padding
+    blob = a.serialize_properties()
+    assert len(blob) == 16                            # cpu_size = offset of the last entry + its size
+    assert blob[off["a"]:off["a"] + 4] == struct.pack("<f", 3.0)
+    assert blob[off["b"]:off["b"] + 12] == struct.pack("<3f", 1.0, 1.0, 1.0)

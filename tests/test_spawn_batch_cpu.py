@@ -165,3 +165,40 @@ def test_effect_sorter_levels_slabs_and_errors():
     cyc.insert(2, 0, 8, parent=1)
     with pytest.raises(HanabiError):
         cyc.sort()
+
+
+def test_once_reset():
+    """spawn.rs:1163-1173 `test_once_reset`."""
+    st = SpawnerSettings.once(5.0)
+    assert st.is_once()
+    sp = EffectSpawner(st)
+    sp.tick(1.0)
+    sp.reset()
+    assert sp.tick(1.0) == 5
+
+
+def test_rate_active():
+    """spawn.rs:1230-1244 `test_rate_active`: an inactive spawner neither spawns nor accumulates."""
+    sp = EffectSpawner(SpawnerSettings.rate(5.0))
+    sp.tick(1.01)
+    sp.active = False
+    assert not sp.active
+    assert sp.tick(0.4) == 0
+    sp.active = True
+    assert sp.active
+    assert sp.tick(0.4) == 2
+
+
+def test_rate_accumulate():
+    """spawn.rs:1247-1255 `test_rate_accumulate`: fractions of a particle carry over from tick to tick."""
+    sp = EffectSpawner(SpawnerSettings.rate(5.0))
+    assert sum(sp.tick(1.0 / 60.0) for _ in range(13)) == 1
+
+
+def test_uniform_range_is_ordered():
+    """spawn.rs:1027-1042 `test_range_*`: CpuValue::range() returns [min, max] whatever the order given; a uniform
+    count therefore samples between the two bounds."""
+    for bounds in ((1.0, 3.0), (3.0, 1.0)):
+        sp = EffectSpawner(SpawnerSettings.once(bounds), rng_seed=5)
+        n = sp.tick(1.0)
+        assert 1 <= n <= 3
