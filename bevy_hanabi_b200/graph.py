@@ -295,20 +295,20 @@ for _op in TERNARY:
 # ---------------------------------------------------------------------------------------------------
 class WriterExpr:
     def __init__(self, writer: "ExprWriter", handle: int):
-        self.w = writer
+        self.writer = writer
         self.h = handle
 
     def expr(self) -> int:
         return self.h
 
     def _wrap(self, other) -> "WriterExpr":
-        return other if isinstance(other, WriterExpr) else self.w.lit(other)
+        return other if isinstance(other, WriterExpr) else self.writer.lit(other)
 
     def _un(self, op):
-        return WriterExpr(self.w, self.w.module.unary(op, self.h))
+        return WriterExpr(self.writer, self.writer.module.unary(op, self.h))
 
     def _bin(self, op, other):
-        return WriterExpr(self.w, self.w.module.binary(op, self.h, self._wrap(other).h))
+        return WriterExpr(self.writer, self.writer.module.binary(op, self.h, self._wrap(other).h))
 
     def __add__(self, o): return self._bin("add", o)
     def __sub__(self, o): return self._bin("sub", o)
@@ -339,20 +339,20 @@ class WriterExpr:
         return self._wrap(edge)._bin("step", self)
 
     def mix(self, other, fraction):
-        return WriterExpr(self.w, self.w.module.ternary("mix", self.h, self._wrap(other).h, self._wrap(fraction).h))
+        return WriterExpr(self.writer, self.writer.module.ternary("mix", self.h, self._wrap(other).h, self._wrap(fraction).h))
 
     def clamp(self, lo, hi):
-        return WriterExpr(self.w, self.w.module.ternary("clamp", self.h, self._wrap(lo).h, self._wrap(hi).h))
+        return WriterExpr(self.writer, self.writer.module.ternary("clamp", self.h, self._wrap(lo).h, self._wrap(hi).h))
 
     def smoothstep(self, lo, hi):
         """``x.smoothstep(lo, hi)`` emits ``smoothstep(lo, hi, x)`` (expr.rs:3819-3822)."""
-        return WriterExpr(self.w, self.w.module.ternary("smoothstep", self._wrap(lo).h, self._wrap(hi).h, self.h))
+        return WriterExpr(self.writer, self.writer.module.ternary("smoothstep", self._wrap(lo).h, self._wrap(hi).h, self.h))
 
     def vec3(self, y, z):
-        return WriterExpr(self.w, self.w.module.ternary("vec3", self.h, self._wrap(y).h, self._wrap(z).h))
+        return WriterExpr(self.writer, self.writer.module.ternary("vec3", self.h, self._wrap(y).h, self._wrap(z).h))
 
     def cast(self, vt: int):
-        return WriterExpr(self.w, self.w.module.cast(self.h, vt))
+        return WriterExpr(self.writer, self.writer.module.cast(self.h, vt))
 
 
 for _op in UNARY:
