@@ -135,3 +135,45 @@ def test_random_typed_graphs_compile_and_interpret(orc, data):
             ref.set_spawns([40 if f == 0 else 5])
             eo.frame(ref, orc)
     assert ref.metadata[0].particle_counter == 45
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), phases=[Phase.generate], derandomize=True)
+@given(st.data())
+def test_random_exact_graphs_generated_code_equals_interpreter(orc, data):
+    """Values, not just syntax: random graphs over the IEEE-exact operators (the generator of the GPU fuzz test), with
+    the generated code executed on the CPU (tests/host_exec.py) and compared bit for bit with the interpreter."""
+    from tests.host_exec import HostEffect, replay_frame
+    from tests.test_gpu_misc import _build as build_exact
+    w = G.ExprWriter()
+    f_expr = build_exact(data.draw, w, data.draw(st.integers(1, 3)), "f")
+    v_expr = build_exact(data.draw, w, data.draw(st.integers(1, 3)), "v")
+    asset = (G.EffectAsset(256, w.module, name="exact_fuzz")
+             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(4.) - w.lit(2.)))
+             .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) - w.lit(0.5)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+             .init(G.SetAttributeModifier(A.LIFETIME, w.lit(0.05).uniform(w.lit(0.2))))
+             .init(G.SetAttributeModifier(A.F32_1, w.rand() * w.lit(3.)))
+             .update(G.SetAttributeModifier(A.F32_0, f_expr))
+             .update(G.SetAttributeModifier(A.F32X3_0, v_expr)))
+    fx = asset.generate()
+    host = HostEffect(fx)
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(256, size // 4, [Instance(0, 256, alive=0, seed=data.draw(st.integers(0, 2**32 - 1)))])
+    eo = EffectOracle(asset)
+
+    def canon(a, b):
+        a, b = a.copy(), b.copy()
+        fa, fb = a.view(np.float32), b.view(np.float32)
+        same = (np.isnan(fa) & np.isnan(fb)) | ((fa == 0) & (fb == 0))  # any NaN == any NaN; min/max may return either zero
+        a[same] = 0
+        b[same] = 0
+        return a, b
+
+    with np.errstate(all="ignore"):
+        for f in range(3):
+            ref.sim.time = np.float32(f) * ref.sim.delta_time
+            ref.set_spawns([120 if f == 0 else 30])
+            ih, io, uh, uo, ah, ao = replay_frame(host, eo, ref, orc)
+            np.testing.assert_array_equal(*canon(ih, io), err_msg="init records\n" + fx.init_code)
+            np.testing.assert_array_equal(*canon(uh, uo), err_msg="update records\n" + fx.update_code)
+            np.testing.assert_array_equal(ah, ao)
