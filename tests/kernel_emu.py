@@ -1,0 +1,322 @@
+"""Runs the real `hnb_init` / `hnb_update` kernel templates on the CPU: test infrastructure for `-m "not gpu"` runs.
+
+The full generated translation unit of an effect (vocabulary + tables + generated bodies + hnb_particle_kernels.cuh)
+is compiled with g++ behind a small emulation layer: every CUDA thread is an OS thread, a warp is 32 threads with a
+barrier and an exchange array (`__ballot_sync`, `__shfl_sync`, `__syncwarp`), a CTA adds a 256-thread barrier, its
+dynamic shared memory and its static shared words; atomics are `__atomic` builtins. The three inline-PTX helpers of
+the kernels (relaxed 64-bit load / store of a tile state, `%lanemask_lt`) and the two shared-memory declarations are
+replaced textually (asserted) — nothing else of the kernel text changes. The grid is a handful of CTAs, so tile
+tickets, the look-back chain, deferred compaction, the dead-stack writes and the last-tile bookkeeping all run
+exactly as written, under real (OS-scheduled) concurrency.
+
+What is NOT emulated: the effect-independent bookkeeping kernel between init and update (its semantics come from the
+C oracle's indirect / prefix-sum restatements plus the deferred init accounting restated in `EmuWorld.frame`), GPU
+spawn events, and of course timing. The GPU suite covers those on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from oracle import c_oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "build" / "kernel_emu"
+
+PRELUDE = r"""
+#include <math.h>
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+#define __device__
+#define __forceinline__ inline
+#define __global__
+#define __launch_bounds__(...)
+#define __align__(n)
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r = {x, y}; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
+static inline float __uint_as_float(unsigned int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned int __float_as_uint(float f) { unsigned int u; memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+namespace emu {
+struct Warp { pthread_barrier_t bar; unsigned long long slot[32]; };
+struct Cta { pthread_barrier_t bar; unsigned char* dyn; unsigned int statics[16]; Warp warps[8]; };
+struct Tls { unsigned tid, bid, lane; Cta* cta; Warp* warp; };
+static thread_local Tls tls;
+struct Dim3 { unsigned x, y, z; };
+static inline void warp_sync() { pthread_barrier_wait(&tls.warp->bar); }
+static inline unsigned char* dyn_smem() { return tls.cta->dyn; }
+static inline unsigned int* static_u32(int i) { return &tls.cta->statics[i]; }
+template <typename T> static inline T exchange(T v, unsigned src) {
+    unsigned long long raw = 0; memcpy(&raw, &v, sizeof(T));
+    tls.warp->slot[tls.lane] = raw;
+    warp_sync();
+    unsigned long long got = tls.warp->slot[src & 31u];
+    warp_sync();
+    T out; memcpy(&out, &got, sizeof(T));
+    return out;
+}
+}  // namespace emu
+#define threadIdx (emu::Dim3{emu::tls.tid, 0u, 0u})
+#define blockIdx (emu::Dim3{emu::tls.bid, 0u, 0u})
+static inline void __syncwarp() { emu::warp_sync(); }
+static inline void __syncthreads() { pthread_barrier_wait(&emu::tls.cta->bar); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    emu::tls.warp->slot[emu::tls.lane] = pred ? 1ull : 0ull;
+    emu::warp_sync();
+    unsigned m = 0;
+    for (unsigned i = 0; i < 32; ++i) m |= unsigned(emu::tls.warp->slot[i]) << i;
+    emu::warp_sync();
+    return m;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, unsigned(src)); }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int d) { return emu::exchange(v, emu::tls.lane ^ unsigned(d)); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(unsigned x) { return __builtin_ffs(int(x)); }
+static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicSub(unsigned* p, unsigned v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+"""
+
+# exact kernel-source lines that need a host spelling (asserted to be present: the harness follows the product text)
+SUBSTITUTIONS = [
+    ('HNB_DI void hnb_st_state(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }',
+     'HNB_DI void hnb_st_state(u64* p, u64 v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }'),
+    ('    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");',
+     '    v = __atomic_load_n(p, __ATOMIC_RELAXED); sched_yield();  /* a poll: let the OS run somebody else */'),
+    ('    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));', '    m = (1u << emu::tls.lane) - 1u;'),
+    ('    extern __shared__ __align__(16) unsigned char hnb_smem[];', '    unsigned char* const hnb_smem = emu::dyn_smem();'),
+    ('    __shared__ u32 sh_first_ticket;', '    u32& sh_first_ticket = *emu::static_u32(0);'),
+]
+
+DRIVER = r"""
+struct EmuBatch {
+    void* frame; void* spawners; uint32_t* spawn_prefix; uint32_t* prefix_sum; uint32_t* tile_prefix; void* batch_info;
+    uint32_t* batch_tiles; uint32_t* ticket; unsigned long long* tile_state; void* metadata; uint32_t* draw_args; void* properties;
+    void* planes[16]; uint32_t* ping; uint32_t* pong; uint32_t* dead;
+    uint32_t capacity, init_thread_count, properties_stride, tile_rows;
+};
+static hnb::BatchParams make_params(const EmuBatch* b) {
+    hnb::BatchParams P;
+    memset((void*)&P, 0, sizeof(P));
+    P.frame = (const hnb::FrameHeader*)b->frame;
+    P.spawners = (hnb::Spawner*)b->spawners;
+    P.spawn_prefix = b->spawn_prefix;
+    P.prefix_sum = b->prefix_sum;
+    P.tile_prefix = b->tile_prefix;
+    P.batch_info = (const hnb::BatchInfo*)b->batch_info;
+    P.batch_tiles = b->batch_tiles;
+    P.ticket = b->ticket;
+    P.tile_state = b->tile_state;
+    P.metadata = (hnb::EffectMetadata*)b->metadata;
+    P.draw_args = b->draw_args;
+    P.properties = b->properties;
+    for (int p = 0; p < 16; ++p) P.slab.planes[p] = b->planes[p];
+    P.slab.particle_index[0] = b->ping;
+    P.slab.particle_index[1] = b->pong;
+    P.slab.dead_index = b->dead;
+    P.slab.capacity_rows = b->capacity;
+    P.init_thread_count = b->init_thread_count;
+    P.properties_stride = b->properties_stride;
+    P.tile_rows = b->tile_rows;
+    return P;
+}
+template <typename K> static void emu_launch(K kernel, const hnb::BatchParams& P, unsigned grid, size_t smem) {
+    std::vector<emu::Cta> ctas(grid);
+    std::vector<std::vector<unsigned char>> dyn(grid, std::vector<unsigned char>(smem + 64));
+    for (unsigned b = 0; b < grid; ++b) {
+        pthread_barrier_init(&ctas[b].bar, nullptr, HNB_BLOCK);
+        ctas[b].dyn = (unsigned char*)(((uintptr_t)dyn[b].data() + 15) & ~(uintptr_t)15);
+        memset(ctas[b].statics, 0, sizeof(ctas[b].statics));
+        for (int w = 0; w < HNB_BLOCK / 32; ++w) pthread_barrier_init(&ctas[b].warps[w].bar, nullptr, 32);
+    }
+    std::vector<std::thread> threads;
+    threads.reserve(size_t(grid) * HNB_BLOCK);
+    for (unsigned b = 0; b < grid; ++b)
+        for (unsigned t = 0; t < HNB_BLOCK; ++t)
+            threads.emplace_back([&, b, t] {
+                emu::tls.tid = t; emu::tls.bid = b; emu::tls.lane = t & 31u;
+                emu::tls.cta = &ctas[b]; emu::tls.warp = &ctas[b].warps[t >> 5];
+                kernel(P);
+            });
+    for (auto& th : threads) th.join();
+    for (unsigned b = 0; b < grid; ++b) {
+        pthread_barrier_destroy(&ctas[b].bar);
+        for (int w = 0; w < HNB_BLOCK / 32; ++w) pthread_barrier_destroy(&ctas[b].warps[w].bar);
+    }
+}
+extern "C" void emu_init(const EmuBatch* b, uint32_t blocks) { emu_launch(hnb::hnb_init, make_params(b), blocks, 0); }
+extern "C" void emu_update(const EmuBatch* b, uint32_t blocks, uint32_t smem) { emu_launch(hnb::hnb_update, make_params(b), blocks, smem); }
+extern "C" void emu_aos_to_planes(const EmuBatch* b, const uint8_t* aos, uint32_t first, uint32_t count, uint32_t stride) {
+    hnb::BatchParams P = make_params(b);
+    for (uint32_t r = 0; r < count; ++r) {
+        hnb::RawParticle raw; memset((void*)&raw, 0, sizeof(raw));
+        memcpy((void*)&raw, aos + size_t(r) * stride, stride);
+        hnb::hnb_store_raw(raw, P.slab, first + r);
+    }
+}
+extern "C" void emu_planes_to_aos(const EmuBatch* b, uint8_t* aos, uint32_t first, uint32_t count, uint32_t stride) {
+    hnb::BatchParams P = make_params(b);
+    for (uint32_t r = 0; r < count; ++r) {
+        hnb::RawParticle raw;
+        hnb::hnb_load_raw(raw, P.slab, first + r);
+        memcpy(aos + size_t(r) * stride, (const void*)&raw, stride);
+    }
+}
+extern "C" uint32_t emu_tile_k(void) { return HNB_TILE_K; }
+extern "C" uint32_t emu_rows_per_lane(void) { return HNB_ROWS_PER_LANE; }
+extern "C" uint32_t emu_init_items(void) { return HNB_INIT_ITEMS; }
+"""
+
+
+class EmuBatch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("frame", "spawners", "spawn_prefix", "prefix_sum", "tile_prefix", "batch_info", "batch_tiles", "ticket",
+                                          "tile_state", "metadata", "draw_args", "properties")] + \
+               [("planes", C.c_void_p * 16), ("ping", C.c_void_p), ("pong", C.c_void_p), ("dead", C.c_void_p),
+                ("capacity", C.c_uint32), ("init_thread_count", C.c_uint32), ("properties_stride", C.c_uint32), ("tile_rows", C.c_uint32)]
+
+
+def build_emulated_effect(lowered) -> C.CDLL:
+    src = lowered.generate_source()
+    if "#define HNB_EMIT_EVENTS 1" in src or "#define HNB_READ_PARENT 1" in src or "#define HNB_CONSUME_EVENTS 1" in src:
+        raise NotImplementedError("the kernel emulation covers effects without GPU spawn events")
+    for old, new in SUBSTITUTIONS:
+        assert src.count(old) == 1, f"kernel source changed, update tests/kernel_emu.py: {old!r}"
+        src = src.replace(old, new)
+    # the remaining `asm` statements sit in #if HNB_PROFILE blocks, which are compiled out (HNB_PROFILE is 0)
+    text = PRELUDE + src + DRIVER
+    OUT.mkdir(parents=True, exist_ok=True)
+    tag = hashlib.sha1(text.encode()).hexdigest()[:16]
+    cpp, so = OUT / f"emu_{tag}.cpp", OUT / f"emu_{tag}.so"
+    if not so.exists():
+        cpp.write_text(text)
+        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread", "-w", str(cpp), "-o", str(so)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("host build of the kernel templates failed:\n" + proc.stderr[:6000])
+    lib = C.CDLL(str(so))
+    lib.emu_init.argtypes = [C.POINTER(EmuBatch), C.c_uint32]
+    lib.emu_update.argtypes = [C.POINTER(EmuBatch), C.c_uint32, C.c_uint32]
+    lib.emu_aos_to_planes.argtypes = [C.POINTER(EmuBatch), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.emu_planes_to_aos.argtypes = [C.POINTER(EmuBatch), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    for f in ("emu_init", "emu_update", "emu_aos_to_planes", "emu_planes_to_aos"):
+        getattr(lib, f).restype = None
+    for f in ("emu_tile_k", "emu_rows_per_lane", "emu_init_items"):
+        getattr(lib, f).restype = C.c_uint32
+    return lib
+
+
+class EmuWorld:
+    """One batch (all instances of `ref`) simulated by the emulated kernels, starting from `ref`'s current state."""
+
+    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None):
+        self.ref, self.lib = ref, build_emulated_effect(lowered)
+        self.stride = ref.stride_words * 4
+        assert lowered.particle_stride == self.stride
+        n, rows = len(ref.instances), ref.slab_rows
+        self.n, self.rows = n, rows
+        k = self.lib.emu_tile_k()
+        assert chunks * k <= self.lib.emu_rows_per_lane()
+        self.tile = 32 * k * chunks
+        self.update_ctas = update_ctas
+        u32 = np.uint32
+        self.planes = [np.zeros(rows * 4, dtype=u32) for _ in range(16)]          # 16 B per row is the widest plane
+        self.cols = [np.ascontiguousarray(ref.indirect[:, c]).copy() for c in range(3)]
+        self.metadata = (O.EffectMetadata * n).from_buffer_copy(bytes(ref.metadata))
+        self.spawners = (O.Spawner * n).from_buffer_copy(bytes(ref.spawners))
+        self.draw = ref.draw.copy()
+        self.spawn_prefix = np.zeros(n, dtype=u32)
+        self.prefix_sum = np.zeros(n, dtype=u32)
+        self.tile_prefix = np.zeros(n + 1, dtype=u32)
+        self.batch_info = (O.BatchInfo * 1)(O.BatchInfo(0, 0, 0, 0, 0, n))
+        self.batch_tiles = np.zeros(1, dtype=u32)
+        self.ticket = np.zeros(1, dtype=u32)
+        self.tile_state = np.zeros(rows // self.tile + n + 2, dtype=np.uint64)
+        self.frame = np.zeros(16, dtype=u32)                                       # FrameHeader: SimParams (7 words) | epoch | num_batches
+        self.dispatch = np.zeros(3, dtype=u32)
+        self.epoch = 0
+        self.props = None
+        self.props_stride = 0
+        if property_blobs:
+            self.props_stride = (len(property_blobs[0]) + 15) // 16 * 16
+            buf = bytearray(self.props_stride * len(property_blobs))
+            for i, b in enumerate(property_blobs):
+                buf[i * self.props_stride: i * self.props_stride + len(b)] = b
+            self.props = np.frombuffer(bytes(buf), dtype=np.uint8).copy()
+        self.b = EmuBatch()
+        self._bind()
+        aos = np.ascontiguousarray(ref.particles)
+        self.lib.emu_aos_to_planes(C.byref(self.b), aos.ctypes.data, 0, rows, self.stride)
+
+    def _bind(self):
+        b, ptr = self.b, lambda a: a.ctypes.data
+        b.frame, b.spawners, b.spawn_prefix, b.prefix_sum, b.tile_prefix = ptr(self.frame), C.addressof(self.spawners), ptr(self.spawn_prefix), ptr(self.prefix_sum), ptr(self.tile_prefix)
+        b.batch_info, b.batch_tiles, b.ticket, b.tile_state = C.addressof(self.batch_info), ptr(self.batch_tiles), ptr(self.ticket), ptr(self.tile_state)
+        b.metadata, b.draw_args = C.addressof(self.metadata), ptr(self.draw)
+        b.properties = ptr(self.props) if self.props is not None else None
+        for p in range(16):
+            b.planes[p] = ptr(self.planes[p])
+        b.ping, b.pong, b.dead = ptr(self.cols[0]), ptr(self.cols[1]), ptr(self.cols[2])
+        b.capacity, b.properties_stride, b.tile_rows = self.rows, self.props_stride, self.tile
+
+    def frame_step(self, orc, sim, spawns, seeds):
+        """One simulate(): init kernel -> bookkeeping (restated) -> update kernel. `sim`: the oracle world's SimParams."""
+        u32p = C.POINTER(C.c_uint32)
+        n = self.n
+        self.frame[:7] = np.frombuffer(bytes(sim), dtype=np.uint32)
+        self.epoch += 1
+        self.frame[7], self.frame[8] = self.epoch, 1
+        run = 0
+        for i in range(n):
+            self.spawners[i].spawn, self.spawners[i].seed = int(spawns[i]), int(seeds[i]) & 0xFFFFFFFF
+            self.spawn_prefix[i] = run
+            run += max(0, int(spawns[i]))
+        self.prefix_sum[:] = self.spawn_prefix
+        # ---- init (vfx_init.wgsl): ceil64(total) logical threads, HNB_INIT_ITEMS of them per emulated thread
+        threads = (run + 63) // 64 * 64
+        self.b.init_thread_count = threads
+        if threads:
+            per_block = 256 * self.lib.emu_init_items()
+            self.lib.emu_init(C.byref(self.b), (threads + per_block - 1) // per_block)
+        # ---- bookkeeping: deferred init accounting (the kernel assigned ranks instead of bumping the counters) ...
+        for i in range(n):
+            md = self.metadata[i]
+            passed = min(max(0, int(spawns[i])), md.max_spawn)
+            md.alive_count += passed
+            md.particle_counter += passed
+        # ... then vfx_indirect + vfx_prefix_sum as restated by the C oracle, and the tile prefix of this launch
+        orc.orc_indirect(self.frame.ctypes.data_as(C.POINTER(O.SimParams)), self.metadata, self.draw.ctypes.data_as(u32p), self.spawners,
+                         self.prefix_sum.ctypes.data_as(u32p), None, 0)
+        alive = self.prefix_sum.copy()
+        orc.orc_prefix_sum(self.batch_info, 1, self.prefix_sum.ctypes.data_as(u32p), self.dispatch.ctypes.data_as(u32p))
+        tiles = (alive + self.tile - 1) // self.tile
+        self.tile_prefix[:n] = np.concatenate([[0], np.cumsum(tiles)[:-1]]) if n else []
+        self.tile_prefix[n] = tiles.sum()
+        self.batch_tiles[0] = tiles.sum()
+        self.ticket[0] = 0
+        # ---- update (vfx_update.wgsl): a persistent grid of a few CTAs
+        self.lib.emu_update(C.byref(self.b), self.update_ctas, 64 * 1024)
+
+    def pull(self):
+        aos = np.zeros((self.rows, self.stride // 4), dtype=np.uint32)
+        self.lib.emu_planes_to_aos(C.byref(self.b), aos.ctypes.data, 0, self.rows, self.stride)
+        return {"particles": aos, "indirect": np.stack(self.cols, axis=1),
+                "metadata": np.frombuffer(bytes(self.metadata), dtype=np.uint32).reshape(self.n, 15).copy(), "draw": self.draw.copy(),
+                "prefix": self.prefix_sum.copy(), "total_update": self.batch_info[0].total_update_count}

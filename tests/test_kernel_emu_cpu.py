@@ -1,0 +1,163 @@
+"""The real kernel templates (hnb_init / hnb_update of hnb_particle_kernels.cuh) executed on the CPU under the thread
+emulation of tests/kernel_emu.py, against the oracle: alive lists in canonical order, dead stack, counters,
+draw-indirect counts and every particle word, bit for bit — the same bar as the GPU suite, on small worlds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bevy_hanabi_b200 import graph as G
+from bevy_hanabi_b200 import recipes
+from oracle.hanabi_oracle import EffectOracle, pcg_hash
+from tests.helpers import Instance, RefWorld
+from tests.kernel_emu import EmuWorld
+from tests.test_gpu_effects import _firework_trails
+from tests.test_gpu_scene import _drifting_sparks
+
+A = G.Attribute
+
+
+def _assert_same(ref, got, what):
+    np.testing.assert_array_equal(got["metadata"], ref.metadata_rows(), err_msg=f"{what}: metadata")
+    np.testing.assert_array_equal(got["draw"], ref.draw, err_msg=f"{what}: draw args")
+    np.testing.assert_array_equal(got["prefix"], ref.prefix, err_msg=f"{what}: prefix sums")
+    assert got["total_update"] == ref.batch_infos[0].total_update_count
+    np.testing.assert_array_equal(got["indirect"], ref.indirect, err_msg=f"{what}: ping / pong / dead")
+    np.testing.assert_array_equal(got["particles"], ref.particles, err_msg=f"{what}: particles")
+
+
+def _c5_world(rng, insts):
+    ref = RefWorld(sum(i.capacity for i in insts), 8, insts)
+    for inst in ref.instances:
+        n = inst.alive
+        p = np.zeros((n, 8), dtype=np.float32)
+        p[:, 0:3] = rng.uniform(-1, 1, (n, 3)); p[:, 4:7] = rng.uniform(-1, 1, (n, 3)); p[:, 7] = rng.uniform(0.02, 0.15, n)
+        ref.particles[inst.slab_offset:inst.slab_offset + n] = p.view(np.uint32)
+    return ref
+
+
+@pytest.mark.parametrize("chunks,ctas", [(1, 1), (1, 3), (2, 2), (4, 2)])
+def test_update_kernel_c5_single_instance(orc, chunks, ctas):
+    """Tile tickets, look-back across 10-40 tiles, deferred compaction, dead-stack pushes, last-tile totals."""
+    rng = np.random.default_rng(chunks * 10 + ctas)
+    ref = _c5_world(rng, [Instance(0, 5000, alive=4700, seed=42)])
+    emu = EmuWorld(ref, recipes.c5_lowered(), chunks=chunks, update_ctas=ctas)
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    for step in range(5):
+        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        emu.frame_step(orc, ref.sim, [0], [42])
+        _assert_same(ref, emu.pull(), f"step {step}")
+    assert 0 < ref.metadata[0].alive_count < 4700
+
+
+def test_update_kernel_many_instances_one_batch(orc):
+    """Instances smaller than, equal to and larger than a tile, empty ones, in one launch: per-tile instance lookup,
+    one look-back chain per instance."""
+    rng = np.random.default_rng(3)
+    caps = [40, 128, 129, 700, 1, 256, 90, 1500]
+    alive = [40, 128, 100, 650, 0, 256, 0, 1400]
+    insts, off = [], 0
+    for c, a in zip(caps, alive):
+        insts.append(Instance(off, c, alive=a, seed=off + 5))
+        off += c
+    ref = _c5_world(rng, insts)
+    emu = EmuWorld(ref, recipes.c5_lowered(), chunks=1, update_ctas=2)
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    seeds = [i.seed for i in insts]
+    for step in range(4):
+        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        emu.frame_step(orc, ref.sim, [0] * len(insts), seeds)
+        _assert_same(ref, emu.pull(), f"step {step}")
+
+
+@pytest.mark.parametrize("name", ["trails", "sparks"])
+def test_init_and_update_kernels_authored_effects(orc, name):
+    """Bursts into recycled slots: rank-based dead-slot pops of hnb_init (4 spawns per thread), spawn caps, then the
+    update kernel on the grown lists — against the numpy interpreter of the same effect."""
+    asset = {"trails": _firework_trails, "sparks": _drifting_sparks}[name](1500)
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(1500, size // 4, [Instance(0, 1500, alive=0, seed=1)], dt=1.0 / 10.0)
+    eo = EffectOracle(asset)
+    emu = EmuWorld(ref, asset.generate(), chunks=1, update_ctas=2)
+    recycled = False
+    for f in range(7):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn = [900 if f % 3 == 0 else 37]
+        seed = [int(pcg_hash(np.array([0x1234 + f], dtype=np.uint32))[0])]
+        ref.set_spawns(spawn, seed)
+        before = ref.metadata[0].particle_counter
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        _assert_same(ref, emu.pull(), f"frame {f}")
+        recycled |= ref.metadata[0].particle_counter - before < spawn[0] or ref.metadata[0].particle_counter > 1500
+    assert recycled, "the scenario must hit the spawn cap or reuse freed slots"
+
+
+def test_update_kernel_more_instances_than_the_shared_table(orc):
+    """2500 instances in one batch: the tile-prefix table is searched in global memory (n_effects > 2047)."""
+    rng = np.random.default_rng(8)
+    caps = rng.integers(1, 12, 2500)
+    insts, off = [], 0
+    for c in caps:
+        a = int(rng.integers(0, c + 1)) if rng.random() > 0.15 else 0
+        insts.append(Instance(off, int(c), alive=a, seed=off * 7 + 1))
+        off += int(c)
+    ref = _c5_world(rng, insts)
+    emu = EmuWorld(ref, recipes.c5_lowered(), chunks=1, update_ctas=2)
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    seeds = [i.seed for i in insts]
+    for step in range(3):
+        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        emu.frame_step(orc, ref.sim, [0] * len(insts), seeds)
+        _assert_same(ref, emu.pull(), f"step {step}")
+
+
+def test_relaxed_order_variant_same_sets(orc):
+    """HNB_EFFECT_RELAXED_ORDER: one warp-aggregated atomic per tile instead of the look-back chain — list ORDER is
+    scheduling-dependent (like the reference's), counts, sets and particle words are not."""
+    rng = np.random.default_rng(4)
+    ref = _c5_world(rng, [Instance(0, 3000, alive=2800, seed=9)])
+    emu = EmuWorld(ref, recipes.c5_lowered(relaxed_order=True), chunks=2, update_ctas=2)
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    for step in range(4):
+        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        emu.frame_step(orc, ref.sim, [0], [9])
+        got = emu.pull()
+        np.testing.assert_array_equal(got["metadata"], ref.metadata_rows())
+        np.testing.assert_array_equal(got["draw"], ref.draw)
+        np.testing.assert_array_equal(got["particles"], ref.particles)
+        md = ref.metadata[0]
+        W, alive = md.indirect_write_index, md.alive_count
+        assert sorted(got["indirect"][:alive, W].tolist()) == sorted(ref.indirect[:alive, W].tolist())
+        assert sorted(got["indirect"][alive:3000, 2].tolist()) == sorted(ref.indirect[alive:3000, 2].tolist())
+        # the next frame reads the list the emulated kernel wrote: keep the oracle on the same order
+        ref.indirect[:, :] = got["indirect"]
+
+
+def test_kernels_with_properties_and_transcendentals(orc):
+    """C3 force field: per-instance Properties staged by the update kernel, sphere sampling in init. libm on the host
+    vs numpy: 1e-5 of the attribute's magnitude per step, integer structures exact."""
+    from tests.helpers import assert_float_attributes_close
+    from tests.test_gpu_effects import _float_word_mask, _force_field
+    asset = _force_field(2048)
+    _, size, _ = asset.particle_layout()
+    props = {"attraction_accel": 18.0, "repulsor_position": G.Vec3(0.25, 0.5, 0.1)}
+    ref = RefWorld(2048, size // 4, [Instance(0, 2048, alive=0, seed=77)])
+    ref.metadata[0].properties_array_index = 0
+    eo = EffectOracle(asset, {0: props})
+    emu = EmuWorld(ref, asset.generate(), chunks=1, update_ctas=2, property_blobs=[asset.serialize_properties(props)])
+    mask, fattrs = _float_word_mask(asset)
+    for f in range(5):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn, seed = [1500 if f == 0 else 20], [int(pcg_hash(np.array([f], dtype=np.uint32))[0])]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        got = emu.pull()
+        np.testing.assert_array_equal(got["metadata"], ref.metadata_rows())
+        np.testing.assert_array_equal(got["indirect"], ref.indirect)
+        np.testing.assert_array_equal(got["particles"][:, ~mask], ref.particles[:, ~mask])
+        assert_float_attributes_close(got["particles"], ref.particles, fattrs, 1e-5, f"frame {f}")
+        # per-step bound: restart the next step from identical state
+        aos = np.ascontiguousarray(ref.particles)
+        emu.lib.emu_aos_to_planes(C.byref(emu.b), aos.ctypes.data, 0, emu.rows, emu.stride)
