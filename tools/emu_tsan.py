@@ -1,0 +1,90 @@
+"""ThreadSanitizer over the emulated update kernel (tests/kernel_emu.py): a stand-alone C++ program runs the real
+hnb_update text of the C5 effect for a few frames on 2 CTAs of OS threads, built with -fsanitize=thread. TSAN knows
+pthread barriers (= __syncwarp / __syncthreads / the collectives) and __atomic operations (= the tile states, tickets),
+so any report is a plain memory access pair of the KERNEL that is not ordered by them — the CPU analogue of
+compute-sanitizer racecheck, but for global memory and the shared-memory stash alike.
+
+    python tools/emu_tsan.py            # prints the TSAN summary; exit code 0 when clean
+"""
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bevy_hanabi_b200 import recipes  # noqa: E402
+from tests import kernel_emu as K  # noqa: E402
+
+MAIN = r"""
+#include <stdio.h>
+#include <stdlib.h>
+int main(int argc, char** argv) {
+    const uint32_t rows = 6000, chunks = argc > 1 ? atoi(argv[1]) : 2, ctas = argc > 2 ? atoi(argv[2]) : 2, frames = 4;
+    const uint32_t tile = 32u * HNB_TILE_K * chunks;
+    std::vector<float4> plane0(rows), plane1(rows);
+    std::vector<uint32_t> ping(rows), pong(rows), dead(rows), tile_prefix(2), prefix_sum(1), spawn_prefix(1), batch_tiles(1), ticket(1), draw(5);
+    std::vector<unsigned long long> states(rows / tile + 4);
+    uint32_t s = 12345u;
+    auto rnd = [&] { s = s * 1664525u + 1013904223u; return float(s >> 8) / 16777216.0f; };
+    const uint32_t alive0 = 5600;
+    for (uint32_t i = 0; i < rows; ++i) {
+        plane0[i] = make_float4(rnd(), rnd(), rnd(), 0.f);
+        plane1[i] = make_float4(rnd() - .5f, rnd() - .5f, rnd() - .5f, 0.01f + 0.08f * rnd());  // lifetimes: many deaths per frame
+        ping[i] = pong[i] = i < alive0 ? i : 0u;
+        dead[i] = i;
+    }
+    hnb::FrameHeader frame; memset(&frame, 0, sizeof frame);
+    frame.sim.delta_time = 1.f / 60.f; frame.sim.num_effects = 1; frame.num_batches = 1;
+    hnb::Spawner sp; memset(&sp, 0, sizeof sp);
+    sp.transform[0] = sp.transform[5] = sp.transform[10] = 1.f; sp.inverse_transform[0] = sp.inverse_transform[5] = sp.inverse_transform[10] = 1.f;
+    sp.seed = 42; sp.parent_slab_offset = 0xFFFFFFFFu;
+    hnb::EffectMetadata md; memset(&md, 0xFF, sizeof md);
+    md.capacity = rows; md.alive_count = alive0; md.max_update = 0; md.max_spawn = rows - alive0; md.indirect_write_index = 0; md.indirect_render_index = 0;
+    md.particle_stride = 8; md.particle_counter = 0;
+    hnb::BatchInfo bi = {0, 0, 0, 0, 0, 1};
+    EmuBatch b; memset(&b, 0, sizeof b);
+    b.frame = &frame; b.spawners = &sp; b.spawn_prefix = spawn_prefix.data(); b.prefix_sum = prefix_sum.data(); b.tile_prefix = tile_prefix.data();
+    b.batch_info = &bi; b.batch_tiles = batch_tiles.data(); b.ticket = ticket.data(); b.tile_state = states.data(); b.metadata = &md; b.draw_args = draw.data();
+    b.planes[0] = plane0.data(); b.planes[1] = plane1.data(); b.ping = ping.data(); b.pong = pong.data(); b.dead = dead.data();
+    b.capacity = rows; b.tile_rows = tile;
+    for (uint32_t f = 0; f < frames; ++f) {
+        frame.epoch = f + 1; frame.sim.time = f * frame.sim.delta_time;
+        // vfx_indirect + vfx_prefix_sum for one instance (restated; the emulation covers the per-particle kernels)
+        draw[1] = 0; md.max_update = md.alive_count; md.max_spawn = md.capacity - md.alive_count;
+        md.indirect_write_index = 1u - md.indirect_write_index; sp.render_indirect_read_index = md.indirect_write_index;
+        prefix_sum[0] = 0; bi.total_update_count = md.alive_count;
+        const uint32_t tiles = (md.alive_count + tile - 1) / tile;
+        tile_prefix[0] = 0; tile_prefix[1] = tiles; batch_tiles[0] = tiles; ticket[0] = 0;
+        emu_update(&b, ctas, 64 * 1024);
+        printf("frame %u: updated %u -> alive %u (instance_count %u)\n", f, md.max_update, md.alive_count, draw[1]);
+        if (md.alive_count != draw[1]) return 2;
+    }
+    return 0;
+}
+"""
+
+
+def main():
+    src = recipes.c5_lowered().generate_source()
+    for old, new in K.SUBSTITUTIONS:
+        assert src.count(old) == 1
+        src = src.replace(old, new)
+    out = ROOT / "build" / "kernel_emu"
+    out.mkdir(parents=True, exist_ok=True)
+    cpp, exe = out / "tsan_c5.cpp", out / "tsan_c5"
+    cpp.write_text(K.PRELUDE + src + K.DRIVER + MAIN)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w", str(cpp), "-o", str(exe)], check=True)
+    rc = 0
+    for chunks, ctas in ((1, 2), (2, 2), (4, 1)):
+        p = subprocess.run([str(exe), str(chunks), str(ctas)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
+        races = p.stderr.count("WARNING: ThreadSanitizer: data race")
+        print(f"chunks={chunks} ctas={ctas}: exit {p.returncode}, {races} data-race reports")
+        print(p.stdout.strip())
+        if races:
+            print(p.stderr[:6000])
+        rc |= p.returncode or races
+    return 1 if rc else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
