@@ -50,7 +50,7 @@ static inline unsigned int __float_as_uint(float f) { unsigned int u; memcpy(&u,
 static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
 namespace emu {
 struct Warp { pthread_barrier_t bar; unsigned long long slot[32]; };
-struct Cta { pthread_barrier_t bar; unsigned char* dyn; unsigned int statics[16]; Warp warps[8]; };
+struct Cta { pthread_barrier_t bar; unsigned char* dyn; unsigned int statics[16]; Warp warps[32]; };
 struct Tls { unsigned tid, bid, lane; Cta* cta; Warp* warp; };
 static thread_local Tls tls;
 struct Dim3 { unsigned x, y, z; };
@@ -226,8 +226,12 @@ def build_emulated_effect(lowered) -> C.CDLL:
 class EmuWorld:
     """One batch (all instances of `ref`) simulated by the emulated kernels, starting from `ref`'s current state."""
 
-    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None):
+    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None, static_lib=None):
+        """`static_lib` (tests/static_emu.build()): run the real bookkeeping and ribbon-sort kernels too instead of their
+        restatements."""
         self.ref, self.lib = ref, build_emulated_effect(lowered)
+        self.static_lib = static_lib
+        self.ribbons = bool(lowered.flags & (1 << 5))  # HNB_EFFECT_RIBBONS
         self.stride = ref.stride_words * 4
         assert lowered.particle_stride == self.stride
         n, rows = len(ref.instances), ref.slab_rows
@@ -251,6 +255,8 @@ class EmuWorld:
         self.tile_state = np.zeros(rows // self.tile + n + 2, dtype=np.uint64)
         self.frame = np.zeros(16, dtype=u32)                                       # FrameHeader: SimParams (7 words) | epoch | num_batches
         self.dispatch = np.zeros(3, dtype=u32)
+        self.spawn_range = np.zeros(n, dtype=u32)
+        self.tile_size = np.array([self.tile], dtype=u32)
         self.epoch = 0
         self.props = None
         self.props_stride = 0
@@ -295,24 +301,68 @@ class EmuWorld:
         if threads:
             per_block = 256 * self.lib.emu_init_items()
             self.lib.emu_init(C.byref(self.b), (threads + per_block - 1) // per_block)
-        # ---- bookkeeping: deferred init accounting (the kernel assigned ranks instead of bumping the counters) ...
-        for i in range(n):
-            md = self.metadata[i]
-            passed = min(max(0, int(spawns[i])), md.max_spawn)
-            md.alive_count += passed
-            md.particle_counter += passed
-        # ... then vfx_indirect + vfx_prefix_sum as restated by the C oracle, and the tile prefix of this launch
-        orc.orc_indirect(self.frame.ctypes.data_as(C.POINTER(O.SimParams)), self.metadata, self.draw.ctypes.data_as(u32p), self.spawners,
-                         self.prefix_sum.ctypes.data_as(u32p), None, 0)
-        alive = self.prefix_sum.copy()
-        orc.orc_prefix_sum(self.batch_info, 1, self.prefix_sum.ctypes.data_as(u32p), self.dispatch.ctypes.data_as(u32p))
-        tiles = (alive + self.tile - 1) // self.tile
-        self.tile_prefix[:n] = np.concatenate([[0], np.cumsum(tiles)[:-1]]) if n else []
-        self.tile_prefix[n] = tiles.sum()
-        self.batch_tiles[0] = tiles.sum()
-        self.ticket[0] = 0
+        if self.static_lib is not None:
+            # ---- bookkeeping by the real fused kernel (k_bookkeeping): per-instance init thread ranges as plan_batch writes them
+            for i in range(n):
+                end = int(self.spawn_prefix[i + 1]) if i + 1 < n else threads
+                self.spawn_range[i] = max(0, end - int(self.spawn_prefix[i])) if threads else 0
+            self.static_lib.semu_bookkeeping(C.byref(self._static_tables()), 1)
+        else:
+            # ---- bookkeeping restated: deferred init accounting (the kernel assigned ranks instead of bumping the counters) ...
+            for i in range(n):
+                md = self.metadata[i]
+                passed = min(max(0, int(spawns[i])), md.max_spawn)
+                md.alive_count += passed
+                md.particle_counter += passed
+            # ... then vfx_indirect + vfx_prefix_sum as restated by the C oracle, and the tile prefix of this launch
+            orc.orc_indirect(self.frame.ctypes.data_as(C.POINTER(O.SimParams)), self.metadata, self.draw.ctypes.data_as(u32p), self.spawners,
+                             self.prefix_sum.ctypes.data_as(u32p), None, 0)
+            alive = self.prefix_sum.copy()
+            orc.orc_prefix_sum(self.batch_info, 1, self.prefix_sum.ctypes.data_as(u32p), self.dispatch.ctypes.data_as(u32p))
+            tiles = (alive + self.tile - 1) // self.tile
+            self.tile_prefix[:n] = np.concatenate([[0], np.cumsum(tiles)[:-1]]) if n else []
+            self.tile_prefix[n] = tiles.sum()
+            self.batch_tiles[0] = tiles.sum()
+            self.ticket[0] = 0
         # ---- update (vfx_update.wgsl): a persistent grid of a few CTAs
         self.lib.emu_update(C.byref(self.b), self.update_ctas, 64 * 1024)
+        if self.ribbons:
+            self._sort_ribbons(orc)
+
+    def _static_tables(self):
+        from tests.static_emu import StaticTables
+        T, p = StaticTables(), lambda a: a.ctypes.data
+        T.frame, T.spawners, T.spawn_range, T.prefix_sum, T.tile_prefix = p(self.frame), C.addressof(self.spawners), p(self.spawn_range), p(self.prefix_sum), p(self.tile_prefix)
+        T.batch_infos, T.batch_tile_size, T.dispatch_args, T.batch_tiles, T.tickets = C.addressof(self.batch_info), p(self.tile_size), p(self.dispatch), p(self.batch_tiles), p(self.ticket)
+        T.metadata, T.draw_args, T.child_infos, T.num_child_infos = C.addressof(self.metadata), p(self.draw), None, 0
+        return T
+
+    def _sort_ribbons(self, orc):
+        """Passes "hanabi:sort_prefix_sum" + "hanabi:sort" of hnb_simulate (needs the static kernels library)."""
+        assert self.static_lib is not None, "ribbon effects need static_lib"
+        from tests.static_emu import RibbonSortArgs
+        lib = self.static_lib
+        lib.semu_prefix_sum(C.byref(self._static_tables()), 1)
+        a = RibbonSortArgs()
+        words = self.stride // 4
+        for pl in range((words + 3) // 4):
+            w = min(4, words - 4 * pl)
+            # plane widths follow the record: 16-byte planes, then an 8- or 4-byte tail (cut_planes)
+            a.planes.ptr[pl], a.planes.words[pl], a.planes.word_off[pl] = self.planes[pl].ctypes.data, (4 if w >= 4 else (2 if w >= 2 else 1)), 4 * pl
+            for k in range(w):
+                a.planes.word_to_plane[4 * pl + k] = pl
+        assert words % 4 == 0, "EmuWorld ribbon sort supports strides that are multiples of 16 bytes"
+        a.ping, a.pong, a.spawners, a.metadata = self.cols[0].ctypes.data, self.cols[1].ctypes.data, C.addressof(self.spawners), C.addressof(self.metadata)
+        a.spawner_base, a.instance_count = 0, self.n
+        grid = 2
+        self._sort_scratch = ([np.zeros(self.rows, dtype=np.uint64) for _ in range(2)], [np.zeros(self.rows, dtype=np.uint32) for _ in range(2)],
+                              np.zeros(lib.semu_hist_words(grid), dtype=np.uint32))
+        for i in range(2):
+            a.scratch_keys[i], a.scratch_vals[i] = self._sort_scratch[0][i].ctypes.data, self._sort_scratch[1][i].ctypes.data
+        a.scratch_hist, a.scratch_rows = self._sort_scratch[2].ctypes.data, self.rows
+        lib.semu_ribbon_sort_small(C.byref(a))
+        if self.rows > 2048:
+            lib.semu_ribbon_sort_large(C.byref(a), grid)
 
     def pull(self):
         aos = np.zeros((self.rows, self.stride // 4), dtype=np.uint32)

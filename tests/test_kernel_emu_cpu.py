@@ -161,3 +161,52 @@ def test_kernels_with_properties_and_transcendentals(orc):
         # per-step bound: restart the next step from identical state
         aos = np.ascontiguousarray(ref.particles)
         emu.lib.emu_aos_to_planes(C.byref(emu.b), aos.ctypes.data, 0, emu.rows, emu.stride)
+
+
+def test_whole_frames_with_real_bookkeeping_and_ribbon_sort(orc):
+    """Every kernel of hnb_simulate under emulation: hnb_init, k_bookkeeping (fused indirect + prefix sums + tile prefix),
+    hnb_update, the second prefix-sum pass and both ribbon-sort kernels — a ribbon effect whose alive count crosses the
+    2048-key boundary between the shared-memory sort and the cooperative radix sort."""
+    from tests import static_emu
+    from tests.test_gpu_ribbons import _assert_sorted, _ribbon_asset
+    asset = _ribbon_asset(3000)
+    fields, size, _ = asset.particle_layout()
+    ref = RefWorld(3000, size // 4, [Instance(0, 3000, alive=0, seed=3)], dt=1 / 30)
+    ref.set_sort_keys(fields)
+    eo = EffectOracle(asset)
+    emu = EmuWorld(ref, asset.generate(), chunks=1, update_ctas=2, static_lib=static_emu.build())
+    crossed = False
+    for f in range(10):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn, seed = [900 if f % 3 == 0 else 23], [3]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        _assert_sorted(ref)
+        _assert_same(ref, emu.pull(), f"frame {f}")
+        crossed |= ref.metadata[0].alive_count > 2048
+    assert crossed
+
+
+def test_real_bookkeeping_kernel_in_multi_instance_frames(orc):
+    """The fused bookkeeping kernel inside whole frames with spawns: deferred init accounting for eight instances."""
+    from tests import static_emu
+    asset = _drifting_sparks(1)
+    _, size, _ = asset.particle_layout()
+    caps = [300, 64, 1000, 5, 128, 700, 33, 256]
+    insts, off = [], 0
+    for i, c in enumerate(caps):
+        insts.append(Instance(off, c, alive=0, seed=10 + i))
+        off += c
+    ref = RefWorld(off, size // 4, insts, dt=1 / 20)
+    eo = EffectOracle(asset)
+    emu = EmuWorld(ref, asset.generate(), chunks=1, update_ctas=2, static_lib=static_emu.build())
+    rng = np.random.default_rng(1)
+    for f in range(6):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawns = [int(rng.integers(0, c + 20)) if rng.random() < 0.7 else 0 for c in caps]   # some exceed the free slots
+        seeds = [int(pcg_hash(np.array([f * 16 + i], dtype=np.uint32))[0]) for i in range(len(caps))]
+        ref.set_spawns(spawns, seeds)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawns, seeds)
+        _assert_same(ref, emu.pull(), f"frame {f}")
