@@ -1,4 +1,5 @@
-"""ThreadSanitizer over the emulated update kernel (tests/kernel_emu.py): a stand-alone C++ program runs the real
+"""ThreadSanitizer over the emulated kernels (tests/kernel_emu.py, tests/static_emu.py): stand-alone C++ programs run the
+ribbon-sort kernels and the real
 hnb_update text of the C5 effect for a few frames on 2 CTAs of OS threads, built with -fsanitize=thread. TSAN knows
 pthread barriers (= __syncwarp / __syncthreads / the collectives) and __atomic operations (= the tile states, tickets),
 so any report is a plain memory access pair of the KERNEL that is not ordered by them — the CPU analogue of
@@ -64,7 +65,89 @@ int main(int argc, char** argv) {
 """
 
 
+SORT_MAIN = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+int main(int argc, char** argv) {
+    // one slab, two instances: 5000 keys (cooperative radix sort) and 900 keys (shared-memory bitonic sort)
+    const uint32_t counts[2] = {5000, 900}, rows = 6000, grid = argc > 1 ? atoi(argv[1]) : 2;
+    const bool wide = argc > 2 && atoi(argv[2]);
+    std::vector<uint32_t> plane(rows * 4), ping(rows), pong(rows);
+    uint32_t s = 99u;
+    auto rnd = [&] { s = s * 1664525u + 1013904223u; return s; };
+    for (uint32_t i = 0; i < rows; ++i) {
+        plane[4 * i + 0] = wide ? rnd() : rnd() % 5u;                          // ribbon id (word 0)
+        const float age = float(rnd() >> 8) / 16777216.0f;
+        plane[4 * i + 1] = wide ? rnd() : __float_as_uint(age);                 // age (word 1)
+    }
+    hnb::Spawner sp[2]; hnb::EffectMetadata md[2];
+    memset(sp, 0, sizeof sp); memset(md, 0, sizeof md);
+    uint32_t off = 0;
+    for (int i = 0; i < 2; ++i) {
+        for (uint32_t r = 0; r < counts[i]; ++r) ping[off + r] = (r * 7919u) % counts[i];   // a permutation (7919 is prime)
+        md[i].capacity = counts[i]; md[i].alive_count = counts[i]; md[i].indirect_write_index = 0; md[i].sort_key_offset = 0; md[i].sort_key2_offset = 1;
+        sp[i].effect_metadata_index = i; sp[i].slab_offset = off;
+        off += counts[i];
+    }
+    hnb::RibbonSortArgs a; memset(&a, 0, sizeof a);
+    a.planes.ptr[0] = plane.data(); a.planes.words[0] = 4; a.planes.word_off[0] = 0;
+    for (int w = 0; w < 4; ++w) a.planes.word_to_plane[w] = 0;
+    a.ping = ping.data(); a.pong = pong.data(); a.spawners = sp; a.metadata = md; a.spawner_base = 0; a.instance_count = 2;
+    std::vector<unsigned long long> k0(rows), k1(rows); std::vector<uint32_t> v0(rows), v1(rows), hist(2 * 8 * 256 + 256 * grid);
+    a.scratch_keys[0] = k0.data(); a.scratch_keys[1] = k1.data(); a.scratch_vals[0] = v0.data(); a.scratch_vals[1] = v1.data();
+    a.scratch_hist = hist.data(); a.scratch_rows = rows; a.scratch_grid = grid;
+    semu_ribbon_sort_small(&a);
+    semu_ribbon_sort_large(&a, grid);
+    off = 0;
+    for (int i = 0; i < 2; ++i) {
+        unsigned long long prev = 0;
+        for (uint32_t r = 0; r < counts[i]; ++r) {
+            const uint32_t row = off + ping[off + r];
+            const unsigned long long key = ((unsigned long long)plane[4 * row] << 32) | plane[4 * row + 1];
+            if (key < prev) { printf("instance %d not sorted at %u\n", i, r); return 2; }
+            prev = key;
+        }
+        printf("instance %d: %u keys sorted\n", i, counts[i]);
+        off += counts[i];
+    }
+    return 0;
+}
+"""
+
+
+def sort_program():
+    """The ribbon-sort kernels (bitonic in shared memory + cooperative radix sort) under ThreadSanitizer."""
+    from tests import static_emu as S
+    wgsl = S._strip_includes((S.KERNELS / "hnb_wgsl.cuh").read_text())
+    tables = S._strip_includes((S.KERNELS / "hnb_tables.cuh").read_text())
+    header = S._strip_includes((S.KERNELS / "hnb_static_kernels.h").read_text())
+    static = (S.KERNELS / "hnb_static_kernels.cu").read_text()
+    static = S._strip_includes(static[:static.index("cudaError_t launch_indirect(")]) + "\n}  // namespace hnb\n"
+    ribbon = (S.KERNELS / "hnb_ribbon_sort.cu").read_text()
+    ribbon = S._strip_includes(ribbon[:ribbon.index("cudaError_t launch_ribbon_sort(")]) + "\n}  // namespace hnb\n"
+    import re
+    static = re.sub(r"__global__ void k_measure_sm_clock.*?\n}\n", "", static, flags=re.S)
+    body = S._rewrite_shared(static + "\n" + ribbon)
+    out = ROOT / "build" / "kernel_emu"
+    out.mkdir(parents=True, exist_ok=True)
+    cpp, exe = out / "tsan_sort.cpp", out / "tsan_sort"
+    cpp.write_text(K.PRELUDE + S.EXTRA_PRELUDE + wgsl + "\n" + tables + "\n" + header + "\n" + body + S.DRIVER + SORT_MAIN)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", str(cpp), "-o", str(exe)], check=True)
+    rc = 0
+    for grid, wide in ((2, 0), (3, 1)):
+        p = subprocess.run([str(exe), str(grid), str(wide)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
+        races = p.stderr.count("WARNING: ThreadSanitizer: data race")
+        print(f"ribbon sort grid={grid} wide_keys={wide}: exit {p.returncode}, {races} data-race reports")
+        print(p.stdout.strip())
+        if races:
+            print(p.stderr[:6000])
+        rc |= p.returncode or races
+    return rc
+
+
 def main():
+    rc_sort = sort_program()
     src = recipes.c5_lowered().generate_source()
     for old, new in K.SUBSTITUTIONS:
         assert src.count(old) == 1
@@ -83,7 +166,7 @@ def main():
         if races:
             print(p.stderr[:6000])
         rc |= p.returncode or races
-    return 1 if rc else 0
+    return 1 if (rc or rc_sort) else 0
 
 
 if __name__ == "__main__":
