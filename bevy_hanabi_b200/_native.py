@@ -159,6 +159,11 @@ SIGNATURES = {
     "hnb_slab_checksum_indirect": (i32, [vp, u32, u32, u32, P(C.c_uint64)]),
     "hnb_effect_compile": (i32, [vp, P(EffectDesc), P(u32)]),
     "hnb_effect_destroy": (i32, [vp, u32]),
+    "hnb_compile_job_start": (vp, [P(EffectDesc)]),
+    "hnb_compile_job_poll": (i32, [vp]),
+    "hnb_compile_job_wait": (i32, [vp]),
+    "hnb_compile_job_destroy": (None, [vp]),
+    "hnb_effect_create_from_job": (i32, [vp, vp, P(u32)]),
     "hnb_effect_generate_source": (i32, [P(EffectDesc), C.c_char_p, C.c_size_t, P(C.c_size_t)]),
     "hnb_nvrtc_check": (i32, [C.c_char_p, P(C.c_size_t)]),
     "hnb_set_sim_params": (i32, [vp, P(SimParams)]),

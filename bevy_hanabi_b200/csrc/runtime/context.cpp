@@ -8,12 +8,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -388,11 +390,14 @@ void check_rows(const Slab& s, uint32_t first, uint32_t count) {
 // Staging through a device buffer in chunks (AoS <-> planes transposes run on the device).
 constexpr size_t kChunkBytes = size_t(64) << 20;
 
-KernelModule* get_module(hnb_ctx* c, const std::string& source, const std::string& name, uint64_t hash, bool fast_math) {
+// `precompiled`: a cubin already built for exactly this source (hnb_compile_job), or NULL to compile here.
+KernelModule* get_module(hnb_ctx* c, const std::string& source, const std::string& name, uint64_t hash, bool fast_math,
+                         const std::string* precompiled = nullptr) {
     auto it = c->modules.find(hash);
     if (it != c->modules.end()) return it->second.get();
     std::string cubin, log;
-    if (!nvrtc_compile_sm100a(source, name + ".cu", cubin, log, fast_math)) fail(HNB_ERR_NVRTC, log);
+    if (precompiled) cubin = *precompiled;
+    else if (!nvrtc_compile_sm100a(source, name + ".cu", cubin, log, fast_math)) fail(HNB_ERR_NVRTC, log);
     auto km = std::make_unique<KernelModule>();
     km->log = log;
     CUresult r = c->drv.ModuleLoadData(&km->mod, cubin.data());
@@ -913,34 +918,119 @@ int32_t hnb_nvrtc_check(const char* source, size_t* cubin_size) {
     });
 }
 
+// Everything hnb_effect_compile derives from the descriptor before it touches the GPU (the descriptor's strings need
+// not outlive the call that builds this).
+struct EffectBlueprint {
+    std::string source, name;
+    uint64_t hash = 0;
+    bool fast_math = false;
+    uint32_t tile_k = 4, rows_per_lane = 16, update_smem = 0, flags = 0, particle_stride = 0, parent_stride = 0, props_size = 0;
+};
+static EffectBlueprint make_blueprint(const hnb_effect_desc& desc) {
+    EffectBlueprint bp;
+    bp.source = generate_effect_source(desc);
+    bp.hash = fnv1a64(bp.source);
+    bp.name = desc.name ? desc.name : "effect";
+    bp.fast_math = (desc.flags & HNB_EFFECT_FAST_MATH) != 0;  // the flag is part of the source (hash)
+    bp.tile_k = choose_tile_k(desc);
+    bp.rows_per_lane = rows_per_lane();
+    bp.update_smem = update_smem_bytes(desc);
+    bp.flags = desc.flags;
+    bp.particle_stride = desc.particle_stride;
+    bp.parent_stride = desc.parent_particle_stride;
+    bp.props_size = desc.properties_size;
+    return bp;
+}
+// Load (or find in the cache) the module of `bp` and register an effect for it.
+static hnb_effect install_effect(hnb_ctx* c, const EffectBlueprint& bp, const std::string* precompiled_cubin) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Effect fx;
+    fx.hash = bp.hash;
+    fx.name = bp.name;
+    fx.km = get_module(c, bp.source, fx.name, fx.hash, bp.fast_math, precompiled_cubin);
+    fx.tile_k = bp.tile_k;
+    fx.rows_per_lane = bp.rows_per_lane;
+    fx.update_smem = bp.update_smem;
+    {
+        CUresult r = c->drv.FuncSetAttribute(fx.km->update, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)fx.update_smem);
+        if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem " + std::to_string(fx.update_smem) + "): " + cu_error_string(c->drv, r));
+        int bps = 0;
+        r = c->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&bps, fx.km->update, 256, fx.update_smem);
+        if (r != CUDA_SUCCESS || bps < 1) bps = 1;
+        fx.update_blocks_per_sm = bps;
+    }
+    fx.flags = bp.flags;
+    fx.particle_stride = bp.particle_stride;
+    fx.parent_stride = bp.parent_stride;
+    fx.props_size = bp.props_size;
+    fx.props_stride = (uint32_t)align_up(bp.props_size, 16);
+    fx.live = true;
+    c->effects.push_back(fx);
+    return (hnb_effect)(c->effects.size() - 1);
+}
+
 int32_t hnb_effect_compile(hnb_ctx* c, const hnb_effect_desc* desc, hnb_effect* out) {
     return guarded([&] {
         if (!desc || !out) fail(HNB_ERR_INVALID_ARG, "NULL argument");
-        CUDA_CHECK(cudaSetDevice(c->device));
-        std::string src = generate_effect_source(*desc);
-        Effect fx;
-        fx.hash = fnv1a64(src);
-        fx.name = desc->name ? desc->name : "effect";
-        fx.km = get_module(c, src, fx.name, fx.hash, (desc->flags & HNB_EFFECT_FAST_MATH) != 0);  // the flag is part of the source (hash)
-        fx.tile_k = choose_tile_k(*desc);
-        fx.rows_per_lane = rows_per_lane();
-        fx.update_smem = update_smem_bytes(*desc);
-        {
-            CUresult r = c->drv.FuncSetAttribute(fx.km->update, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)fx.update_smem);
-            if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem " + std::to_string(fx.update_smem) + "): " + cu_error_string(c->drv, r));
-            int bps = 0;
-            r = c->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&bps, fx.km->update, 256, fx.update_smem);
-            if (r != CUDA_SUCCESS || bps < 1) bps = 1;
-            fx.update_blocks_per_sm = bps;
-        }
-        fx.flags = desc->flags;
-        fx.particle_stride = desc->particle_stride;
-        fx.parent_stride = desc->parent_particle_stride;
-        fx.props_size = desc->properties_size;
-        fx.props_stride = (uint32_t)align_up(desc->properties_size, 16);
-        fx.live = true;
-        c->effects.push_back(fx);
-        *out = (hnb_effect)(c->effects.size() - 1);
+        *out = install_effect(c, make_blueprint(*desc), nullptr);
+    });
+}
+
+// ---- background compilation ------------------------------------------------------------------
+// The reference compiles pipelines asynchronously and neither ticks nor batches an effect until both are ready
+// (spawn.rs:968-973, mod.rs:3853-3894). A compile job runs the NVRTC step (the 0.3-1 s part) on its own thread and
+// needs no context; hnb_effect_create_from_job() then only loads the finished cubin.
+struct hnb_compile_job {
+    EffectBlueprint bp;
+    std::string cubin, log;
+    std::atomic<int> state{0};  // 0 running, 1 ready, -1 failed
+    std::thread worker;
+};
+
+hnb_compile_job* hnb_compile_job_start(const hnb_effect_desc* desc) {
+    hnb_compile_job* job = nullptr;
+    int32_t rc = guarded([&] {
+        if (!desc) fail(HNB_ERR_INVALID_ARG, "desc is NULL");
+        auto j = std::make_unique<hnb_compile_job>();
+        j->bp = make_blueprint(*desc);  // copies every string of the descriptor
+        hnb_compile_job* raw = j.get();
+        raw->worker = std::thread([raw] {
+            const bool ok = nvrtc_compile_sm100a(raw->bp.source, raw->bp.name + ".cu", raw->cubin, raw->log, raw->bp.fast_math);
+            raw->state.store(ok ? 1 : -1, std::memory_order_release);
+        });
+        job = j.release();
+    });
+    return rc == HNB_OK ? job : nullptr;
+}
+
+int32_t hnb_compile_job_poll(hnb_compile_job* job) {
+    if (!job) return HNB_ERR_INVALID_ARG;
+    const int st = job->state.load(std::memory_order_acquire);
+    if (st == 0) return 0;
+    if (st == 1) return 1;
+    g_last_error = job->log;
+    return HNB_ERR_NVRTC;
+}
+
+int32_t hnb_compile_job_wait(hnb_compile_job* job) {
+    if (!job) return HNB_ERR_INVALID_ARG;
+    if (job->worker.joinable()) job->worker.join();
+    return hnb_compile_job_poll(job);
+}
+
+void hnb_compile_job_destroy(hnb_compile_job* job) {
+    if (!job) return;
+    if (job->worker.joinable()) job->worker.join();
+    delete job;
+}
+
+int32_t hnb_effect_create_from_job(hnb_ctx* c, hnb_compile_job* job, hnb_effect* out) {
+    return guarded([&] {
+        if (!job || !out) fail(HNB_ERR_INVALID_ARG, "NULL argument");
+        const int st = job->state.load(std::memory_order_acquire);
+        if (st == 0) fail(HNB_ERR_NOT_READY, "the compile job is still running");
+        if (st < 0) fail(HNB_ERR_NVRTC, job->log);
+        *out = install_effect(c, job->bp, &job->cubin);
     });
 }
 

@@ -88,6 +88,39 @@ class LoweredEffect:
         return buf.value.decode()
 
 
+class CompileJob:
+    """Background NVRTC compilation of a lowered effect (needs no context and no GPU): `poll()` -> False while
+    compiling, True when ready; raises HanabiError with the compiler log if it failed."""
+
+    def __init__(self, fx: LoweredEffect):
+        d, _keep = fx.to_c()
+        self._h = lib.hnb_compile_job_start(C.byref(d))
+        if not self._h:
+            raise N.HanabiError(N.HNB_ERR_INVALID_ARG, N.last_error())
+
+    def poll(self) -> bool:
+        rc = lib.hnb_compile_job_poll(self._h)
+        if rc < 0:
+            raise N.HanabiError(rc, N.last_error())
+        return rc == 1
+
+    def wait(self) -> None:
+        rc = lib.hnb_compile_job_wait(self._h)
+        if rc < 0:
+            raise N.HanabiError(rc, N.last_error())
+
+    def close(self) -> None:
+        if self._h:
+            lib.hnb_compile_job_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def nvrtc_check(source: str) -> tuple[int, str]:
     """Compile a translation unit for sm_100a with NVRTC (no GPU needed). Returns (cubin bytes, log)."""
     n = C.c_size_t(0)
@@ -241,6 +274,12 @@ class Context:
 
     def effect_destroy(self, effect: int) -> None:
         check(lib.hnb_effect_destroy(self._h, effect))
+
+    def effect_create_from_job(self, job: "CompileJob") -> int:
+        """Register an effect compiled in the background; raises HanabiError(HNB_ERR_NOT_READY) while the job runs."""
+        out = N.u32(0)
+        check(lib.hnb_effect_create_from_job(self._h, job._h, C.byref(out)))
+        return out.value
 
     def upload_properties(self, effect: int, array_index: int, blob: bytes) -> None:
         buf = C.create_string_buffer(blob, len(blob))

@@ -272,6 +272,21 @@ typedef struct hnb_effect_desc {
 /** Compile (NVRTC, sm_100a, cached by source hash ≙ ShaderCache) the init+update kernels. */
 HNB_API int32_t hnb_effect_compile(hnb_ctx* ctx, const hnb_effect_desc* desc, hnb_effect* out);
 HNB_API int32_t hnb_effect_destroy(hnb_ctx* ctx, hnb_effect effect);
+
+/* Background compilation. The reference compiles pipelines asynchronously and neither ticks nor batches an effect
+ * until both are ready (spawn.rs:968-973, mod.rs:3853-3894). A job runs the NVRTC step on its own thread and needs no
+ * context (it also works without a GPU); hnb_effect_create_from_job() then only loads the finished binary. */
+typedef struct hnb_compile_job hnb_compile_job;
+/** Copies the descriptor and starts compiling. NULL (message in hnb_last_error()) if the descriptor is invalid. */
+HNB_API hnb_compile_job* hnb_compile_job_start(const hnb_effect_desc* desc);
+/** 0 = still compiling, 1 = ready, HNB_ERR_NVRTC = failed (compiler log in hnb_last_error()). Never blocks. */
+HNB_API int32_t hnb_compile_job_poll(hnb_compile_job* job);
+/** Blocks until the job has finished; returns like hnb_compile_job_poll. */
+HNB_API int32_t hnb_compile_job_wait(hnb_compile_job* job);
+HNB_API void hnb_compile_job_destroy(hnb_compile_job* job);
+/** Register the compiled effect with a context: HNB_ERR_NOT_READY while the job runs (simulate nothing for that
+ *  effect meanwhile, like the reference), HNB_ERR_NVRTC if it failed. The job can be reused for other contexts. */
+HNB_API int32_t hnb_effect_create_from_job(hnb_ctx* ctx, hnb_compile_job* job, hnb_effect* out);
 /**
  * Generate the full CUDA C translation unit for `desc` without a GPU (works with ctx=NULL):
  * writes a NUL-terminated string of at most `cap` bytes into `out`, returns its full length

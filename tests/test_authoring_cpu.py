@@ -399,3 +399,32 @@ def test_effect_properties_serialize_reference_vector():
     assert len(blob) == 16                            # cpu_size = offset of the last entry + its size
     assert blob[off["a"]:off["a"] + 4] == struct.pack("<f", 3.0)
     assert blob[off["b"]:off["b"] + 12] == struct.pack("<3f", 1.0, 1.0, 1.0)
+
+
+def test_background_compile_job():
+    """hnb_compile_job_*: the NVRTC step on its own thread, without a context (and without a GPU) — the reference
+    compiles pipelines asynchronously too (spawn.rs:968-973). Several jobs run concurrently; a broken effect reports the
+    compiler log; polling never blocks."""
+    import time
+    from bevy_hanabi_b200 import recipes
+    from bevy_hanabi_b200 import runtime as R
+    t0 = time.perf_counter()
+    jobs = [R.CompileJob(recipes.c5_lowered()), R.CompileJob(_c5_asset().generate()), R.CompileJob(recipes.c5_lowered(relaxed_order=True))]
+    started = time.perf_counter() - t0
+    assert started < 0.25, "starting a job must not wait for the compiler"
+    polls = 0
+    while not all(j.poll() for j in jobs):
+        polls += 1
+        time.sleep(0.01)
+        assert time.perf_counter() - t0 < 120
+    assert polls > 0, "the compile really ran in the background"
+    bad = recipes.c5_lowered()
+    bad.update_code = "    this is not CUDA;"
+    job = R.CompileJob(bad)
+    with pytest.raises(HanabiError) as e:
+        job.wait()
+    assert e.value.code == N.HNB_ERR_NVRTC and "error" in e.value.message
+    with pytest.raises(HanabiError):
+        job.poll()
+    for j in jobs + [job]:
+        j.close()

@@ -175,6 +175,28 @@ def test_empty_frames(ctx):
     np.testing.assert_array_equal(ind[:, 2], np.arange(256))
 
 
+def test_effect_from_background_compile_job(ctx, orc):
+    """hnb_compile_job_* + hnb_effect_create_from_job: compiled off-thread, loaded into the context, same results as
+    the synchronous path; one job serves several contexts."""
+    job = R.CompileJob(recipes.c5_lowered())
+    job.wait()
+    effect = ctx.effect_create_from_job(job)
+    rng = np.random.default_rng(11)
+    n = 5000
+    ref = RefWorld(n, 8, [Instance(0, n, alive=n, seed=9)])
+    p = np.zeros((n, 8), dtype=np.float32)
+    p[:, 0:3] = rng.uniform(-1, 1, (n, 3)); p[:, 4:7] = rng.uniform(-1, 1, (n, 3)); p[:, 7] = rng.uniform(0.01, 0.2, n)
+    ref.particles[:] = p.view(np.uint32)
+    gpu = GpuWorld(ctx, ref, None, effect=effect)
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    for step in range(4):
+        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        gpu.frame()
+    assert_world_equal(ref, gpu.pull(), what="effect from a compile job")
+    assert ctx.effect_create_from_job(job) != effect   # registering again gives a new handle on the cached module
+    job.close()
+
+
 def test_epoch_wrap(native, orc, monkeypatch):
     """The look-back's tile states carry a 30-bit frame epoch; frames across the wrap must stay exact."""
     monkeypatch.setenv("HNB_EPOCH_START", str(0x3fffffff - 3))
