@@ -210,3 +210,33 @@ def test_real_bookkeeping_kernel_in_multi_instance_frames(orc):
         eo.frame(ref, orc)
         emu.frame_step(orc, ref.sim, spawns, seeds)
         _assert_same(ref, emu.pull(), f"frame {f}")
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_random_worlds_through_every_kernel(orc, seed):
+    """Fuzz of the kernels' index arithmetic: random instance layouts (capacities around tile multiples, empty and
+    full instances), random spawn requests (some beyond the free slots), random tile size and grid, whole frames with
+    the real bookkeeping kernel — every buffer bit-exact against the oracle after every frame."""
+    from tests import static_emu
+    rng = np.random.default_rng(1000 + seed)
+    asset = _drifting_sparks(1) if seed % 2 else _firework_trails(1)
+    _, size, _ = asset.particle_layout()
+    n_inst = int(rng.integers(1, 7))
+    caps = [int(rng.choice([1, 31, 32, 33, 127, 128, 129, 255, 256, 257, 400, 511, 512, 513, 900])) for _ in range(n_inst)]
+    insts, off = [], 0
+    for i, c in enumerate(caps):
+        insts.append(Instance(off, c, alive=0, seed=seed * 100 + i))
+        off += c
+    dt = float(rng.choice([1 / 10, 1 / 20, 1 / 4]))
+    ref = RefWorld(off, size // 4, insts, dt=dt)
+    eo = EffectOracle(asset)
+    chunks, ctas = int(rng.choice([1, 2, 4])), int(rng.integers(1, 4))
+    emu = EmuWorld(ref, asset.generate(), chunks=chunks, update_ctas=ctas, static_lib=static_emu.build())
+    for f in range(5):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawns = [int(rng.integers(0, c + 40)) if rng.random() < 0.6 else 0 for c in caps]
+        seeds = [int(pcg_hash(np.array([seed * 64 + f * 8 + i], dtype=np.uint32))[0]) for i in range(n_inst)]
+        ref.set_spawns(spawns, seeds)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawns, seeds)
+        _assert_same(ref, emu.pull(), f"seed {seed} (caps {caps}, chunks {chunks}, ctas {ctas}) frame {f}")
