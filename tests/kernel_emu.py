@@ -112,6 +112,8 @@ struct EmuBatch {
     uint32_t* batch_tiles; uint32_t* ticket; unsigned long long* tile_state; void* metadata; uint32_t* draw_args; void* properties;
     void* planes[16]; uint32_t* ping; uint32_t* pong; uint32_t* dead;
     uint32_t capacity, init_thread_count, properties_stride, tile_rows;
+    // GPU spawn events (EmuScene)
+    void* child_infos; uint32_t* consume_events; uint32_t* emit_events[4]; uint32_t emit_caps[4]; void* parent_planes[16];
 };
 static hnb::BatchParams make_params(const EmuBatch* b) {
     hnb::BatchParams P;
@@ -136,6 +138,10 @@ static hnb::BatchParams make_params(const EmuBatch* b) {
     P.init_thread_count = b->init_thread_count;
     P.properties_stride = b->properties_stride;
     P.tile_rows = b->tile_rows;
+    P.child_infos = (hnb::ChildInfo*)b->child_infos;
+    P.consume_events = b->consume_events;
+    for (int i = 0; i < 4; ++i) { P.emit_events[i] = b->emit_events[i]; P.emit_events_capacity[i] = b->emit_caps[i]; }
+    for (int p = 0; p < 16; ++p) P.parent_slab.planes[p] = b->parent_planes[p];
     return P;
 }
 template <typename K> static void emu_launch(K kernel, const hnb::BatchParams& P, unsigned grid, size_t smem) {
@@ -190,13 +196,15 @@ class EmuBatch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("frame", "spawners", "spawn_prefix", "prefix_sum", "tile_prefix", "batch_info", "batch_tiles", "ticket",
                                           "tile_state", "metadata", "draw_args", "properties")] + \
                [("planes", C.c_void_p * 16), ("ping", C.c_void_p), ("pong", C.c_void_p), ("dead", C.c_void_p),
-                ("capacity", C.c_uint32), ("init_thread_count", C.c_uint32), ("properties_stride", C.c_uint32), ("tile_rows", C.c_uint32)]
+                ("capacity", C.c_uint32), ("init_thread_count", C.c_uint32), ("properties_stride", C.c_uint32), ("tile_rows", C.c_uint32),
+                ("child_infos", C.c_void_p), ("consume_events", C.c_void_p), ("emit_events", C.c_void_p * 4), ("emit_caps", C.c_uint32 * 4),
+                ("parent_planes", C.c_void_p * 16)]
 
 
-def build_emulated_effect(lowered) -> C.CDLL:
+def build_emulated_effect(lowered, allow_events: bool = False) -> C.CDLL:
     src = lowered.generate_source()
-    if "#define HNB_EMIT_EVENTS 1" in src or "#define HNB_READ_PARENT 1" in src or "#define HNB_CONSUME_EVENTS 1" in src:
-        raise NotImplementedError("the kernel emulation covers effects without GPU spawn events")
+    if not allow_events and ("#define HNB_EMIT_EVENTS 1" in src or "#define HNB_READ_PARENT 1" in src or "#define HNB_CONSUME_EVENTS 1" in src):
+        raise NotImplementedError("EmuWorld covers effects without GPU spawn events; use EmuScene")
     for old, new in SUBSTITUTIONS:
         assert src.count(old) == 1, f"kernel source changed, update tests/kernel_emu.py: {old!r}"
         src = src.replace(old, new)
@@ -370,3 +378,120 @@ class EmuWorld:
         return {"particles": aos, "indirect": np.stack(self.cols, axis=1),
                 "metadata": np.frombuffer(bytes(self.metadata), dtype=np.uint32).reshape(self.n, 15).copy(), "draw": self.draw.copy(),
                 "prefix": self.prefix_sum.copy(), "total_update": self.batch_info[0].total_update_count}
+
+
+class EmuScene:
+    """Several single-instance batches with shared global tables — spawners, metadata, prefix sums, child infos, event
+    buffers — i.e. what one hnb_ctx holds, so that parents can emit GPU spawn events and children consume them. A frame is
+    hnb_simulate(): init of every batch in order, the real fused bookkeeping kernel (+ event clear), update of every batch.
+
+    members: list of dicts  {ref: RefWorld (1 instance), lowered, parent: member index or None,
+                             consume: event buffer index or None, emit: [event buffer indices], child_row: ChildInfo row or None}
+    """
+
+    def __init__(self, members, event_caps, static_lib, chunks: int = 1, update_ctas: int = 2):
+        from tests.static_emu import StaticTables
+        self.static, self.members, n = static_lib, members, len(members)
+        u32 = np.uint32
+        self.n = n
+        self.metadata = (O.EffectMetadata * n)()
+        self.spawners = (O.Spawner * n)()
+        self.draw = np.zeros(5 * n, dtype=u32)
+        self.spawn_prefix, self.prefix_sum, self.spawn_range = np.zeros(n, dtype=u32), np.zeros(n, dtype=u32), np.zeros(n, dtype=u32)
+        self.tile_prefix = np.zeros(n + 1, dtype=u32)
+        self.batch_infos = (O.BatchInfo * n)()
+        self.tile_size, self.dispatch = np.zeros(n, dtype=u32), np.zeros(3 * n, dtype=u32)
+        self.batch_tiles, self.tickets = np.zeros(n, dtype=u32), np.zeros(n, dtype=u32)
+        self.frame = np.zeros(16, dtype=u32)
+        self.child_infos = np.zeros((max(1, len(event_caps)), 2), dtype=np.int32)     # {init_indirect_dispatch_index, event_count}
+        self.events = [np.zeros(c, dtype=u32) for c in event_caps]
+        self.epoch = 0
+        self.update_ctas = update_ctas
+        self.slabs = []
+        for b, m in enumerate(members):
+            ref, lib = m["ref"], build_emulated_effect(m["lowered"], allow_events=True)
+            assert len(ref.instances) == 1
+            k = lib.emu_tile_k()
+            tile = 32 * k * chunks
+            self.tile_size[b] = tile
+            rows = ref.slab_rows
+            slab = dict(lib=lib, rows=rows, stride=ref.stride_words * 4, tile=tile, planes=[np.zeros(rows * 4, dtype=u32) for _ in range(16)],
+                        cols=[np.ascontiguousarray(ref.indirect[:, c]).copy() for c in range(3)], tile_state=np.zeros(rows // tile + 4, dtype=np.uint64), b=EmuBatch())
+            self.slabs.append(slab)
+            md = O.EffectMetadata.from_buffer_copy(bytes(ref.metadata[0]))
+            md.indirect_render_index = b
+            if m.get("consume") is not None:
+                md.global_child_index, md.local_child_index = m["child_row"], 0
+            if m.get("emit"):
+                md.base_child_index = m["base_child_row"]
+            self.metadata[b] = md
+            sp = O.Spawner.from_buffer_copy(bytes(ref.spawners[0]))
+            sp.effect_metadata_index, sp.draw_indirect_index = b, b
+            if m.get("parent") is not None:
+                sp.parent_slab_offset = 0
+            self.spawners[b] = sp
+            self.batch_infos[b] = O.BatchInfo(0, 0, b, 0, b, 1)
+        for b, m in enumerate(members):
+            self._bind(b)
+            slab = self.slabs[b]
+            aos = np.ascontiguousarray(m["ref"].particles)
+            slab["lib"].emu_aos_to_planes(C.byref(slab["b"]), aos.ctypes.data, 0, slab["rows"], slab["stride"])
+        T, p = StaticTables(), lambda a: a.ctypes.data
+        T.frame, T.spawners, T.spawn_range, T.prefix_sum, T.tile_prefix = p(self.frame), C.addressof(self.spawners), p(self.spawn_range), p(self.prefix_sum), p(self.tile_prefix)
+        T.batch_infos, T.batch_tile_size, T.dispatch_args, T.batch_tiles, T.tickets = C.addressof(self.batch_infos), p(self.tile_size), p(self.dispatch), p(self.batch_tiles), p(self.tickets)
+        T.metadata, T.draw_args, T.child_infos, T.num_child_infos = C.addressof(self.metadata), p(self.draw), p(self.child_infos), len(event_caps)
+        self.T = T
+
+    def _bind(self, b):
+        slab, m, ptr = self.slabs[b], self.members[b], lambda a: a.ctypes.data
+        e = slab["b"]
+        e.frame, e.spawners, e.spawn_prefix, e.prefix_sum, e.tile_prefix = ptr(self.frame), C.addressof(self.spawners), ptr(self.spawn_prefix), ptr(self.prefix_sum), ptr(self.tile_prefix)
+        e.batch_info = C.addressof(self.batch_infos) + b * C.sizeof(O.BatchInfo)
+        e.batch_tiles, e.ticket, e.tile_state = ptr(self.batch_tiles) + 4 * b, ptr(self.tickets) + 4 * b, ptr(slab["tile_state"])
+        e.metadata, e.draw_args, e.properties = C.addressof(self.metadata), ptr(self.draw), None
+        for p in range(16):
+            e.planes[p] = ptr(slab["planes"][p])
+        e.ping, e.pong, e.dead = (ptr(c) for c in slab["cols"])
+        e.capacity, e.properties_stride, e.tile_rows = slab["rows"], 0, slab["tile"]
+        e.child_infos = ptr(self.child_infos)
+        if m.get("consume") is not None:
+            e.consume_events = ptr(self.events[m["consume"]])
+        for i, ev in enumerate(m.get("emit") or []):
+            e.emit_events[i], e.emit_caps[i] = ptr(self.events[ev]), len(self.events[ev])
+        if m.get("parent") is not None:
+            for p in range(16):
+                e.parent_planes[p] = ptr(self.slabs[m["parent"]]["planes"][p])
+
+    def frame_step(self, sim, spawns, seeds):
+        n = self.n
+        self.frame[:7] = np.frombuffer(bytes(sim), dtype=np.uint32)
+        self.frame[6] = n                       # sim.num_effects of the shared context
+        self.epoch += 1
+        self.frame[7], self.frame[8] = self.epoch, n
+        threads = []
+        for b, m in enumerate(self.members):
+            self.spawners[b].spawn, self.spawners[b].seed = int(spawns[b]), int(seeds[b]) & 0xFFFFFFFF
+            self.spawn_prefix[b] = self.prefix_sum[b] = 0
+            if m.get("consume") is not None:
+                t = (len(self.events[m["consume"]]) + 63) // 64 * 64    # dispatch sized by the buffer, capped on the device by event_count
+                self.spawn_range[b] = t | 0x80000000
+            else:
+                t = (max(0, int(spawns[b])) + 63) // 64 * 64
+                self.spawn_range[b] = t
+            threads.append(t)
+        for b, slab in enumerate(self.slabs):       # pass "hanabi:init"
+            slab["b"].init_thread_count = threads[b]
+            if threads[b]:
+                per_block = 256 * slab["lib"].emu_init_items()
+                slab["lib"].emu_init(C.byref(slab["b"]), (threads[b] + per_block - 1) // per_block)
+        self.static.semu_bookkeeping(C.byref(self.T), n)   # indirect + prefix sums (+ deferred init accounting), then the event clear
+        self.static.semu_clear_events(C.byref(self.T), n)
+        for slab in self.slabs:                     # pass "hanabi:update"
+            slab["lib"].emu_update(C.byref(slab["b"]), self.update_ctas, 64 * 1024)
+
+    def pull(self, b):
+        slab = self.slabs[b]
+        aos = np.zeros((slab["rows"], slab["stride"] // 4), dtype=np.uint32)
+        slab["lib"].emu_planes_to_aos(C.byref(slab["b"]), aos.ctypes.data, 0, slab["rows"], slab["stride"])
+        return {"particles": aos, "indirect": np.stack(slab["cols"], axis=1), "metadata": np.frombuffer(bytes(self.metadata[b]), dtype=np.uint32).copy(),
+                "instance_count": int(self.draw[5 * b + 1])}

@@ -240,3 +240,68 @@ def test_random_worlds_through_every_kernel(orc, seed):
         eo.frame(ref, orc)
         emu.frame_step(orc, ref.sim, spawns, seeds)
         _assert_same(ref, emu.pull(), f"seed {seed} (caps {caps}, chunks {chunks}, ctas {ctas}) frame {f}")
+
+
+def test_emulated_parent_child_spawn_events(orc):
+    """GPU spawn events under emulation (tests/kernel_emu.py::EmuScene): the parent's update kernel appends events with
+    atomics, the bookkeeping kernel accounts the event-driven child init and clears the counts, the child's init kernel
+    reads the parent's records. Same scenario and same comparison rules as tests/test_gpu_events.py (event buffers as
+    multisets — their order is scheduling-dependent here too —, everything else exact)."""
+    from collections import Counter
+    from tests import static_emu
+    from tests.kernel_emu import EmuScene
+    from tests.test_gpu_events import EVENT_CAP, _assets, _oracle_append_events, _oracle_child_init
+    parent, child = _assets()
+    p_fx, c_fx = parent.generate(num_event_bindings=1), child.generate(parent=parent)
+    dt = 1.0 / 30.0
+    pw = RefWorld(512, p_fx.particle_stride // 4, [Instance(0, 512, alive=0, seed=11)], dt=dt)
+    cw = RefWorld(2048, c_fx.particle_stride // 4, [Instance(0, 2048, alive=0, seed=22)], dt=dt)
+    po, co = EffectOracle(parent), EffectOracle(child)
+    scene = EmuScene([dict(ref=pw, lowered=p_fx, emit=[0], base_child_row=0),
+                      dict(ref=cw, lowered=c_fx, parent=0, consume=0, child_row=0)], [EVENT_CAP], static_emu.build())
+    events, event_count, all_emitted = np.zeros(EVENT_CAP, dtype=np.uint32), 0, []
+    spawn_sched = [40, 0, 25, 0, 0, 60, 0, 0, 10, 0, 0, 0, 30, 0]
+    total_children = 0
+    for f, spawn in enumerate(spawn_sched):
+        seed_p = int(pcg_hash(np.array([100 + f], dtype=np.uint32))[0])
+        seed_c = int(pcg_hash(np.array([900 + f], dtype=np.uint32))[0])
+        # what the previous frame's update left in the buffer
+        assert int(scene.child_infos[0, 1]) == event_count
+        n_valid = min(event_count, EVENT_CAP)
+        got = scene.events[0].copy()
+        if event_count <= EVENT_CAP:
+            assert sorted(got[:n_valid].tolist()) == sorted(events[:n_valid].tolist())
+        else:
+            emitted, kept = Counter(all_emitted), Counter(got.tolist())
+            assert all(kept[p] <= emitted[p] for p in kept)
+        events[:n_valid] = got[:n_valid]
+        # ----- oracle frame (same order of passes as hnb_simulate: parent init, child init, bookkeeping, updates)
+        t = np.float32(f * dt)
+        pw.sim.time = cw.sim.time = t
+        pw.set_spawns([spawn], [seed_p])
+        cw.set_spawns([0], [seed_c])
+        po.init_pass(pw)
+        total_children += _oracle_child_init(child, co, cw, po, pw, events, n_valid, seed_c)
+        event_count = 0
+        for w in (pw, cw):
+            w.oracle_indirect(orc)
+            w.oracle_prefix_sum(orc)
+        po.update_pass(pw)
+        co.update_pass(cw)
+        for channel, counts in po.last_emitted:
+            event_count = _oracle_append_events(pw, counts, events, event_count)
+            rows_read = pw.indirect[:pw.metadata[0].max_update, 1 - pw.metadata[0].indirect_write_index]
+            all_emitted = np.repeat(rows_read, counts[:len(rows_read)]).tolist()
+        # ----- emulated frame
+        scene.frame_step(pw.sim, [spawn, 0], [seed_p, seed_c])
+        for b, world in enumerate((pw, cw)):
+            got_w = scene.pull(b)
+            want_md = world.metadata_rows()[0].copy()
+            want_md[5] = b
+            for fld in (7, 8, 9, 10):
+                want_md[fld] = got_w["metadata"][fld]
+            np.testing.assert_array_equal(got_w["metadata"], want_md, err_msg=f"frame {f} member {b}: metadata")
+            assert got_w["instance_count"] == world.draw[1]
+            np.testing.assert_array_equal(got_w["indirect"], world.indirect, err_msg=f"frame {f} member {b}: lists")
+            np.testing.assert_array_equal(got_w["particles"], world.particles, err_msg=f"frame {f} member {b}: particles")
+    assert total_children > 100
