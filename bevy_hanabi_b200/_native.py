@@ -124,6 +124,7 @@ EFFECT_READ_PARENT_PARTICLE = 1 << 3
 EFFECT_RELAXED_ORDER = 1 << 4
 EFFECT_RIBBONS = 1 << 5
 EFFECT_FAST_MATH = 1 << 6
+EFFECT_ORDERED_EVENTS = 1 << 7
 
 
 def _load() -> C.CDLL:

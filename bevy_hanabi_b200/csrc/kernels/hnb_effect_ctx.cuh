@@ -29,6 +29,9 @@ struct Ctx {
     u32 base_child_index;
     u32* emit_events[HNB_MAX_EVENT_BINDINGS];
     u32 emit_events_capacity[HNB_MAX_EVENT_BINDINGS];
+#if HNB_ORDERED_EVENTS
+    u32 event_request[HNB_MAX_EVENT_BINDINGS];  // events this particle asked for, per channel (appended later, in row order)
+#endif
 #endif
 };
 
@@ -60,6 +63,13 @@ struct Ctx {
 // buffer with one atomic on ChildInfo.event_count, clamp to the buffer capacity, write the parent
 // particle index `count` times.
 HNB_DI void hnb_append_spawn_events(Ctx& hnb_ctx, u32 binding, u32 particle_index, u32 count) {
+#if HNB_ORDERED_EVENTS
+    // HNB_EFFECT_ORDERED_EVENTS: only record the request; k_events_* append every row's events after the update pass in
+    // the canonical (row) order, so the buffer — and which appends an overflow drops — no longer depends on scheduling.
+    (void)particle_index;
+    hnb_ctx.event_request[binding] += count;
+    return;
+#endif
     if (count == 0u) return;
     const u32 capacity = hnb_ctx.emit_events_capacity[binding];
     const u32 base = min(u32(atomicAdd(&hnb_ctx.child_infos[hnb_ctx.base_child_index + binding].event_count, i32(count))), capacity);

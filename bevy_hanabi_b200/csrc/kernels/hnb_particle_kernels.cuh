@@ -469,7 +469,19 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                     hnb_ctx.particle_index = pidx[k];
                     hnb_ctx.seed = pcg_hash(pidx[k] ^ spawner_seed);  // :138
                     hnb_ctx.is_alive = true;
+#if HNB_EMIT_EVENTS && HNB_ORDERED_EVENTS
+#pragma unroll
+                    for (int b = 0; b < HNB_MAX_EVENT_BINDINGS; ++b) hnb_ctx.event_request[b] = 0u;
+#endif
                     alive = hnb_update_body(particle, hnb_ctx);
+#if HNB_EMIT_EVENTS && HNB_ORDERED_EVENTS
+                    {
+                        const u32 row = row0 + (j * HNB_TILE_K + k) * 32u + lane;  // update thread index within the (single) instance
+#pragma unroll
+                        for (int b = 0; b < HNB_MAX_EVENT_BINDINGS; ++b)
+                            if (P.event_counts[b]) P.event_counts[b][row] = hnb_ctx.event_request[b];
+                    }
+#endif
                     hnb_pack<false>(particle, raw[k]);
                     hnb_store_raw(raw[k], P.slab, base_particle + pidx[k]);
                 }

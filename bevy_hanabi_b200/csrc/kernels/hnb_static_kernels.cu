@@ -291,6 +291,92 @@ __global__ void k_checksum(PlaneSet planes, u32 first, u32 count, u32 stride_wor
     if ((threadIdx.x & 31u) == 0) atomicAdd((unsigned long long*)out, (unsigned long long)acc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ordered event append (HNB_EFFECT_ORDERED_EVENTS). The update kernel stored, per update row, how many events the
+// particle asked for on a channel; these three launches append them in row order — the order a serial execution of the
+// reference's threads would produce (append_spawn_events_N, lib.rs:976-993): position = exclusive prefix of the counts,
+// clamped to the buffer capacity; ChildInfo.event_count receives the unclamped total like the reference's atomicAdd.
+// ---------------------------------------------------------------------------------------------
+#define EV_THREADS 256
+#define EV_ITEMS 8
+#define EV_ROWS_PER_BLOCK (EV_THREADS * EV_ITEMS)
+
+__device__ __forceinline__ u32 ev_block_exclusive_scan(u32 v, u32* s_warp, u32* total) {
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u;
+    u32 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    u32 before = 0u, all = 0u;
+    for (u32 w = 0; w < EV_THREADS / 32; ++w) {
+        const u32 x = s_warp[w];
+        before += w < warp ? x : 0u;
+        all += x;
+    }
+    __syncthreads();
+    if (total) *total = all;
+    return before + incl - v;
+}
+
+__global__ void __launch_bounds__(EV_THREADS) k_events_block_sums(EventAppendArgs a) {
+    __shared__ u32 s_warp[EV_THREADS / 32];
+    const u32 rows = a.metadata->max_update;
+    const u32 first = blockIdx.x * EV_ROWS_PER_BLOCK + threadIdx.x * EV_ITEMS;
+    u32 sum = 0u;
+#pragma unroll
+    for (u32 k = 0; k < EV_ITEMS; ++k)
+        if (first + k < rows) sum += a.counts[first + k];
+    u32 total;
+    ev_block_exclusive_scan(sum, s_warp, &total);
+    if (threadIdx.x == 0) a.block_sums[blockIdx.x] = total;
+}
+
+// one CTA: exclusive scan of the block sums in place, total into the child's event count
+__global__ void __launch_bounds__(EV_THREADS) k_events_scan_blocks(EventAppendArgs a, u32 num_blocks) {
+    __shared__ u32 s_warp[EV_THREADS / 32];
+    __shared__ u32 s_carry;
+    if (threadIdx.x == 0) s_carry = 0u;
+    __syncthreads();
+    for (u32 chunk = 0; chunk < num_blocks; chunk += EV_THREADS) {
+        const u32 i = chunk + threadIdx.x;
+        const u32 v = i < num_blocks ? a.block_sums[i] : 0u;
+        u32 total;
+        const u32 excl = ev_block_exclusive_scan(v, s_warp, &total);
+        const u32 carry = s_carry;
+        if (i < num_blocks) a.block_sums[i] = carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(&a.child_infos[a.metadata->base_child_index + a.binding].event_count, i32(s_carry));
+}
+
+__global__ void __launch_bounds__(EV_THREADS) k_events_write(EventAppendArgs a) {
+    __shared__ u32 s_warp[EV_THREADS / 32];
+    const u32 rows = a.metadata->max_update;
+    // the alive list the update pass READ: the column that is not indirect_write_index, instance-local rows
+    const u32* read_col = (a.metadata->indirect_write_index == 0u ? a.pong : a.ping) + a.spawner->slab_offset;
+    const u32 first = blockIdx.x * EV_ROWS_PER_BLOCK + threadIdx.x * EV_ITEMS;
+    u32 c[EV_ITEMS], sum = 0u;
+#pragma unroll
+    for (u32 k = 0; k < EV_ITEMS; ++k) {
+        c[k] = first + k < rows ? a.counts[first + k] : 0u;
+        sum += c[k];
+    }
+    u32 pos = a.block_sums[blockIdx.x] + ev_block_exclusive_scan(sum, s_warp, nullptr);
+#pragma unroll
+    for (u32 k = 0; k < EV_ITEMS; ++k) {
+        if (c[k] == 0u) continue;
+        const u32 particle_index = read_col[first + k];
+        for (u32 i = 0; i < c[k] && pos + i < a.capacity; ++i) a.buffer[pos + i] = particle_index;
+        pos += c[k];
+    }
+}
+
 // Effective SM clock: cycles elapsed on one SM over ~`window_ns` of the global timer.
 __global__ void k_measure_sm_clock(u64* out, u64 window_ns) {
     u64 t0, t1;
@@ -328,6 +414,14 @@ cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_b
     if (num_batches == 0) return cudaSuccess;
     k_bookkeeping<<<num_batches, BK_THREADS, 0, st>>>(T);
     if (T.num_child_infos) k_clear_events<<<blocks_for(num_effects, 64), 64, 0, st>>>(T);
+    return cudaGetLastError();
+}
+cudaError_t launch_ordered_event_append(const EventAppendArgs& a, u32 capacity_rows, cudaStream_t st) {
+    const u32 blocks = (capacity_rows + EV_ROWS_PER_BLOCK - 1) / EV_ROWS_PER_BLOCK;
+    if (blocks == 0) return cudaSuccess;
+    k_events_block_sums<<<blocks, EV_THREADS, 0, st>>>(a);
+    k_events_scan_blocks<<<1, EV_THREADS, 0, st>>>(a, blocks);
+    k_events_write<<<blocks, EV_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,

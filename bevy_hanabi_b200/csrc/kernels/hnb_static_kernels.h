@@ -54,6 +54,22 @@ struct RibbonSortArgs {
 cudaError_t launch_ribbon_sort(const RibbonSortArgs& args, bool any_large, u32 sm_count, cudaStream_t st, u32* launches);
 size_t ribbon_sort_hist_words(u32 grid);
 
+// Ordered event append of one emitting instance and one channel (HNB_EFFECT_ORDERED_EVENTS).
+struct EventAppendArgs {
+    const u32* counts;              // events requested by update row r (written by hnb_update)
+    const u32* ping;                // alive-list columns of the parent's slab
+    const u32* pong;
+    const Spawner* spawner;         // the emitting instance (slab_offset)
+    const EffectMetadata* metadata; // its row: max_update rows were updated, indirect_write_index tells the read column
+    u32* block_sums;                // scratch: one word per 2048 rows of slab capacity
+    ChildInfo* child_infos;         // event_count of row metadata->base_child_index + binding += total
+    u32 binding;                    // event channel
+    u32* buffer;                    // the child's event buffer
+    u32 capacity;                   // ... and its length
+};
+cudaError_t launch_ordered_event_append(const EventAppendArgs& a, u32 capacity_rows, cudaStream_t st);
+inline u32 ordered_event_blocks(u32 capacity_rows) { return (capacity_rows + 2047u) / 2048u; }
+
 cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t st);
 cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st);
 cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile, cudaStream_t st);

@@ -98,6 +98,7 @@ struct BatchParams {
     u32 tile_rows;                   // rows per update tile of this launch (multiple of 32*K, <= 32*K*HNB_MAX_CHUNKS)
     u32 _pad0;
     unsigned long long* debug;       // 16 counters, written only by kernels compiled with HNB_PROFILE=1
+    u32* event_counts[HNB_MAX_EVENT_BINDINGS];  // HNB_EFFECT_ORDERED_EVENTS: events requested by update row r on channel b (else NULL)
 };
 
 }  // namespace hnb

@@ -85,6 +85,9 @@ struct Slab {
     std::vector<Plane> planes;
     void* d_planes[HNB_RT_MAX_PLANES] = {};
     uint32_t *ping = nullptr, *pong = nullptr, *dead = nullptr;
+    // HNB_EFFECT_ORDERED_EVENTS scratch, allocated on first use: per channel the per-row event counts and their block sums
+    uint32_t* event_counts[HNB_MAX_EVENT_BINDINGS] = {};
+    uint32_t* event_block_sums[HNB_MAX_EVENT_BINDINGS] = {};
 };
 
 struct KernelModule {
@@ -512,6 +515,17 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
             P.emit_events_capacity[i] = c->event_buffers[bl.emit_events[i]].capacity;
         }
     }
+    if ((lp.fx->flags & HNB_EFFECT_ORDERED_EVENTS) && (lp.fx->flags & HNB_EFFECT_EMIT_GPU_SPAWN_EVENTS)) {
+        if (bi.prefix_sum_count != 1) fail(HNB_ERR_INVALID_ARG, "HNB_EFFECT_ORDERED_EVENTS needs a batch of exactly one instance");
+        for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
+            if (!P.emit_events[i]) continue;
+            if (!lp.slab->event_counts[i]) {
+                CUDA_CHECK(cudaMalloc((void**)&lp.slab->event_counts[i], size_t(lp.slab->capacity) * 4));
+                CUDA_CHECK(cudaMalloc((void**)&lp.slab->event_block_sums[i], size_t(hnb::ordered_event_blocks(lp.slab->capacity) + 1) * 4));
+            }
+            P.event_counts[i] = lp.slab->event_counts[i];
+        }
+    }
     P.init_thread_count = init_threads;
     P.debug = c->d_debug;
     P.tile_rows = tile;
@@ -699,6 +713,7 @@ void hnb_ctx_destroy(hnb_ctx* c) {
         if (!s.live) continue;
         for (auto p : s.d_planes) if (p) cudaFree(p);
         cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead);
+        for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) { cudaFree(s.event_counts[i]); cudaFree(s.event_block_sums[i]); }
     }
     for (auto& e : c->effects) if (e.d_props) cudaFree(e.d_props);
     for (auto& b : c->event_buffers) if (b.d) cudaFree(b.d);
@@ -761,6 +776,10 @@ int32_t hnb_slab_destroy(hnb_ctx* c, hnb_slab h) {
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         for (auto& p : s.d_planes) if (p) { cudaFree(p); p = nullptr; }
         cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead);
+        for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
+            cudaFree(s.event_counts[i]); cudaFree(s.event_block_sums[i]);
+            s.event_counts[i] = s.event_block_sums[i] = nullptr;
+        }
         s.live = false;
     });
 }
@@ -1213,6 +1232,30 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             uint32_t k = 0;
             for (auto& lp : plans) launch_update(c, lp, fork.lane(k++));
             fork.join();
+        }
+        // HNB_EFFECT_ORDERED_EVENTS: append the events the update rows asked for, in row order (three small launches
+        // per channel; the default is the reference's per-particle atomics inside the update kernel)
+        for (auto& lp : plans) {
+            if (!(lp.fx->flags & HNB_EFFECT_ORDERED_EVENTS) || !(lp.fx->flags & HNB_EFFECT_EMIT_GPU_SPAWN_EVENTS)) continue;
+            const hnb_batch_info& bi = c->h_at<hnb_batch_info>(c->lay.off_batch_infos)[lp.batch];
+            const hnb_spawner& sp = c->h_at<hnb_spawner>(c->lay.off_spawners)[bi.spawner_base];
+            if (sp.effect_metadata_index >= c->md_rows) fail(HNB_ERR_OUT_OF_RANGE, "spawner row points outside the metadata table");
+            for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
+                if (!lp.params.event_counts[i]) continue;
+                hnb::EventAppendArgs a{};
+                a.counts = lp.params.event_counts[i];
+                a.ping = lp.slab->ping;
+                a.pong = lp.slab->pong;
+                a.spawner = c->d_at<hnb::Spawner>(c->lay.off_spawners) + bi.spawner_base;
+                a.metadata = c->d_metadata + sp.effect_metadata_index;
+                a.block_sums = lp.slab->event_block_sums[i];
+                a.child_infos = c->d_child_infos;
+                a.binding = uint32_t(i);
+                a.buffer = lp.params.emit_events[i];
+                a.capacity = lp.params.emit_events_capacity[i];
+                CUDA_CHECK(hnb::launch_ordered_event_append(a, lp.slab->capacity, c->stream));
+                c->launches += 3;
+            }
         }
         // ribbons: passes "hanabi:sort_prefix_sum" (the reference re-runs vfx_prefix_sum over every batch,
         // mod.rs:7393-7428) and "hanabi:sort" (mod.rs:7444-7610)

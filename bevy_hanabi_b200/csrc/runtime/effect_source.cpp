@@ -236,6 +236,7 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
     o << "#define HNB_EMIT_EVENTS " << (emit ? 1 : 0) << "\n";
     o << "#define HNB_READ_PARENT " << (read_parent ? 1 : 0) << "\n";
     o << "#define HNB_RELAXED_ORDER " << ((d.flags & HNB_EFFECT_RELAXED_ORDER) ? 1 : 0) << "\n";
+    o << "#define HNB_ORDERED_EVENTS " << ((emit && (d.flags & HNB_EFFECT_ORDERED_EVENTS)) ? 1 : 0) << "\n";
     o << "#define HNB_FAST_MATH " << ((d.flags & HNB_EFFECT_FAST_MATH) ? 1 : 0) << "\n";  // compiled with contraction + approximate div/sqrt
     o << "#ifndef HNB_LOAD_PLANE\n"
          "#define HNB_LOAD_PLANE(T, base, row) (((const T*)(base))[row])\n"

@@ -237,10 +237,16 @@ enum {
                                                   order scheduling-dependent like the reference) */
     HNB_EFFECT_RIBBONS = 1u << 5,              /* LayoutFlags::RIBBONS (lib.rs:1018-1019): the layout has RIBBON_ID;
                                                   hnb_simulate() sorts the alive list by (RIBBON_ID, AGE) after the update */
-    HNB_EFFECT_FAST_MATH = 1u << 6             /* compile the effect with FMA contraction and approximate division /
+    HNB_EFFECT_FAST_MATH = 1u << 6,            /* compile the effect with FMA contraction and approximate division /
                                                   square root — the latitude a WGSL compiler has. fp32 results stay within
                                                   the 1e-5 relative bound but are no longer bit-identical to the oracle;
                                                   integer bookkeeping is unaffected. Pays off for ALU-bound effects. */
+    HNB_EFFECT_ORDERED_EVENTS = 1u << 7        /* with EMIT_GPU_SPAWN_EVENTS: events are appended after the update pass in
+                                                  the canonical (row) order instead of with per-particle atomics, so the
+                                                  event buffer and what an overflow drops are deterministic (the
+                                                  reference's order is scheduling-dependent, lib.rs:976-993). The batch must
+                                                  hold one instance (parents of GPU-event children never merge). Costs
+                                                  12 B of traffic per updated particle and channel. */
 };
 
 /**

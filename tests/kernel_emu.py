@@ -114,6 +114,7 @@ struct EmuBatch {
     uint32_t capacity, init_thread_count, properties_stride, tile_rows;
     // GPU spawn events (EmuScene)
     void* child_infos; uint32_t* consume_events; uint32_t* emit_events[4]; uint32_t emit_caps[4]; void* parent_planes[16];
+    uint32_t* event_counts[4];  // HNB_EFFECT_ORDERED_EVENTS
 };
 static hnb::BatchParams make_params(const EmuBatch* b) {
     hnb::BatchParams P;
@@ -142,6 +143,7 @@ static hnb::BatchParams make_params(const EmuBatch* b) {
     P.consume_events = b->consume_events;
     for (int i = 0; i < 4; ++i) { P.emit_events[i] = b->emit_events[i]; P.emit_events_capacity[i] = b->emit_caps[i]; }
     for (int p = 0; p < 16; ++p) P.parent_slab.planes[p] = b->parent_planes[p];
+    for (int i = 0; i < 4; ++i) P.event_counts[i] = b->event_counts[i];
     return P;
 }
 template <typename K> static void emu_launch(K kernel, const hnb::BatchParams& P, unsigned grid, size_t smem) {
@@ -198,7 +200,7 @@ class EmuBatch(C.Structure):
                [("planes", C.c_void_p * 16), ("ping", C.c_void_p), ("pong", C.c_void_p), ("dead", C.c_void_p),
                 ("capacity", C.c_uint32), ("init_thread_count", C.c_uint32), ("properties_stride", C.c_uint32), ("tile_rows", C.c_uint32),
                 ("child_infos", C.c_void_p), ("consume_events", C.c_void_p), ("emit_events", C.c_void_p * 4), ("emit_caps", C.c_uint32 * 4),
-                ("parent_planes", C.c_void_p * 16)]
+                ("parent_planes", C.c_void_p * 16), ("event_counts", C.c_void_p * 4)]
 
 
 def build_emulated_effect(lowered, allow_events: bool = False) -> C.CDLL:
@@ -458,6 +460,10 @@ class EmuScene:
             e.consume_events = ptr(self.events[m["consume"]])
         for i, ev in enumerate(m.get("emit") or []):
             e.emit_events[i], e.emit_caps[i] = ptr(self.events[ev]), len(self.events[ev])
+            if m.get("ordered"):
+                slab.setdefault("event_counts", {})[i] = np.zeros(slab["rows"], dtype=np.uint32)
+                slab.setdefault("event_block_sums", {})[i] = np.zeros(slab["rows"] // 2048 + 2, dtype=np.uint32)
+                e.event_counts[i] = ptr(slab["event_counts"][i])
         if m.get("parent") is not None:
             for p in range(16):
                 e.parent_planes[p] = ptr(self.slabs[m["parent"]]["planes"][p])
@@ -488,6 +494,19 @@ class EmuScene:
         self.static.semu_clear_events(C.byref(self.T), n)
         for slab in self.slabs:                     # pass "hanabi:update"
             slab["lib"].emu_update(C.byref(slab["b"]), self.update_ctas, 64 * 1024)
+        from tests.static_emu import EventAppendArgs
+        for b, m in enumerate(self.members):        # HNB_EFFECT_ORDERED_EVENTS: the three k_events_* launches per channel
+            if not m.get("ordered"):
+                continue
+            slab = self.slabs[b]
+            for i, ev in enumerate(m.get("emit") or []):
+                a = EventAppendArgs()
+                a.counts, a.ping, a.pong = slab["event_counts"][i].ctypes.data, slab["cols"][0].ctypes.data, slab["cols"][1].ctypes.data
+                a.spawner = C.addressof(self.spawners) + b * C.sizeof(O.Spawner)
+                a.metadata = C.addressof(self.metadata) + b * C.sizeof(O.EffectMetadata)
+                a.block_sums, a.child_infos, a.binding = slab["event_block_sums"][i].ctypes.data, self.child_infos.ctypes.data, i
+                a.buffer, a.capacity = self.events[ev].ctypes.data, len(self.events[ev])
+                self.static.semu_ordered_event_append(C.byref(a), slab["rows"])
 
     def pull(self, b):
         slab = self.slabs[b]

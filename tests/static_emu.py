@@ -100,6 +100,15 @@ extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTab
 extern "C" void semu_tile_prefix(const StaticTables* T, uint32_t batch, uint32_t tile) { StaticTables t = *T; emu_run([&] { k_tile_prefix(t, batch, tile); }, 1, 256); }
 extern "C" void semu_ribbon_sort_small(const RibbonSortArgs* a) { RibbonSortArgs r = *a; emu_run([&] { k_ribbon_sort_small(r); }, r.instance_count, 1024); }
 extern "C" void semu_ribbon_sort_large(const RibbonSortArgs* a, uint32_t grid) { RibbonSortArgs r = *a; r.scratch_grid = grid; emu_run([&] { k_ribbon_sort_large(r); }, grid, 512); }
+extern "C" void semu_ordered_event_append(const EventAppendArgs* a, uint32_t capacity_rows) {
+    EventAppendArgs e = *a;
+    const unsigned blocks = (capacity_rows + EV_ROWS_PER_BLOCK - 1) / EV_ROWS_PER_BLOCK;
+    emu_run([&] { k_events_block_sums(e); }, blocks, EV_THREADS);
+    emu_run([&] { k_events_scan_blocks(e, blocks); }, 1, EV_THREADS);
+    emu_run([&] { k_events_write(e); }, blocks, EV_THREADS);
+}
+extern "C" void semu_events_scan_blocks(const EventAppendArgs* a, uint32_t blocks) { EventAppendArgs e = *a; emu_run([&] { k_events_scan_blocks(e, blocks); }, 1, EV_THREADS); }
+extern "C" uint32_t semu_sizeof_event_args(void) { return sizeof(EventAppendArgs); }
 extern "C" uint32_t semu_sizeof_static_tables(void) { return sizeof(StaticTables); }
 extern "C" uint32_t semu_sizeof_ribbon_args(void) { return sizeof(RibbonSortArgs); }
 extern "C" uint32_t semu_hist_words(uint32_t grid) { return 2 * 8 * 256 + 256 * grid; }
@@ -157,7 +166,7 @@ def build() -> C.CDLL:
         if proc.returncode != 0:
             raise RuntimeError("host build of the static kernels failed:\n" + proc.stderr[:6000])
     lib = C.CDLL(str(so))
-    for f in ("semu_sizeof_static_tables", "semu_sizeof_ribbon_args"):
+    for f in ("semu_sizeof_static_tables", "semu_sizeof_ribbon_args", "semu_sizeof_event_args"):
         getattr(lib, f).restype = C.c_uint32
     lib.semu_hist_words.restype = C.c_uint32
     lib.semu_hist_words.argtypes = [C.c_uint32]
@@ -178,3 +187,9 @@ class RibbonSortArgs(C.Structure):
     _fields_ = [("planes", PlaneSet), ("ping", C.c_void_p), ("pong", C.c_void_p), ("spawners", C.c_void_p), ("metadata", C.c_void_p),
                 ("spawner_base", C.c_uint32), ("instance_count", C.c_uint32), ("scratch_keys", C.c_void_p * 2), ("scratch_vals", C.c_void_p * 2),
                 ("scratch_hist", C.c_void_p), ("scratch_rows", C.c_uint32), ("scratch_grid", C.c_uint32)]
+
+
+class EventAppendArgs(C.Structure):
+    """hnb::EventAppendArgs (hnb_static_kernels.h)"""
+    _fields_ = [("counts", C.c_void_p), ("ping", C.c_void_p), ("pong", C.c_void_p), ("spawner", C.c_void_p), ("metadata", C.c_void_p),
+                ("block_sums", C.c_void_p), ("child_infos", C.c_void_p), ("binding", C.c_uint32), ("buffer", C.c_void_p), ("capacity", C.c_uint32)]

@@ -305,3 +305,80 @@ def test_emulated_parent_child_spawn_events(orc):
             np.testing.assert_array_equal(got_w["indirect"], world.indirect, err_msg=f"frame {f} member {b}: lists")
             np.testing.assert_array_equal(got_w["particles"], world.particles, err_msg=f"frame {f} member {b}: particles")
     assert total_children > 100
+
+
+def test_emulated_ordered_spawn_events(orc):
+    """HNB_EFFECT_ORDERED_EVENTS under emulation: one parent, two channels (Always with a random count, OnDie x4), two
+    children, buffers that overflow. With ordered append the event buffers — and therefore both children — must equal
+    the oracle's canonical (serial thread order) result EXACTLY, frame after frame, overflow included."""
+    from tests import static_emu
+    from tests.kernel_emu import EmuScene
+    from tests.test_gpu_events import EVENT_CAP, _oracle_append_events, _oracle_child_init
+    wp = G.ExprWriter()
+    parent = (G.EffectAsset(1024, wp.module, name="emitter")
+              .init(G.SetAttributeModifier(A.POSITION, wp.rand(G.VEC3) * wp.lit(2.) - wp.lit(1.)))
+              .init(G.SetAttributeModifier(A.VELOCITY, wp.rand(G.VEC3) - wp.lit(0.5)))
+              .init(G.SetAttributeModifier(A.AGE, wp.lit(0.)))
+              .init(G.SetAttributeModifier(A.LIFETIME, wp.lit(0.1).uniform(wp.lit(0.5))))
+              .update(G.EmitSpawnEventModifier(G.ALWAYS, (wp.rand(G.FLOAT) * wp.lit(1.25)).cast(G.UINT), 0))
+              .update(G.EmitSpawnEventModifier(G.ON_DIE, wp.lit(G.U32(4)), 1)))
+    children = []
+    for tag in (0, 1):
+        wc = G.ExprWriter()
+        children.append(G.EffectAsset(4096, wc.module, name=f"child{tag}")
+                        .init(G.InheritAttributeModifier(A.POSITION))
+                        .init(G.SetAttributeModifier(A.VELOCITY, wc.parent_attr(A.VELOCITY) * wc.lit(0.25 + tag) + (wc.rand(G.VEC3) - wc.lit(0.5))))
+                        .init(G.SetAttributeModifier(A.AGE, wc.lit(0.)))
+                        .init(G.SetAttributeModifier(A.LIFETIME, wc.lit(0.2 + 0.1 * tag)))
+                        .init(G.SetAttributeModifier(A.U32_0, wc.parent_attr(A.ID))))
+    p_fx = parent.generate(num_event_bindings=2, ordered_events=True)
+    c_fx = [c.generate(parent=parent) for c in children]
+    dt = 1.0 / 30.0
+    pw = RefWorld(1024, p_fx.particle_stride // 4, [Instance(0, 1024, alive=0, seed=1)], dt=dt)
+    cw = [RefWorld(4096, c_fx[0].particle_stride // 4, [Instance(0, 4096, alive=0, seed=2 + k)], dt=dt) for k in (0, 1)]
+    po, co = EffectOracle(parent), [EffectOracle(c) for c in children]
+    # members in batch order: children first (EffectSorter), then the parent; child infos / buffers 0, 1 = channels 0, 1
+    scene = EmuScene([dict(ref=cw[0], lowered=c_fx[0], parent=2, consume=0, child_row=0),
+                      dict(ref=cw[1], lowered=c_fx[1], parent=2, consume=1, child_row=1),
+                      dict(ref=pw, lowered=p_fx, emit=[0, 1], base_child_row=0, ordered=True)], [EVENT_CAP, EVENT_CAP], static_emu.build())
+    events = [np.zeros(EVENT_CAP, dtype=np.uint32) for _ in (0, 1)]
+    event_count, spawned, overflowed = [0, 0], [0, 0], False
+    spawn_sched = [700, 0, 0, 150, 0, 0, 0, 800, 0, 0, 0, 0, 100, 0]
+    for f, spawn in enumerate(spawn_sched):
+        seed_p = int(pcg_hash(np.array([5000 + f], dtype=np.uint32))[0])
+        seed_c = [int(pcg_hash(np.array([6000 + 10 * f + k], dtype=np.uint32))[0]) for k in (0, 1)]
+        # the buffers as the previous frame's ordered append left them: EXACTLY the canonical sequence
+        for k in (0, 1):
+            assert int(scene.child_infos[k, 1]) == event_count[k], f"frame {f} channel {k}: event count"
+            nv = min(event_count[k], EVENT_CAP)
+            overflowed |= event_count[k] > EVENT_CAP
+            np.testing.assert_array_equal(scene.events[k][:nv], events[k][:nv], err_msg=f"frame {f} channel {k}: event order")
+        n_valid = [min(event_count[k], EVENT_CAP) for k in (0, 1)]
+        t = np.float32(f * dt)
+        pw.sim.time = t
+        for k in (0, 1):
+            cw[k].sim.time = t
+            cw[k].set_spawns([0], [seed_c[k]])
+            spawned[k] += _oracle_child_init(children[k], co[k], cw[k], po, pw, events[k], n_valid[k], seed_c[k])
+        pw.set_spawns([spawn], [seed_p])
+        po.init_pass(pw)
+        event_count = [0, 0]
+        for w in (cw[0], cw[1], pw):
+            w.oracle_indirect(orc)
+            w.oracle_prefix_sum(orc)
+        for k in (0, 1):
+            co[k].update_pass(cw[k])
+        po.update_pass(pw)
+        for channel, counts in po.last_emitted:
+            event_count[channel] = _oracle_append_events(pw, counts, events[channel], event_count[channel])
+        scene.frame_step(pw.sim, [0, 0, spawn], [seed_c[0], seed_c[1], seed_p])
+        for b, world in enumerate((cw[0], cw[1], pw)):
+            got = scene.pull(b)
+            want_md = world.metadata_rows()[0].copy()
+            want_md[5] = b
+            for fld in (7, 8, 9, 10):
+                want_md[fld] = got["metadata"][fld]
+            np.testing.assert_array_equal(got["metadata"], want_md, err_msg=f"frame {f} member {b}: metadata")
+            np.testing.assert_array_equal(got["indirect"], world.indirect, err_msg=f"frame {f} member {b}: lists")
+            np.testing.assert_array_equal(got["particles"], world.particles, err_msg=f"frame {f} member {b}: particles")
+    assert spawned[0] > 100 and spawned[1] > 100 and overflowed

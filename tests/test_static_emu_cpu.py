@@ -187,3 +187,52 @@ def test_ribbon_sort_large_kernel(semu, wide):
     semu.semu_ribbon_sort_large(C.byref(a), grid)
     expect_large = [e for e in expect if e[1] > 2048]     # the large kernel leaves n <= 2048 to the small one
     _check_sorted(keep, expect_large, before)
+
+
+# ---- ordered event append ---------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cap", [(0, 16), (1, 16), (300, 64), (2048, 256), (2049, 100000), (9000, 1000)])
+def test_ordered_event_append_kernels(semu, rows, cap):
+    """k_events_block_sums / _scan_blocks / _write against the serial definition (append_spawn_events_N in thread order,
+    lib.rs:976-993): position = exclusive prefix of the requested counts, clamped to the buffer; count = total."""
+    rng = np.random.default_rng(rows + cap)
+    capacity_rows, base = rows + 500, 37
+    counts = rng.integers(0, 2**32, capacity_rows).astype(u32)                  # junk beyond `rows` must be ignored
+    counts[:rows] = np.where(rng.random(rows) < 0.3, rng.integers(1, 6, rows), 0)
+    if rows > 10:
+        counts[rows // 2] = 700                                                  # one particle asking for many events
+    read_col = rng.permutation(capacity_rows).astype(u32)
+    ping, pong = np.zeros(base + capacity_rows, dtype=u32), np.zeros(base + capacity_rows, dtype=u32)
+    pong[base:] = read_col                                                       # indirect_write_index 0 -> the update read pong
+    md, sp = (O.EffectMetadata * 1)(), (O.Spawner * 1)()
+    md[0].max_update, md[0].indirect_write_index, md[0].base_child_index = rows, 0, 2
+    sp[0].slab_offset = base
+    child_infos = np.zeros((5, 2), dtype=np.int32)
+    child_infos[3, 1] = 11                                                       # event_count accumulates (atomicAdd)
+    buffer = np.full(cap, 0xDEADBEEF, dtype=u32)
+    block_sums = np.zeros(capacity_rows // 2048 + 2, dtype=u32)
+    a = S.EventAppendArgs()
+    a.counts, a.ping, a.pong, a.spawner, a.metadata = counts.ctypes.data, ping.ctypes.data, pong.ctypes.data, C.addressof(sp), C.addressof(md)
+    a.block_sums, a.child_infos, a.binding, a.buffer, a.capacity = block_sums.ctypes.data, child_infos.ctypes.data, 1, buffer.ctypes.data, cap
+    semu.semu_ordered_event_append(C.byref(a), capacity_rows)
+    want = np.repeat(read_col[:rows], counts[:rows])
+    total = int(counts[:rows].sum())
+    assert child_infos[3, 1] == 11 + total and not child_infos[[0, 1, 2, 4]].any()
+    kept = min(total, cap)
+    np.testing.assert_array_equal(buffer[:kept], want[:kept])
+    assert (buffer[kept:] == 0xDEADBEEF).all()
+
+
+def test_ordered_event_block_scan_over_many_blocks(semu):
+    """The single-CTA scan of the block sums loops over chunks of 256 blocks (slabs above 512 Ki rows)."""
+    rng = np.random.default_rng(5)
+    n = 700
+    sums = rng.integers(0, 5000, n).astype(u32)
+    work = sums.copy()
+    md = (O.EffectMetadata * 1)()
+    md[0].base_child_index = 0
+    child_infos = np.zeros((1, 2), dtype=np.int32)
+    a = S.EventAppendArgs()
+    a.block_sums, a.child_infos, a.metadata, a.binding = work.ctypes.data, child_infos.ctypes.data, C.addressof(md), 0
+    semu.semu_events_scan_blocks(C.byref(a), n)
+    np.testing.assert_array_equal(work, np.concatenate([[0], np.cumsum(sums)[:-1]]).astype(u32))
+    assert child_infos[0, 1] == int(sums.sum())
