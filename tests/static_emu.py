@@ -21,6 +21,7 @@ KERNELS = ROOT / "bevy_hanabi_b200" / "csrc" / "kernels"
 OUT = ROOT / "build" / "kernel_emu"
 
 EXTRA_PRELUDE = r"""
+#include <algorithm>
 #include <map>
 #include <mutex>
 typedef int cudaError_t;
@@ -65,29 +66,34 @@ namespace cooperative_groups {
 struct grid_group { void sync() const { pthread_barrier_wait(&emu::launch->grid_bar); } };
 static inline grid_group this_grid() { return grid_group(); }
 }
-template <typename F> static void emu_run(F body, unsigned grid, unsigned block) {
+// `wave`: how many CTAs run at the same time (0 = the whole grid, required when the kernel has grid-wide barriers)
+template <typename F> static void emu_run(F body, unsigned grid, unsigned block, unsigned wave = 0) {
+    if (wave == 0 || wave > grid) wave = grid;
     emu::Launch L;
     L.grid = grid; L.block = block;
     pthread_barrier_init(&L.grid_bar, nullptr, grid * block);
-    std::vector<emu::Cta> ctas(grid);
-    std::vector<emu::CtaExtra> extra(grid);
-    for (unsigned b = 0; b < grid; ++b) {
-        pthread_barrier_init(&ctas[b].bar, nullptr, block);
-        ctas[b].dyn = nullptr;
-        extra[b].or_acc = 0;
-        for (unsigned w = 0; w < (block + 31) / 32; ++w) pthread_barrier_init(&ctas[b].warps[w].bar, nullptr, 32);
+    for (unsigned first = 0; first < grid; first += wave) {
+        const unsigned count = std::min(wave, grid - first);
+        std::vector<emu::Cta> ctas(count);
+        std::vector<emu::CtaExtra> extra(count);
+        for (unsigned b = 0; b < count; ++b) {
+            pthread_barrier_init(&ctas[b].bar, nullptr, block);
+            ctas[b].dyn = nullptr;
+            extra[b].or_acc = 0;
+            for (unsigned w = 0; w < (block + 31) / 32; ++w) pthread_barrier_init(&ctas[b].warps[w].bar, nullptr, 32);
+        }
+        std::vector<std::thread> threads;
+        for (unsigned b = 0; b < count; ++b)
+            for (unsigned t = 0; t < block; ++t)
+                threads.emplace_back([&, b, t] {
+                    emu::tls.tid = t; emu::tls.bid = first + b; emu::tls.lane = t & 31u;
+                    emu::tls.cta = &ctas[b]; emu::tls.warp = &ctas[b].warps[t >> 5];
+                    emu::launch = &L; emu::cta_extra = &extra[b];
+                    body();
+                });
+        for (auto& th : threads) th.join();
+        for (auto& e : extra) for (auto& kv : e.shared) free(kv.second);
     }
-    std::vector<std::thread> threads;
-    for (unsigned b = 0; b < grid; ++b)
-        for (unsigned t = 0; t < block; ++t)
-            threads.emplace_back([&, b, t] {
-                emu::tls.tid = t; emu::tls.bid = b; emu::tls.lane = t & 31u;
-                emu::tls.cta = &ctas[b]; emu::tls.warp = &ctas[b].warps[t >> 5];
-                emu::launch = &L; emu::cta_extra = &extra[b];
-                body();
-            });
-    for (auto& th : threads) th.join();
-    for (auto& e : extra) for (auto& kv : e.shared) free(kv.second);
 }
 """
 
@@ -96,16 +102,16 @@ using namespace hnb;
 extern "C" void semu_indirect(const StaticTables* T, uint32_t n) { StaticTables t = *T; emu_run([&] { k_indirect(t); }, (n + 63) / 64, 64); }
 extern "C" void semu_clear_events(const StaticTables* T, uint32_t n) { StaticTables t = *T; emu_run([&] { k_clear_events(t); }, (n + 63) / 64, 64); }
 extern "C" void semu_prefix_sum(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_prefix_sum(t); }, (nb + 63) / 64, 64); }
-extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_bookkeeping(t); }, nb, 256); }
+extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_bookkeeping(t); }, nb, 256, 8); }
 extern "C" void semu_tile_prefix(const StaticTables* T, uint32_t batch, uint32_t tile) { StaticTables t = *T; emu_run([&] { k_tile_prefix(t, batch, tile); }, 1, 256); }
-extern "C" void semu_ribbon_sort_small(const RibbonSortArgs* a) { RibbonSortArgs r = *a; emu_run([&] { k_ribbon_sort_small(r); }, r.instance_count, 1024); }
+extern "C" void semu_ribbon_sort_small(const RibbonSortArgs* a) { RibbonSortArgs r = *a; emu_run([&] { k_ribbon_sort_small(r); }, r.instance_count, 1024, 3); }
 extern "C" void semu_ribbon_sort_large(const RibbonSortArgs* a, uint32_t grid) { RibbonSortArgs r = *a; r.scratch_grid = grid; emu_run([&] { k_ribbon_sort_large(r); }, grid, 512); }
 extern "C" void semu_ordered_event_append(const EventAppendArgs* a, uint32_t capacity_rows) {
     EventAppendArgs e = *a;
     const unsigned blocks = (capacity_rows + EV_ROWS_PER_BLOCK - 1) / EV_ROWS_PER_BLOCK;
-    emu_run([&] { k_events_block_sums(e); }, blocks, EV_THREADS);
+    emu_run([&] { k_events_block_sums(e); }, blocks, EV_THREADS, 8);
     emu_run([&] { k_events_scan_blocks(e, blocks); }, 1, EV_THREADS);
-    emu_run([&] { k_events_write(e); }, blocks, EV_THREADS);
+    emu_run([&] { k_events_write(e); }, blocks, EV_THREADS, 8);
 }
 extern "C" void semu_events_scan_blocks(const EventAppendArgs* a, uint32_t blocks) { EventAppendArgs e = *a; emu_run([&] { k_events_scan_blocks(e, blocks); }, 1, EV_THREADS); }
 extern "C" uint32_t semu_sizeof_event_args(void) { return sizeof(EventAppendArgs); }
