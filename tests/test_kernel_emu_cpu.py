@@ -382,3 +382,41 @@ def test_emulated_ordered_spawn_events(orc):
             np.testing.assert_array_equal(got["indirect"], world.indirect, err_msg=f"frame {f} member {b}: lists")
             np.testing.assert_array_equal(got["particles"], world.particles, err_msg=f"frame {f} member {b}: particles")
     assert spawned[0] > 100 and spawned[1] > 100 and overflowed
+
+
+@pytest.mark.parametrize("extra", [0, 1, 2])
+def test_wide_records_and_plane_tails(orc, extra):
+    """Record widths that change the kernel's shape: with many attributes the tile K drops from 4 (C5) over 2 (48-byte
+    trails) to 1 row per lane. (Every effect has POSITION, a vec3, so records are multiples of 16 bytes: the 8- and
+    4-byte tail planes only exist for raw slabs, tests/test_gpu_misc.py::test_aos_soa_roundtrip_odd_strides.)"""
+    w = G.ExprWriter()
+    asset = (G.EffectAsset(700, w.module, name=f"wide{extra}")
+             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(2.) - w.lit(1.)))
+             .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) - w.lit(0.5)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+             .init(G.SetAttributeModifier(A.LIFETIME, w.lit(0.15).uniform(w.lit(0.5))))
+             .init(G.SetAttributeModifier(A.F32X4_0, w.rand(G.VEC4)))
+             .init(G.SetAttributeModifier(A.HDR_COLOR, w.rand(G.VEC4) * w.lit(3.)))
+             .update(G.SetAttributeModifier(A.F32X4_1, w.attr(A.F32X4_0) * w.attr(A.HDR_COLOR) + w.attr(A.F32X4_1)))
+             .update(G.SetAttributeModifier(A.F32X3_0, w.attr(A.VELOCITY).cross(w.attr(A.POSITION))))
+             .update(G.AccelModifier(w.lit(G.Vec3(0., -3., 0.)))))
+    if extra >= 1:
+        asset = asset.update(G.SetAttributeModifier(A.SIZE2, w.attr(A.SIZE2) + w.lit(G.Vec2(0.5, 0.25))))          # + an 8-byte attribute
+    if extra >= 2:
+        asset = (asset.update(G.SetAttributeModifier(A.F32X3_1, w.attr(A.F32X3_1) + w.attr(A.VELOCITY)))
+                 .update(G.SetAttributeModifier(A.AXIS_X, w.attr(A.VELOCITY).normalize()))
+                 .update(G.SetAttributeModifier(A.U32_0, w.attr(A.U32_0) + w.lit(G.U32(3)))))
+    fx = asset.generate()
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(700, size // 4, [Instance(0, 700, alive=0, seed=5 + extra)], dt=1 / 10)
+    eo = EffectOracle(asset)
+    emu = EmuWorld(ref, fx, chunks=1, update_ctas=2)
+    for f in range(5):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn, seed = [500 if f == 0 else 60], [int(pcg_hash(np.array([f + 50], dtype=np.uint32))[0])]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        _assert_same(ref, emu.pull(), f"stride {size}, frame {f}")
+    print(f"stride {size} bytes, tile K {emu.lib.emu_tile_k()}")
+
