@@ -11,6 +11,8 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA GPU (B200); run with -m gpu on the GPU box")
+    # emulation tests spin on real OS threads: a protocol bug must fail, not hang (marker of pytest-timeout; a no-op without it)
+    config.addinivalue_line("markers", "timeout(seconds): per-test time limit (pytest-timeout)")
 
 
 def _has_gpu() -> bool:

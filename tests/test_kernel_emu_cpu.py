@@ -15,6 +15,7 @@ from tests.test_gpu_effects import _firework_trails
 from tests.test_gpu_scene import _drifting_sparks
 
 A = G.Attribute
+pytestmark = pytest.mark.timeout(600)  # real threads: a protocol bug must fail, not hang
 
 
 def _assert_same(ref, got, what):

@@ -20,6 +20,7 @@ import random
 import pytest
 
 WINDOW = 32
+pytestmark = pytest.mark.timeout(600)  # a protocol bug must fail, not hang
 
 
 class Grid:

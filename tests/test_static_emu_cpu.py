@@ -10,6 +10,7 @@ from tests import static_emu as S
 
 u32 = np.uint32
 u32p = C.POINTER(C.c_uint32)
+pytestmark = pytest.mark.timeout(600)  # real threads: a protocol bug must fail, not hang
 
 
 @pytest.fixture(scope="module")
