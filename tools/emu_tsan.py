@@ -116,6 +116,64 @@ int main(int argc, char** argv) {
 """
 
 
+EVENTS_MAIN = r"""
+#include <stdio.h>
+#include <stdlib.h>
+int main() {
+    const uint32_t rows = 9000, capacity_rows = 9500, cap = 4000;
+    std::vector<uint32_t> counts(capacity_rows), ping(capacity_rows), pong(capacity_rows), buffer(cap, 0xDEADBEEFu), block_sums(capacity_rows / 2048 + 2);
+    uint32_t s = 7u, total = 0;
+    auto rnd = [&] { s = s * 1664525u + 1013904223u; return s; };
+    for (uint32_t i = 0; i < capacity_rows; ++i) { counts[i] = (rnd() >> 8) % 3u; pong[i] = i * 3u; if (i < rows) total += counts[i]; }
+    hnb::EffectMetadata md; memset(&md, 0, sizeof md); md.max_update = rows; md.indirect_write_index = 0; md.base_child_index = 0;
+    hnb::Spawner sp; memset(&sp, 0, sizeof sp);
+    hnb::ChildInfo ci[1] = {{0, 0}};
+    hnb::EventAppendArgs a; memset(&a, 0, sizeof a);
+    a.counts = counts.data(); a.ping = ping.data(); a.pong = pong.data(); a.spawner = &sp; a.metadata = &md; a.block_sums = block_sums.data();
+    a.child_infos = ci; a.binding = 0; a.buffer = buffer.data(); a.capacity = cap;
+    semu_ordered_event_append(&a, capacity_rows);
+    uint32_t pos = 0;
+    for (uint32_t r = 0; r < rows && pos < cap; ++r)
+        for (uint32_t i = 0; i < counts[r] && pos < cap; ++i, ++pos)
+            if (buffer[pos] != r * 3u) { printf("event %u wrong\n", pos); return 2; }
+    printf("ordered append: %u events requested, %d counted, %u kept and in order\n", total, ci[0].event_count, pos);
+    return ci[0].event_count == (int)total ? 0 : 3;
+}
+"""
+
+
+def static_program(name, main_text):
+    """Build the emulated static kernels + `main_text` with -fsanitize=thread."""
+    from tests import static_emu as S
+    import re
+    wgsl = S._strip_includes((S.KERNELS / "hnb_wgsl.cuh").read_text())
+    tables = S._strip_includes((S.KERNELS / "hnb_tables.cuh").read_text())
+    header = S._strip_includes((S.KERNELS / "hnb_static_kernels.h").read_text())
+    static = (S.KERNELS / "hnb_static_kernels.cu").read_text()
+    static = S._strip_includes(static[:static.index("cudaError_t launch_indirect(")]) + "\n}  // namespace hnb\n"
+    ribbon = (S.KERNELS / "hnb_ribbon_sort.cu").read_text()
+    ribbon = S._strip_includes(ribbon[:ribbon.index("cudaError_t launch_ribbon_sort(")]) + "\n}  // namespace hnb\n"
+    static = re.sub(r"__global__ void k_measure_sm_clock.*?\n}\n", "", static, flags=re.S)
+    body = S._rewrite_shared(static + "\n" + ribbon)
+    out = ROOT / "build" / "kernel_emu"
+    out.mkdir(parents=True, exist_ok=True)
+    cpp, exe = out / f"tsan_{name}.cpp", out / f"tsan_{name}"
+    cpp.write_text(K.PRELUDE + S.EXTRA_PRELUDE + wgsl + "\n" + tables + "\n" + header + "\n" + body + S.DRIVER + main_text)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", str(cpp), "-o", str(exe)], check=True)
+    return exe
+
+
+def events_program():
+    exe = static_program("events", EVENTS_MAIN)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
+    races = p.stderr.count("WARNING: ThreadSanitizer: data race")
+    print(f"ordered event append kernels: exit {p.returncode}, {races} data-race reports")
+    print(p.stdout.strip())
+    if races:
+        print(p.stderr[:6000])
+    return p.returncode or races
+
+
 def sort_program():
     """The ribbon-sort kernels (bitonic in shared memory + cooperative radix sort) under ThreadSanitizer."""
     from tests import static_emu as S
@@ -147,7 +205,7 @@ def sort_program():
 
 
 def main():
-    rc_sort = sort_program()
+    rc_sort = sort_program() | events_program()
     src = recipes.c5_lowered().generate_source()
     for old, new in K.SUBSTITUTIONS:
         assert src.count(old) == 1
