@@ -421,3 +421,18 @@ def test_wide_records_and_plane_tails(orc, extra):
         _assert_same(ref, emu.pull(), f"stride {size}, frame {f}")
     print(f"stride {size} bytes, tile K {emu.lib.emu_tile_k()}")
 
+
+
+@pytest.mark.parametrize("defines", ["HNB_DEFER_COMPACTION=0", "HNB_LOOKBACK_GROUPS=4", "HNB_LOOKBACK_GROUPS=2;HNB_DEFER_COMPACTION=0"])
+def test_kernel_tuning_variants_stay_exact(orc, monkeypatch, defines):
+    """The tuning hooks of the update kernel (HNB_DEFINES: immediate instead of deferred compaction, wider look-back
+    windows) are different schedules of the same computation: results must not change."""
+    monkeypatch.setenv("HNB_DEFINES", defines)
+    rng = np.random.default_rng(21)
+    ref = _c5_world(rng, [Instance(0, 9000, alive=8800, seed=42)])   # ~70 tiles of 128 rows: several look-back windows
+    emu = EmuWorld(ref, recipes.c5_lowered(), chunks=1, update_ctas=3)
+    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+    for step in range(3):
+        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
+        emu.frame_step(orc, ref.sim, [0], [42])
+        _assert_same(ref, emu.pull(), f"{defines}: step {step}")
