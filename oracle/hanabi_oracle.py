@@ -608,6 +608,7 @@ class EffectOracle:
             md.particle_counter = (md.particle_counter + n) & 0xFFFFFFFF
 
     def update_pass(self, world, b: int = 0):
+        self.last_emitted = []  # [(channel, per-row event counts)] of the last instance updated (none when nothing was alive)
         for i in world.batches[b]:
             sp, md = world.spawners[i], world.metadata[i]
             n = md.max_update

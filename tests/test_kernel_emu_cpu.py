@@ -436,3 +436,93 @@ def test_kernel_tuning_variants_stay_exact(orc, monkeypatch, defines):
         ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
         emu.frame_step(orc, ref.sim, [0], [42])
         _assert_same(ref, emu.pull(), f"{defines}: step {step}")
+
+
+@pytest.mark.parametrize("ordered", [False, True])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_event_scenes(orc, ordered, seed):
+    """Randomised parent / two-children scenes (emission probability, events per death, lifetimes, spawn schedule,
+    tile size, grid). Default mode: event buffers as multisets (sub-multisets on overflow), the oracle adopts the
+    buffer's order; ordered mode: exact buffers. Everything else exact in both."""
+    from collections import Counter
+    from tests import static_emu
+    from tests.kernel_emu import EmuScene
+    from tests.test_gpu_events import EVENT_CAP, _oracle_append_events, _oracle_child_init
+    rng = np.random.default_rng(700 + seed)
+    p_cap, c_cap = int(rng.choice([300, 1024, 1500])), 4096
+    wp = G.ExprWriter()
+    parent = (G.EffectAsset(p_cap, wp.module, name="emitter")
+              .init(G.SetAttributeModifier(A.POSITION, wp.rand(G.VEC3) * wp.lit(2.) - wp.lit(1.)))
+              .init(G.SetAttributeModifier(A.VELOCITY, wp.rand(G.VEC3) - wp.lit(0.5)))
+              .init(G.SetAttributeModifier(A.AGE, wp.lit(0.)))
+              .init(G.SetAttributeModifier(A.LIFETIME, wp.lit(float(rng.choice([0.05, 0.1]))).uniform(wp.lit(float(rng.choice([0.3, 0.6]))))))
+              .update(G.EmitSpawnEventModifier(G.ALWAYS, (wp.rand(G.FLOAT) * wp.lit(float(rng.choice([1.0625, 1.25, 1.5])))).cast(G.UINT), 0))
+              .update(G.EmitSpawnEventModifier(G.ON_DIE, wp.lit(G.U32(int(rng.integers(1, 6)))), 1)))
+    children = []
+    for tag in (0, 1):
+        wc = G.ExprWriter()
+        children.append(G.EffectAsset(c_cap, wc.module, name=f"child{tag}")
+                        .init(G.InheritAttributeModifier(A.POSITION))
+                        .init(G.SetAttributeModifier(A.VELOCITY, wc.parent_attr(A.VELOCITY) * wc.lit(0.5 + tag) + (wc.rand(G.VEC3) - wc.lit(0.5))))
+                        .init(G.SetAttributeModifier(A.AGE, wc.lit(0.)))
+                        .init(G.SetAttributeModifier(A.LIFETIME, wc.lit(0.15 + 0.1 * tag)))
+                        .init(G.SetAttributeModifier(A.U32_0, wc.parent_attr(A.ID))))
+    p_fx = parent.generate(num_event_bindings=2, ordered_events=ordered)
+    c_fx = [c.generate(parent=parent) for c in children]
+    dt = 1.0 / 30.0
+    pw = RefWorld(p_cap, p_fx.particle_stride // 4, [Instance(0, p_cap, alive=0, seed=1)], dt=dt)
+    cw = [RefWorld(c_cap, c_fx[0].particle_stride // 4, [Instance(0, c_cap, alive=0, seed=2 + k)], dt=dt) for k in (0, 1)]
+    po, co = EffectOracle(parent), [EffectOracle(c) for c in children]
+    scene = EmuScene([dict(ref=cw[0], lowered=c_fx[0], parent=2, consume=0, child_row=0),
+                      dict(ref=cw[1], lowered=c_fx[1], parent=2, consume=1, child_row=1),
+                      dict(ref=pw, lowered=p_fx, emit=[0, 1], base_child_row=0, ordered=ordered)], [EVENT_CAP, EVENT_CAP], static_emu.build(),
+                     chunks=int(rng.choice([1, 2])), update_ctas=int(rng.integers(1, 4)))
+    events = [np.zeros(EVENT_CAP, dtype=np.uint32) for _ in (0, 1)]
+    event_count, all_emitted = [0, 0], [[], []]
+    for f in range(10):
+        spawn = int(rng.integers(0, p_cap)) if rng.random() < 0.4 else 0
+        seed_p = int(pcg_hash(np.array([seed * 1000 + f], dtype=np.uint32))[0])
+        seed_c = [int(pcg_hash(np.array([seed * 1000 + 500 + 10 * f + k], dtype=np.uint32))[0]) for k in (0, 1)]
+        n_valid = []
+        for k in (0, 1):
+            assert int(scene.child_infos[k, 1]) == event_count[k]
+            nv = min(event_count[k], EVENT_CAP)
+            got = scene.events[k].copy()
+            if ordered:
+                np.testing.assert_array_equal(got[:nv], events[k][:nv], err_msg=f"frame {f} channel {k}: event order")
+            elif event_count[k] <= EVENT_CAP:
+                assert sorted(got[:nv].tolist()) == sorted(events[k][:nv].tolist())
+            else:
+                emitted, kept = Counter(all_emitted[k]), Counter(got.tolist())
+                assert all(kept[p] <= emitted[p] for p in kept)
+            events[k][:nv] = got[:nv]
+            n_valid.append(nv)
+        t = np.float32(f * dt)
+        pw.sim.time = t
+        for k in (0, 1):
+            cw[k].sim.time = t
+            cw[k].set_spawns([0], [seed_c[k]])
+            _oracle_child_init(children[k], co[k], cw[k], po, pw, events[k], n_valid[k], seed_c[k])
+        pw.set_spawns([spawn], [seed_p])
+        po.init_pass(pw)
+        event_count = [0, 0]
+        for w in (cw[0], cw[1], pw):
+            w.oracle_indirect(orc)
+            w.oracle_prefix_sum(orc)
+        for k in (0, 1):
+            co[k].update_pass(cw[k])
+        po.update_pass(pw)
+        for channel, counts in po.last_emitted:
+            event_count[channel] = _oracle_append_events(pw, counts, events[channel], event_count[channel])
+            rows_read = pw.indirect[:pw.metadata[0].max_update, 1 - pw.metadata[0].indirect_write_index]
+            all_emitted[channel] = np.repeat(rows_read, counts[:len(rows_read)]).tolist()
+        scene.frame_step(pw.sim, [0, 0, spawn], [seed_c[0], seed_c[1], seed_p])
+        for b, world in enumerate((cw[0], cw[1], pw)):
+            got = scene.pull(b)
+            want_md = world.metadata_rows()[0].copy()
+            want_md[5] = b
+            for fld in (7, 8, 9, 10):
+                want_md[fld] = got["metadata"][fld]
+            np.testing.assert_array_equal(got["metadata"], want_md, err_msg=f"frame {f} member {b}: metadata")
+            np.testing.assert_array_equal(got["indirect"], world.indirect, err_msg=f"frame {f} member {b}: lists")
+            np.testing.assert_array_equal(got["particles"], world.particles, err_msg=f"frame {f} member {b}: particles")
