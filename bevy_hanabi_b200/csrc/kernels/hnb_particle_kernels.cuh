@@ -21,8 +21,8 @@
 //     list (coalesced u32), particles through float4 SoA planes, processed in registers and written
 //     back; survivors are compacted into the write list in row order with warp ballots inside the tile
 //     and a decoupled look-back chain (one 64-bit state word per tile) across the tiles of the same
-//     instance; dead rows are pushed on the dead stack in the same canonical (row) order. There is no
-//     block barrier and — in ordered mode — the only atomic is the tile ticket: the per-particle contended
+//     instance; dead rows are pushed on the dead stack in the same canonical (row) order. There is one
+//     block barrier (after the prologue) and — in ordered mode — the only atomic is the tile ticket: the per-particle contended
 //     atomics of the reference (vfx_update.wgsl:150,160,164) become exact ranks, which also makes the
 //     list ORDER deterministic (= the reference's threads run in ascending global_invocation_id).
 //     With HNB_RELAXED_ORDER the chain is replaced by one warp-aggregated atomic per tile (counts and
