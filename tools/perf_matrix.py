@@ -212,7 +212,46 @@ def many_batches():
         ctx.close()
 
 
-SCENARIOS = {"many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
+def churn():
+    """Steady-state churn: constant spawn rate into recycled slots until the alive list is a random-looking permutation
+    of the slab (survivors keep their relative order, new particles land in whatever slots died). The gathers then touch
+    scattered 16-byte plane elements (half-used 32-byte sectors): the honest number for long-running effects, unlike the
+    freshly filled slabs of the other rows."""
+    from tests.test_gpu_scene import _drifting_sparks
+    P = 16 << 20
+    ctx = hb.Context(0, stream.cuda_stream)
+    asset = _drifting_sparks(P)          # lifetimes U(0.2, 0.9) s
+    fx = asset.generate()
+    stride = fx.particle_stride
+    slab = ctx.slab_create(P, stride)
+    effect = ctx.effect_compile(fx)
+    ctx.metadata_insert(0, R.initial_metadata(P, 0, stride // 4))
+    ctx.draw_args_insert(0)
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+    dt, rate = 1 / 60, P // 40           # ~33 frames mean life -> the population settles around 0.8 P
+    for f in range(240):                 # 4 s of simulated time: every slot has been recycled several times
+        ctx.set_sim_params(dt, f * dt, 1)
+        ctx.upload_spawners([R.make_spawner(spawn=rate, seed=1000 + f)])
+        ctx.simulate([N.BatchLaunch.make(effect, slab, 0, rate)])
+    alive = ctx.read_metadata(0).alive_count
+    ind = ctx.slab_download_indirect(slab, 0, 1 << 16)
+    col = ctx.read_metadata(0).indirect_write_index
+    jumps = np.abs(np.diff(ind[:, col].astype(np.int64)))
+    la = [N.BatchLaunch.make(effect, slab, 0, rate)]
+    ctx.sync(); ctx.enable_kernel_timing(True); ctx.kernel_time_ms()
+    for f in range(240, 250):
+        ctx.set_sim_params(dt, f * dt, 1)
+        ctx.upload_spawners([R.make_spawner(spawn=rate, seed=1000 + f)])
+        ctx.simulate(la)
+    ms, k = ctx.kernel_time_ms()
+    ctx.enable_kernel_timing(False)
+    alive2 = ctx.read_metadata(0).alive_count
+    report(f"churn steady state: {alive2 >> 10} Ki of {P >> 10} Ki alive, stride {stride}", ms / k, (8 + 2 * stride) * alive2,
+           f"median |slot jump| between consecutive alive-list entries {np.median(jumps):.0f} (1 = identity order)")
+    ctx.close()
+
+
+SCENARIOS = {"churn": churn, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
