@@ -125,6 +125,8 @@ EFFECT_RELAXED_ORDER = 1 << 4
 EFFECT_RIBBONS = 1 << 5
 EFFECT_FAST_MATH = 1 << 6
 EFFECT_ORDERED_EVENTS = 1 << 7
+EFFECT_SECTOR_PLANES = 1 << 8
+SLAB_SECTOR_PLANES = 1 << 0
 
 
 def _load() -> C.CDLL:
@@ -149,6 +151,7 @@ SIGNATURES = {
     "hnb_ctx_stream": (C.c_size_t, [vp]),
     "hnb_ctx_launch_count": (C.c_uint64, [vp]),
     "hnb_slab_create": (i32, [vp, u32, u32, P(u32)]),
+    "hnb_slab_create_ex": (i32, [vp, u32, u32, u32, P(u32)]),
     "hnb_slab_destroy": (i32, [vp, u32]),
     "hnb_slab_reset_rows": (i32, [vp, u32, u32, u32]),
     "hnb_slab_upload_aos": (i32, [vp, u32, u32, u32, vp]),

@@ -82,7 +82,8 @@ namespace {
 struct Slab {
     bool live = false;
     uint32_t capacity = 0, stride = 0;
-    std::vector<Plane> planes;
+    bool sector_planes = false;  // HNB_SLAB_SECTOR_PLANES
+    std::vector<Plane> planes;   // physical columns
     void* d_planes[HNB_RT_MAX_PLANES] = {};
     uint32_t *ping = nullptr, *pong = nullptr, *dead = nullptr;
     // HNB_EFFECT_ORDERED_EVENTS scratch, allocated on first use: per channel the per-row event counts and their block sums
@@ -444,6 +445,8 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     lp.fx = &get_effect(c, bl.effect);
     lp.slab = &get_slab(c, bl.slab);
     if (lp.fx->particle_stride != lp.slab->stride) fail(HNB_ERR_LAYOUT, "effect particle stride does not match the slab");
+    if (((lp.fx->flags & HNB_EFFECT_SECTOR_PLANES) != 0) != lp.slab->sector_planes)
+        fail(HNB_ERR_LAYOUT, "effect and slab disagree on HNB_EFFECT_SECTOR_PLANES / HNB_SLAB_SECTOR_PLANES");
     if (bl.batch_info_index >= c->B) fail(HNB_ERR_OUT_OF_RANGE, "batch_info_index out of range");
     lp.batch = bl.batch_info_index;
     lp.total_spawn = bl.total_spawn_count;
@@ -506,7 +509,11 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     P.properties = lp.fx->d_props;
     P.properties_stride = lp.fx->props_stride;
     P.slab = slab_view(*lp.slab);
-    if (bl.parent_slab != 0xFFFFFFFFu) P.parent_slab = slab_view(get_slab(c, bl.parent_slab));
+    if (bl.parent_slab != 0xFFFFFFFFu) {
+        const Slab& parent = get_slab(c, bl.parent_slab);
+        if (parent.sector_planes) fail(HNB_ERR_LAYOUT, "a parent slab read by a child effect must use the default plane layout");
+        P.parent_slab = slab_view(parent);
+    }
     if (consume) P.consume_events = c->event_buffers[bl.consume_events].d;
     for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
         if (bl.emit_events[i] != 0xFFFFFFFFu) {
@@ -746,14 +753,18 @@ uintptr_t hnb_ctx_stream(hnb_ctx* c) { return (uintptr_t)c->stream; }
 uint64_t hnb_ctx_launch_count(hnb_ctx* c) { return c->launches; }
 
 // ---- slabs ----------------------------------------------------------------------------------
-int32_t hnb_slab_create(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, hnb_slab* out) {
+int32_t hnb_slab_create(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, hnb_slab* out) { return hnb_slab_create_ex(c, capacity_rows, stride, 0u, out); }
+
+int32_t hnb_slab_create_ex(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, uint32_t flags, hnb_slab* out) {
     return guarded([&] {
         if (!out || capacity_rows == 0) fail(HNB_ERR_INVALID_ARG, "bad slab arguments");
+        if (flags & ~uint32_t(HNB_SLAB_SECTOR_PLANES)) fail(HNB_ERR_INVALID_ARG, "unknown slab flags");
         CUDA_CHECK(cudaSetDevice(c->device));
         Slab s;
         s.capacity = capacity_rows;
         s.stride = stride;
-        s.planes = cut_planes(stride);
+        s.sector_planes = (flags & HNB_SLAB_SECTOR_PLANES) != 0;
+        s.planes = physical_planes(stride, s.sector_planes);
         for (size_t p = 0; p < s.planes.size(); ++p) {
             CUDA_CHECK(cudaMalloc(&s.d_planes[p], size_t(capacity_rows) * s.planes[p].width));
             // zero-filled (debug builds of the reference poison the particle buffer instead, effect_cache.rs:284-296)
@@ -868,6 +879,7 @@ int32_t hnb_slab_fill_c5(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count,
         Slab& s = get_slab(c, h);
         check_rows(s, first, count);
         if (s.stride != 32) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 needs the 32-byte {position,age,velocity,lifetime} layout");
+        if (s.sector_planes) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 writes the default plane layout; spawn through the init pass or use hnb_slab_upload_aos");
         CUDA_CHECK(hnb::launch_fill_c5(s.d_planes[0], s.d_planes[1], s.ping, s.pong, first, count, seed, lo, hi, c->stream));
         c->launches++;
     });

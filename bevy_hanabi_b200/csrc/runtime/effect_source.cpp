@@ -55,6 +55,24 @@ std::vector<Plane> cut_planes(uint32_t stride_bytes) {
     return planes;
 }
 
+// Physical columns of a slab. Default: one column per piece of cut_planes(). Sector planes (HNB_SLAB_SECTOR_PLANES): two
+// consecutive 16-byte pieces share one 32-byte-wide column, so that a gathered record piece pair is one full DRAM sector.
+std::vector<Plane> physical_planes(uint32_t stride_bytes, bool sector_planes) {
+    std::vector<Plane> pieces = cut_planes(stride_bytes);
+    if (!sector_planes) return pieces;
+    std::vector<Plane> out;
+    for (size_t p = 0; p < pieces.size();) {
+        if (p + 1 < pieces.size() && pieces[p].width == 16 && pieces[p + 1].width == 16) {
+            out.push_back({pieces[p].offset, 32});
+            p += 2;
+        } else {
+            out.push_back(pieces[p]);
+            p += 1;
+        }
+    }
+    return out;
+}
+
 namespace {
 
 const char* comp_name(int c) {
@@ -75,8 +93,22 @@ struct FieldRef {
     char kind;         // f,i,u
 };
 
+// physical column and element index of piece p of row `row` ("row" is the generated variable name)
+static std::string piece_address(const std::vector<Plane>& pieces, size_t p, bool sector) {
+    if (!sector) return "s.planes[" + std::to_string(p) + "], row";
+    size_t column = 0;
+    for (size_t q = 0; q < pieces.size();) {
+        const bool pair = q + 1 < pieces.size() && pieces[q].width == 16 && pieces[q + 1].width == 16;
+        if (pair && (p == q || p == q + 1)) return "s.planes[" + std::to_string(column) + "], 2u * row + " + std::to_string(p - q) + "u";
+        if (!pair && p == q) return "s.planes[" + std::to_string(column) + "], row";
+        q += pair ? 2 : 1;
+        ++column;
+    }
+    throw std::logic_error("piece_address");
+}
+
 void gen_layout_code(std::ostringstream& o, const char* prefix, const char* struct_name, const hnb_attr_layout* attrs,
-                     uint32_t n_attrs, uint32_t stride, bool with_store) {
+                     uint32_t n_attrs, uint32_t stride, bool with_store, bool sector = false) {
     auto planes = cut_planes(stride);
     // map AoS word -> field component
     std::vector<FieldRef> words(stride / 4);
@@ -117,14 +149,14 @@ void gen_layout_code(std::ostringstream& o, const char* prefix, const char* stru
     o << "HNB_DI void " << fn_prefix << "load_raw(" << raw_t << "& r, const SlabView& s, u32 row) {\n";
     for (size_t p = 0; p < planes.size(); ++p) {
         const char* t = planes[p].width == 16 ? "float4" : planes[p].width == 8 ? "float2" : "f32";
-        o << "    r.q" << p << " = HNB_LOAD_PLANE(" << t << ", s.planes[" << p << "], row);\n";
+        o << "    r.q" << p << " = HNB_LOAD_PLANE(" << t << ", " << piece_address(planes, p, sector) << ");\n";
     }
     o << "}\n";
     if (with_store) {
         o << "HNB_DI void " << fn_prefix << "store_raw(const " << raw_t << "& r, const SlabView& s, u32 row) {\n";
         for (size_t p = 0; p < planes.size(); ++p) {
             const char* t = planes[p].width == 16 ? "float4" : planes[p].width == 8 ? "float2" : "f32";
-            o << "    HNB_STORE_PLANE(" << t << ", s.planes[" << p << "], row, r.q" << p << ");\n";
+            o << "    HNB_STORE_PLANE(" << t << ", " << piece_address(planes, p, sector) << ", r.q" << p << ");\n";
         }
         o << "}\n";
     }
@@ -243,7 +275,7 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
          "#define HNB_STORE_PLANE(T, base, row, v) (((T*)(base))[row] = (v))\n"
          "#endif\n";
     // {{ATTRIBUTES}} / {{PROPERTIES}} / {{PARENT_ATTRIBUTES}}
-    gen_layout_code(o, "", "Particle", d.attrs, d.n_attrs, d.particle_stride, true);
+    gen_layout_code(o, "", "Particle", d.attrs, d.n_attrs, d.particle_stride, true, (d.flags & HNB_EFFECT_SECTOR_PLANES) != 0);
     if (read_parent) gen_layout_code(o, "Parent", "ParentParticle", d.parent_attrs, d.n_parent_attrs, d.parent_particle_stride, false);
     if (d.properties_size) {
         o << "struct Properties {\n" << nz(d.properties_struct) << "\n};\n";

@@ -27,6 +27,8 @@ struct Plane {
 // 4-byte tail. Because the reference layout keeps vec3/vec4 16-byte aligned and vec2 8-byte aligned
 // (attributes.rs:1516-1670) no attribute straddles two planes.
 std::vector<Plane> cut_planes(uint32_t stride_bytes);
+// Physical columns of a slab: the pieces themselves, or (sector planes) pairs of 16-byte pieces in 32-byte-wide columns.
+std::vector<Plane> physical_planes(uint32_t stride_bytes, bool sector_planes);
 
 // Update tiles are walked by one warp each: tile_rows = 32 lanes * k rows per lane * chunks. k is
 // chosen from the record size (register footprint) at compile time, the chunk count per launch.

@@ -222,9 +222,12 @@ class Context:
         return ms.value, n.value
 
     # -- slabs
-    def slab_create(self, capacity_rows: int, particle_stride: int) -> int:
+    def slab_create(self, capacity_rows: int, particle_stride: int, sector_planes: bool = False) -> int:
         out = N.u32(0)
-        check(lib.hnb_slab_create(self._h, capacity_rows, particle_stride, C.byref(out)))
+        if sector_planes:
+            check(lib.hnb_slab_create_ex(self._h, capacity_rows, particle_stride, N.SLAB_SECTOR_PLANES, C.byref(out)))
+        else:
+            check(lib.hnb_slab_create(self._h, capacity_rows, particle_stride, C.byref(out)))
         return out.value
 
     def slab_destroy(self, slab: int) -> None:

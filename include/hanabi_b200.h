@@ -173,6 +173,13 @@ typedef uint32_t hnb_slab;
  */
 HNB_API int32_t hnb_slab_create(hnb_ctx* ctx, uint32_t capacity_rows, uint32_t particle_stride_bytes,
                                 hnb_slab* out);
+/** Slab layout options. HNB_SLAB_SECTOR_PLANES: pairs of 16-byte record pieces share one 32-byte-wide column, so the
+ *  two pieces a gather reads are ONE full DRAM sector. For long-running effects whose alive list has become a permutation
+ *  of the slab (spawning into recycled slots) 16-byte-wide columns waste half of every sector; coalesced
+ *  access is unchanged. Effects for such a slab are compiled with HNB_EFFECT_SECTOR_PLANES. Experimental: validated under
+ *  the CPU kernel emulation, not yet measured on a GPU. */
+enum { HNB_SLAB_SECTOR_PLANES = 1u << 0 };
+HNB_API int32_t hnb_slab_create_ex(hnb_ctx* ctx, uint32_t capacity_rows, uint32_t particle_stride_bytes, uint32_t flags, hnb_slab* out);
 HNB_API int32_t hnb_slab_destroy(hnb_ctx* ctx, hnb_slab slab);
 /** Re-initialise dead[i]=i, ping=pong=0 for rows [first,first+count). */
 HNB_API int32_t hnb_slab_reset_rows(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count);
@@ -241,12 +248,13 @@ enum {
                                                   square root — the latitude a WGSL compiler has. fp32 results stay within
                                                   the 1e-5 relative bound but are no longer bit-identical to the oracle;
                                                   integer bookkeeping is unaffected. Pays off for ALU-bound effects. */
-    HNB_EFFECT_ORDERED_EVENTS = 1u << 7        /* with EMIT_GPU_SPAWN_EVENTS: events are appended after the update pass in
+    HNB_EFFECT_ORDERED_EVENTS = 1u << 7,       /* with EMIT_GPU_SPAWN_EVENTS: events are appended after the update pass in
                                                   the canonical (row) order instead of with per-particle atomics, so the
                                                   event buffer and what an overflow drops are deterministic (the
                                                   reference's order is scheduling-dependent, lib.rs:976-993). The batch must
                                                   hold one instance (parents of GPU-event children never merge). Costs
                                                   12 B of traffic per updated particle and channel. */
+    HNB_EFFECT_SECTOR_PLANES = 1u << 8         /* the effect addresses slabs created with HNB_SLAB_SECTOR_PLANES (must match) */
 };
 
 /**

@@ -251,7 +251,8 @@ class EmuWorld:
         self.tile = 32 * k * chunks
         self.update_ctas = update_ctas
         u32 = np.uint32
-        self.planes = [np.zeros(rows * 4, dtype=u32) for _ in range(16)]          # 16 B per row is the widest plane
+        self.planes = [np.zeros(rows * 8, dtype=u32) for _ in range(16)]          # room for 32-byte-wide (sector) columns
+        self.sector = bool(lowered.flags & (1 << 8))                               # HNB_EFFECT_SECTOR_PLANES
         self.cols = [np.ascontiguousarray(ref.indirect[:, c]).copy() for c in range(3)]
         self.metadata = (O.EffectMetadata * n).from_buffer_copy(bytes(ref.metadata))
         self.spawners = (O.Spawner * n).from_buffer_copy(bytes(ref.spawners))
@@ -355,13 +356,16 @@ class EmuWorld:
         lib.semu_prefix_sum(C.byref(self._static_tables()), 1)
         a = RibbonSortArgs()
         words = self.stride // 4
-        for pl in range((words + 3) // 4):
-            w = min(4, words - 4 * pl)
-            # plane widths follow the record: 16-byte planes, then an 8- or 4-byte tail (cut_planes)
-            a.planes.ptr[pl], a.planes.words[pl], a.planes.word_off[pl] = self.planes[pl].ctypes.data, (4 if w >= 4 else (2 if w >= 2 else 1)), 4 * pl
-            for k in range(w):
-                a.planes.word_to_plane[4 * pl + k] = pl
-        assert words % 4 == 0, "EmuWorld ribbon sort supports strides that are multiples of 16 bytes"
+        assert words % 4 == 0, "effect records are multiples of 16 bytes"
+        pieces = words // 4
+        col, p = 0, 0
+        while p < pieces:                         # physical columns (effect_source.cpp::physical_planes)
+            width = 8 if (self.sector and p + 1 < pieces) else 4
+            a.planes.ptr[col], a.planes.words[col], a.planes.word_off[col] = self.planes[col].ctypes.data, width, 4 * p
+            for k in range(width):
+                a.planes.word_to_plane[4 * p + k] = col
+            p += width // 4
+            col += 1
         a.ping, a.pong, a.spawners, a.metadata = self.cols[0].ctypes.data, self.cols[1].ctypes.data, C.addressof(self.spawners), C.addressof(self.metadata)
         a.spawner_base, a.instance_count = 0, self.n
         grid = 2

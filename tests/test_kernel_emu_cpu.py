@@ -526,3 +526,43 @@ def test_random_event_scenes(orc, ordered, seed):
             np.testing.assert_array_equal(got["metadata"], want_md, err_msg=f"frame {f} member {b}: metadata")
             np.testing.assert_array_equal(got["indirect"], world.indirect, err_msg=f"frame {f} member {b}: lists")
             np.testing.assert_array_equal(got["particles"], world.particles, err_msg=f"frame {f} member {b}: particles")
+
+
+@pytest.mark.parametrize("name", ["c5", "trails", "ribbons", "wide"])
+def test_sector_plane_layout(orc, name):
+    """HNB_SLAB_SECTOR_PLANES / HNB_EFFECT_SECTOR_PLANES: pairs of 16-byte record pieces in 32-byte-wide columns (one
+    DRAM sector per gathered pair). Same results as the default layout, through init, update and the ribbon sort."""
+    from tests import static_emu
+    from tests.test_gpu_ribbons import _ribbon_asset
+    if name == "c5":
+        asset = recipes.c5_asset(2000)
+    elif name == "trails":
+        asset = _firework_trails(2000)          # 48 bytes: one sector column + one 16-byte column
+    elif name == "ribbons":
+        asset = _ribbon_asset(2000)
+    else:
+        w = G.ExprWriter()
+        asset = (G.EffectAsset(2000, w.module, name="wide_sector")
+                 .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3)))
+                 .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) - w.lit(0.5)))
+                 .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+                 .init(G.SetAttributeModifier(A.LIFETIME, w.lit(0.2).uniform(w.lit(0.6))))
+                 .init(G.SetAttributeModifier(A.F32X4_0, w.rand(G.VEC4)))
+                 .init(G.SetAttributeModifier(A.HDR_COLOR, w.rand(G.VEC4)))
+                 .update(G.SetAttributeModifier(A.F32X4_1, w.attr(A.F32X4_0) + w.attr(A.HDR_COLOR) * w.attr(A.F32X4_1)))
+                 .update(G.SetAttributeModifier(A.F32X3_0, w.attr(A.VELOCITY).cross(w.attr(A.POSITION)))))
+    fields, size, _ = asset.particle_layout()
+    fx = asset.generate(sector_planes=True)
+    ref = RefWorld(2000, size // 4, [Instance(0, 2000, alive=0, seed=4)], dt=1 / 10)
+    if name == "ribbons":
+        ref.set_sort_keys(fields)
+    eo = EffectOracle(asset)
+    emu = EmuWorld(ref, fx, chunks=1, update_ctas=2, static_lib=static_emu.build())
+    assert emu.sector
+    for f in range(6):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn, seed = [900 if f % 3 == 0 else 40], [int(pcg_hash(np.array([f + 300], dtype=np.uint32))[0])]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        _assert_same(ref, emu.pull(), f"{name} (stride {size}) frame {f}")

@@ -6,4 +6,4 @@ mkdir -p gpurun_out;
 python -m pytest tests/pending/gpu_ordered_events.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/pending_ordered_events.txt;
 timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/gpu_suite.txt;
 timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json;
-timeout 900 python tools/perf_matrix.py 2>&1 | tee gpurun_out/perf_matrix.txt | tail -25;
+timeout 1200 python tools/perf_matrix.py 2>&1 | tee gpurun_out/perf_matrix.txt | tail -30;

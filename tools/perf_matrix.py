@@ -120,11 +120,11 @@ def c4_topology():
     ctx.close()
 
 
-def _burst(name, asset, P, spawn, props=None, steps=10, fast_math=False):
+def _burst(name, asset, P, spawn, props=None, steps=10, fast_math=False, sector_planes=False):
     ctx = hb.Context(0, stream.cuda_stream)
-    fx = asset.generate(fast_math=fast_math)
+    fx = asset.generate(fast_math=fast_math, sector_planes=sector_planes)
     stride = fx.particle_stride
-    slab = ctx.slab_create(P, stride)
+    slab = ctx.slab_create(P, stride, sector_planes=sector_planes)
     effect = ctx.effect_compile(fx)
     if props is not None:
         ctx.upload_properties(effect, 0, props)
@@ -212,7 +212,7 @@ def many_batches():
         ctx.close()
 
 
-def churn():
+def churn(sector_planes: bool = False):
     """Steady-state churn: constant spawn rate into recycled slots until the alive list is a random-looking permutation
     of the slab (survivors keep their relative order, new particles land in whatever slots died). The gathers then touch
     scattered 16-byte plane elements (half-used 32-byte sectors): the honest number for long-running effects, unlike the
@@ -221,9 +221,9 @@ def churn():
     P = 16 << 20
     ctx = hb.Context(0, stream.cuda_stream)
     asset = _drifting_sparks(P)          # lifetimes U(0.2, 0.9) s
-    fx = asset.generate()
+    fx = asset.generate(sector_planes=sector_planes)
     stride = fx.particle_stride
-    slab = ctx.slab_create(P, stride)
+    slab = ctx.slab_create(P, stride, sector_planes=sector_planes)
     effect = ctx.effect_compile(fx)
     ctx.metadata_insert(0, R.initial_metadata(P, 0, stride // 4))
     ctx.draw_args_insert(0)
@@ -246,12 +246,30 @@ def churn():
     ms, k = ctx.kernel_time_ms()
     ctx.enable_kernel_timing(False)
     alive2 = ctx.read_metadata(0).alive_count
-    report(f"churn steady state: {alive2 >> 10} Ki of {P >> 10} Ki alive, stride {stride}", ms / k, (8 + 2 * stride) * alive2,
+    report(f"churn steady state{' (sector planes)' if sector_planes else ''}: {alive2 >> 10} Ki of {P >> 10} Ki alive, stride {stride}", ms / k, (8 + 2 * stride) * alive2,
            f"median |slot jump| between consecutive alive-list entries {np.median(jumps):.0f} (1 = identity order)")
     ctx.close()
 
 
-SCENARIOS = {"churn": churn, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
+def churn_sector():
+    """The same with HNB_SLAB_SECTOR_PLANES (32-byte-wide columns): one full sector per gathered record."""
+    churn(sector_planes=True)
+
+
+def fresh_sector():
+    """Cost of sector planes when access IS coalesced: C5 recipe burst + update, like `c5_init`, on a sector slab."""
+    w = G.ExprWriter()
+    asset = (G.EffectAsset(64 << 20, w.module, name="c5_spawned_sector")
+             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(2.) - w.lit(1.)))
+             .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) * w.lit(2.) - w.lit(1.)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+             .init(G.SetAttributeModifier(A.LIFETIME, w.lit(1e9)))
+             .update(G.AccelModifier(w.lit(G.Vec3(0., -9.8, 0.))))
+             .update(G.LinearDragModifier(w.lit(0.5))))
+    _burst("C5 recipe on SECTOR planes, 32Mi burst", asset, 64 << 20, 32 << 20, sector_planes=True)
+
+
+SCENARIOS = {"churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
