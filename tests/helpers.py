@@ -175,7 +175,7 @@ class RefWorld:
 class GpuWorld:
     """The same world on the GPU backend, driven through the C ABI only."""
 
-    def __init__(self, ctx, ref: RefWorld, lowered_effect, property_blobs=None, effect=None):
+    def __init__(self, ctx, ref: RefWorld, lowered_effect, property_blobs=None, effect=None, sector_planes=False):
         """`property_blobs`: list (per instance) of serialized Properties records, uploaded at array index =
         instance index; the metadata rows of `ref` must carry the same properties_array_index."""
         import bevy_hanabi_b200._native as N
@@ -184,7 +184,7 @@ class GpuWorld:
         self.ctx = ctx
         self.ref = ref
         self.stride = ref.stride_words * 4
-        self.slab = ctx.slab_create(ref.slab_rows, self.stride)
+        self.slab = ctx.slab_create(ref.slab_rows, self.stride, sector_planes=sector_planes)
         self.effect = effect if effect is not None else ctx.effect_compile(lowered_effect)  # `effect`: an already registered handle
         for i, blob in enumerate(property_blobs or []):
             ctx.upload_properties(self.effect, i, blob)
