@@ -428,3 +428,35 @@ def test_background_compile_job():
         job.poll()
     for j in jobs + [job]:
         j.close()
+
+
+def test_value_bytes_and_text_reference_vectors():
+    """graph/mod.rs `as_bytes` (:1709-1760) and `to_wgsl_string` (:1905-1977): the byte images of scalar / vector values
+    (through the property serialiser, which is where values become bytes on this path) and the literal text of the
+    same inputs the reference formats (C literals here: the reference's text plus the `f` suffix)."""
+    for value, fmt, expect in [
+        (3.0, "<f", bytes([0, 0, 0x40, 0x40])),
+        (G.U32(0x12FF89AC), "<I", bytes([0xAC, 0x89, 0xFF, 0x12])),
+        (G.I32(0x12FF89AC), "<i", bytes([0xAC, 0x89, 0xFF, 0x12])),
+        (G.Vec2(-2., 3.), "<2f", bytes([0, 0, 0, 0xC0, 0, 0, 0x40, 0x40])),
+        (G.Vec3(-2., 3., 4.), "<3f", bytes([0, 0, 0, 0xC0, 0, 0, 0x40, 0x40, 0, 0, 0x80, 0x40])),
+        (G.Vec4(-2., 3., 4., -5.), "<4f", bytes([0, 0, 0, 0xC0, 0, 0, 0x40, 0x40, 0, 0, 0x80, 0x40, 0, 0, 0xA0, 0xC0])),
+    ]:
+        blob = _asset_with_props([("v", value)]).serialize_properties({})
+        assert blob[:len(expect)] == expect, (value, blob.hex())
+        assert not any(blob[len(expect):])                      # the tail of the binding is zero padding
+
+    m = G.Module()
+    text = lambda v: m.eval(m.lit(v))[0]
+    assert [G.format_f32(f) for f in (0., -1., 1., 1e-5)] == ["0.f", "-1.f", "1.f", "0.00001f"]
+    assert [text(G.U32(u)) for u in (0, 1, 42, 999999)] == ["0u", "1u", "42u", "999999u"]
+    assert [text(G.I32(i)) for i in (0, -1, 1, -42, 42, -100000, 100000)] == ["0", "-1", "1", "-42", "42", "-100000", "100000"]
+    assert text(True) == "true" and text(False) == "false"
+    assert text(G.Vec2(0., 0.)) == "vec2<f32>(0.f,0.f)" and text(G.Vec2(-1., -1.)) == "vec2<f32>(-1.f,-1.f)"
+    assert text(G.Vec3(0., 0., -1.)) == "vec3<f32>(0.f,0.f,-1.f)"
+    # f32(-42.578) = -42.57799911…, f32(663.449) = 663.44897460…, f32(-42558.35) = -42558.3515625 (a tie: both Rust
+    # and glibc round it to even), f32(-4.2) = -4.19999980…: six decimals, trailing zeros trimmed
+    assert text(G.Vec4(-42.578, 663.449, -42558.35, -4.2)) == "vec4<f32>(-42.577999f,663.448975f,-42558.351562f,-4.2f)"
+    # magnitudes the reference prints in full ("{:.6}" never switches to an exponent)
+    assert G.format_f32(1e20) == "100000002004087734272.f" and G.format_f32(100.0) == "100.f"
+    assert G.format_f32(-0.0) == "-0.f" and G.format_f32(5.1e-7) == "0.000001f"
