@@ -62,7 +62,7 @@ Attribute attr_or_throw(const char* name) {
 }
 Value value_from(uint32_t vt, const uint32_t* words) {
     ValueType t(vt);
-    if (vt > HNB_MAT4) throw ExprError(ExprError::TypeError, "invalid value type");
+    if (vt > HNB_MAT4X3) throw ExprError(ExprError::TypeError, "invalid value type");
     if (!words) throw ExprError(ExprError::TypeError, "NULL literal data");
     Value v = Value::from_words(t, words);
     if (t.elem() == ScalarType::Bool)

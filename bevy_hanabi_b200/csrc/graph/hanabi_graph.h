@@ -39,13 +39,17 @@ struct ValueType {
     static ValueType scalar(ScalarType s) { return ValueType((uint32_t)s); }
     static ValueType vector(ScalarType s, int count);
     static ValueType matrix(int n) { return ValueType(16u + (uint32_t)(n - 2)); }
+    static ValueType matrix(int cols, int rows);  // matCxR<f32>, MatrixType::new(cols, rows) (attributes.rs:358-362)
     bool is_scalar() const { return code < 4; }
     bool is_vector() const { return code >= 4 && code < 16; }
     bool is_matrix() const { return code >= 16; }
+    bool is_valid() const { return code <= 24; }
     ScalarType elem() const;
-    int count() const;              // number of 32-bit components (matrix: n*n)
-    uint32_t size() const { return 4u * (uint32_t)count(); }
-    uint32_t align() const;         // WGSL rules: vec2 8, vec3/vec4 16, scalar 4
+    int cols() const;               // matrices only
+    int rows() const;
+    int count() const;              // number of 32-bit components (matrix: cols*rows, packed column-major)
+    uint32_t size() const;          // WGSL rules; a matrix is array<vecR, C>: matCx3 and matCx4 have the same size (attributes.rs:377-386)
+    uint32_t align() const;         // WGSL rules: vec2 8, vec3/vec4 16, scalar 4, matrix = AlignOf(vecR)
     std::string to_cuda_string() const;  // "f32", "vec3<f32>", ...
     bool operator==(const ValueType& o) const { return code == o.code; }
     bool operator!=(const ValueType& o) const { return code != o.code; }

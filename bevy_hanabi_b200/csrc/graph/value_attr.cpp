@@ -29,16 +29,30 @@ ScalarType ValueType::elem() const {
     if (code < 16) return ScalarType::Uint;
     return ScalarType::Float;
 }
+// Matrix codes: 16..18 = mat2x2, mat3x3, mat4x4; 19..24 = mat2x3, mat2x4, mat3x2, mat3x4, mat4x2, mat4x3 (CxR).
+static const uint8_t kMatCols[9] = {2, 3, 4, 2, 2, 3, 3, 4, 4};
+static const uint8_t kMatRows[9] = {2, 3, 4, 3, 4, 2, 4, 2, 3};
+ValueType ValueType::matrix(int cols, int rows) {
+    if (cols < 2 || cols > 4 || rows < 2 || rows > 4) throw ExprError(ExprError::TypeError, "invalid matrix size");
+    for (uint32_t i = 0; i < 9; ++i)
+        if (kMatCols[i] == cols && kMatRows[i] == rows) return ValueType(16u + i);
+    return ValueType(16u);
+}
+int ValueType::cols() const { return is_matrix() && is_valid() ? kMatCols[code - 16] : 1; }
+int ValueType::rows() const { return is_matrix() && is_valid() ? kMatRows[code - 16] : count(); }
 int ValueType::count() const {
     if (code < 4) return 1;
     if (code < 16) return 2 + (int)((code - 4) % 3);
-    int n = 2 + (int)(code - 16);
-    return n * n;
+    return cols() * (is_valid() ? kMatRows[code - 16] : 1);
+}
+uint32_t ValueType::size() const {
+    if (!is_matrix()) return 4u * (uint32_t)count();
+    return (uint32_t)cols() * (rows() >= 3 ? 16u : 8u);
 }
 uint32_t ValueType::align() const {
     if (is_scalar()) return 4;
     if (is_vector()) return count() == 2 ? 8 : 16;
-    return code == 16 ? 8 : 16;
+    return rows() == 2 ? 8 : 16;
 }
 static const char* scalar_name(ScalarType s) {
     switch (s) {
@@ -51,8 +65,7 @@ static const char* scalar_name(ScalarType s) {
 std::string ValueType::to_cuda_string() const {
     if (is_scalar()) return scalar_name(elem());
     if (is_vector()) return "vec" + std::to_string(count()) + "<" + scalar_name(elem()) + ">";
-    int n = 2 + (int)(code - 16);
-    return "mat" + std::to_string(n) + "x" + std::to_string(n) + "f";
+    return "mat" + std::to_string(cols()) + "x" + std::to_string(rows()) + "f";
 }
 
 // ---- Value --------------------------------------------------------------------------------------
@@ -99,7 +112,7 @@ static std::string scalar_to_string(ScalarType t, uint32_t bits) {
 
 std::string Value::to_cuda_string() const {
     if (type.is_scalar()) return scalar_to_string(type.elem(), bits[0]);
-    if (type.is_matrix()) throw ExprError(ExprError::TypeError, "matrix literals are not supported by the CUDA backend");
+    // matrices: every component in storage order = column by column (MatrixValue::to_wgsl_string, graph/mod.rs:1428-1441)
     std::string s = type.to_cuda_string() + "(";
     for (int i = 0; i < type.count(); ++i) {
         if (i) s += ",";
@@ -337,6 +350,11 @@ std::string PropertyLayout::generate_struct_body() const {
     uint32_t cursor = 0;
     int pad = 0;
     for (const auto& e : layout) {
+        // PropertyLayout::new advances by 16 bytes after every property of 16 bytes or more (properties.rs:572-580):
+        // a matrix larger than that is only laid out consistently when nothing follows it. The reference would
+        // silently overlap the next field; refuse instead.
+        if (cursor > e.offset)
+            throw ExprError(ExprError::Validate, "property '" + e.property.name + "' overlaps the matrix property before it (the reference's property layout only holds a matrix larger than 16 bytes as its last entry: the largest property, with no scalar, vec2 or vec3 property beside it)");
         while (cursor < e.offset) { s += "    u32 _hnb_pad" + std::to_string(pad++) + ";\n"; cursor += 4; }
         ValueType t = e.property.default_value.type;
         if (t.elem() == ScalarType::Bool) {

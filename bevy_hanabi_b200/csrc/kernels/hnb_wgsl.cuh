@@ -241,17 +241,100 @@ HNB_DI vec4f unpack4x8snorm(u32 p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4x4 matrix, column-major like WGSL mat4x4<f32>. Only what the modifiers need: construction from
-// the spawner rows, m * vec4, column access.
+// Matrices matCxR<f32>: C columns of R rows, column-major like WGSL, with WGSL's memory layout
+// (array<vecR, C>: a vec3 column occupies 16 bytes) so that a matrix can sit in the Properties struct.
+// Generated code builds them from C*R scalars (MatrixValue::to_wgsl_string, reference
+// src/graph/mod.rs:1428-1441) and combines them with the WGSL arithmetic operators: m + m, m - m,
+// m * s, s * m, m * v (vecC -> vecR), v * m (vecR -> vecC), m * m. Sums run over the columns from
+// left to right, one rounding per operation.
 // ---------------------------------------------------------------------------------------------
-struct mat4x4f {
+template <int R> struct hnb_col;
+template <> struct hnb_col<2> { typedef vec2f vec; vec2f v; };
+template <> struct hnb_col<3> { typedef vec3f vec; vec3f v; f32 _pad; };
+template <> struct hnb_col<4> { typedef vec4f vec; vec4f v; };
+
+template <int C, int R> struct hnb_mat {
+    typedef typename hnb_col<R>::vec col_t;
+    hnb_col<R> c[C];
+    HNB_DI hnb_mat() {}
+    template <typename... A> HNB_DI explicit hnb_mat(f32 e0, A... rest) {
+        static_assert(sizeof...(A) + 1 == C * R, "a matCxR literal takes C*R scalars");
+        const f32 e[C * R] = {e0, f32(rest)...};
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+#pragma unroll
+            for (int i = 0; i < R; ++i) c[j].v[i] = e[j * R + i];
+    }
+    HNB_DI col_t& operator[](int j) { return c[j].v; }
+    HNB_DI const col_t& operator[](int j) const { return c[j].v; }
+};
+// The 4x4 case keeps bare vec4 columns: the kernel templates build the spawner transforms through `c[]`.
+template <> struct hnb_mat<4, 4> {
+    typedef vec4f col_t;
     vec4f c[4];
+    HNB_DI hnb_mat() {}
+    HNB_DI hnb_mat(f32 e0, f32 e1, f32 e2, f32 e3, f32 e4, f32 e5, f32 e6, f32 e7, f32 e8, f32 e9, f32 e10, f32 e11, f32 e12, f32 e13,
+                   f32 e14, f32 e15) {
+        c[0] = vec4f(e0, e1, e2, e3);
+        c[1] = vec4f(e4, e5, e6, e7);
+        c[2] = vec4f(e8, e9, e10, e11);
+        c[3] = vec4f(e12, e13, e14, e15);
+    }
     HNB_DI vec4f& operator[](int i) { return c[i]; }
     HNB_DI const vec4f& operator[](int i) const { return c[i]; }
 };
+typedef hnb_mat<2, 2> mat2x2f; typedef hnb_mat<2, 3> mat2x3f; typedef hnb_mat<2, 4> mat2x4f;
+typedef hnb_mat<3, 2> mat3x2f; typedef hnb_mat<3, 3> mat3x3f; typedef hnb_mat<3, 4> mat3x4f;
+typedef hnb_mat<4, 2> mat4x2f; typedef hnb_mat<4, 3> mat4x3f; typedef hnb_mat<4, 4> mat4x4f;
+static_assert(sizeof(mat2x2f) == 16 && sizeof(mat3x2f) == 24 && sizeof(mat4x2f) == 32, "matCx2: 8-byte columns");
+static_assert(sizeof(mat2x3f) == 32 && sizeof(mat3x3f) == 48 && sizeof(mat4x3f) == 64, "matCx3: 16-byte columns");
+static_assert(sizeof(mat2x4f) == 32 && sizeof(mat3x4f) == 48 && sizeof(mat4x4f) == 64, "matCx4: 16-byte columns");
+
 HNB_DI vec4f operator*(const mat4x4f& m, const vec4f& v) {
     // WGSL: sum over columns, accumulated left to right
     return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z + m.c[3] * v.w;
+}
+template <int C, int R> HNB_DI typename hnb_col<R>::vec operator*(const hnb_mat<C, R>& m, const typename hnb_col<C>::vec& v) {
+    typename hnb_col<R>::vec acc = m[0] * v[0];
+#pragma unroll
+    for (int j = 1; j < C; ++j) acc = acc + m[j] * v[j];
+    return acc;
+}
+template <int C, int R> HNB_DI typename hnb_col<C>::vec operator*(const typename hnb_col<R>::vec& v, const hnb_mat<C, R>& m) {
+    typename hnb_col<C>::vec r;
+#pragma unroll
+    for (int j = 0; j < C; ++j) r[j] = dot(v, m[j]);
+    return r;
+}
+template <int K, int R, int C> HNB_DI hnb_mat<C, R> operator*(const hnb_mat<K, R>& a, const hnb_mat<C, K>& b) {
+    hnb_mat<C, R> r;
+#pragma unroll
+    for (int j = 0; j < C; ++j) r[j] = a * b[j];
+    return r;
+}
+template <int C, int R> HNB_DI hnb_mat<C, R> operator*(const hnb_mat<C, R>& a, f32 s) {
+    hnb_mat<C, R> r;
+#pragma unroll
+    for (int j = 0; j < C; ++j) r[j] = a[j] * s;
+    return r;
+}
+template <int C, int R> HNB_DI hnb_mat<C, R> operator*(f32 s, const hnb_mat<C, R>& a) {
+    hnb_mat<C, R> r;
+#pragma unroll
+    for (int j = 0; j < C; ++j) r[j] = s * a[j];
+    return r;
+}
+template <int C, int R> HNB_DI hnb_mat<C, R> operator+(const hnb_mat<C, R>& a, const hnb_mat<C, R>& b) {
+    hnb_mat<C, R> r;
+#pragma unroll
+    for (int j = 0; j < C; ++j) r[j] = a[j] + b[j];
+    return r;
+}
+template <int C, int R> HNB_DI hnb_mat<C, R> operator-(const hnb_mat<C, R>& a, const hnb_mat<C, R>& b) {
+    hnb_mat<C, R> r;
+#pragma unroll
+    for (int j = 0; j < C; ++j) r[j] = a[j] - b[j];
+    return r;
 }
 // transpose(mat4x4(row0,row1,row2,(0,0,0,1))) as built in vfx_init.wgsl:157-164
 HNB_DI mat4x4f hnb_transform_from_rows(const f32* r0, const f32* r1, const f32* r2) {

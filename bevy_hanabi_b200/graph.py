@@ -65,7 +65,33 @@ VEC2, VEC3, VEC4 = N.VEC2, N.VEC3, N.VEC4
 _ELEM = {0: "b", 1: "f", 2: "i", 3: "u"}
 
 
+# matCxR<f32> codes (hnb_value_type): (columns, rows)
+_MAT_DIMS = {16: (2, 2), 17: (3, 3), 18: (4, 4), 19: (2, 3), 20: (2, 4), 21: (3, 2), 22: (3, 4), 23: (4, 2), 24: (4, 3)}
+MAT2, MAT3, MAT4 = 16, 17, 18
+
+
+def vt_is_matrix(vt: int) -> bool:
+    return vt >= 16
+
+
+def vt_matrix_dims(vt: int) -> tuple:
+    """(columns, rows) of a matrix type."""
+    return _MAT_DIMS[vt]
+
+
+def vt_matrix(cols: int, rows: int) -> int:
+    """MatrixType::new(cols, rows) (reference src/attributes.rs:358-362)."""
+    for vt, d in _MAT_DIMS.items():
+        if d == (cols, rows):
+            return vt
+    raise ValueError("matrix sizes are 2..4 columns by 2..4 rows")
+
+
 def vt_count(vt: int) -> int:
+    """Number of 32-bit lanes of a value (matrix: columns x rows, stored column by column)."""
+    if vt >= 16:
+        c, r = _MAT_DIMS[vt]
+        return c * r
     return 1 if vt < 4 else 2 + (vt - 4) % 3
 
 
@@ -73,6 +99,8 @@ def vt_elem(vt: int) -> str:
     """'b', 'f', 'i' or 'u'"""
     if vt < 4:
         return _ELEM[vt]
+    if vt >= 16:
+        return "f"
     return "bfiu"[(vt - 4) // 3]
 
 
@@ -138,6 +166,35 @@ def Vec3(x, y, z) -> Value:
 
 def Vec4(x, y, z, w) -> Value:
     return Value.of((float(x), float(y), float(z), float(w)))
+
+
+def Mat(cols: int, rows: int, data) -> Value:
+    """MatrixValue::new(cols, rows, data) (reference src/graph/mod.rs:1283-1311): ``data`` holds cols*rows floats,
+    column by column."""
+    data = [float(x) for x in data]
+    if len(data) != cols * rows:
+        raise ValueError(f"a mat{cols}x{rows} takes {cols * rows} values")
+    return Value(vt_matrix(cols, rows), tuple(_f32_bits(x) for x in data))
+
+
+def Mat2(*cols_) -> Value:
+    """From two columns (glam `Mat2::from_cols`) or four floats in column-major order."""
+    return Mat(2, 2, _flatten(cols_))
+
+
+def Mat3(*cols_) -> Value:
+    return Mat(3, 3, _flatten(cols_))
+
+
+def Mat4(*cols_) -> Value:
+    return Mat(4, 4, _flatten(cols_))
+
+
+def _flatten(xs):
+    out = []
+    for x in xs:
+        out.extend(x if isinstance(x, (tuple, list)) else [x])
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -225,7 +225,9 @@ typedef enum hnb_value_type {
     HNB_VEC2 = 7, HNB_VEC3 = 8, HNB_VEC4 = 9,
     HNB_IVEC2 = 10, HNB_IVEC3 = 11, HNB_IVEC4 = 12,
     HNB_UVEC2 = 13, HNB_UVEC3 = 14, HNB_UVEC4 = 15,
-    HNB_MAT2 = 16, HNB_MAT3 = 17, HNB_MAT4 = 18 /* square float matrices only in this build */
+    /* float matrices matCxR<f32> (C columns of R rows; values are C*R words, column by column) */
+    HNB_MAT2 = 16, HNB_MAT3 = 17, HNB_MAT4 = 18,
+    HNB_MAT2X3 = 19, HNB_MAT2X4 = 20, HNB_MAT3X2 = 21, HNB_MAT3X4 = 22, HNB_MAT4X2 = 23, HNB_MAT4X3 = 24
 } hnb_value_type;
 
 /** One field of the reference's AoS `Particle` record (ParticleLayout, attributes.rs:1807-1913). */

@@ -42,10 +42,13 @@ enum { HNB_TER_MIX = 0, HNB_TER_CLAMP, HNB_TER_SMOOTHSTEP, HNB_TER_VEC3 };
 /* ---- Module --------------------------------------------------------------------------------- */
 HNB_API hnb_module* hnb_module_create(void);
 HNB_API void hnb_module_destroy(hnb_module* m);
-/** Literal of `value_type` (hnb_value_type); `words` holds its 32-bit lanes (bools: 0 / non-zero). */
+/** Literal of `value_type` (hnb_value_type); `words` holds its 32-bit lanes (bools: 0 / non-zero; a matCxR: C*R floats,
+ *  column by column, like MatrixValue::new in the reference's src/graph/mod.rs:1283-1311). */
 HNB_API hnb_expr hnb_module_lit(hnb_module* m, uint32_t value_type, const uint32_t* words);
 HNB_API hnb_expr hnb_module_attr(hnb_module* m, const char* attribute_name);
 HNB_API hnb_expr hnb_module_parent_attr(hnb_module* m, const char* attribute_name);
+/** A matrix property larger than 16 bytes must end up as the last entry of the property layout (the reference's
+ *  PropertyLayout::new, properties.rs:561-699, cannot place anything after it); hnb_asset_generate reports a violation. */
 HNB_API hnb_prop hnb_module_add_property(hnb_module* m, const char* name, uint32_t value_type, const uint32_t* default_words);
 HNB_API hnb_expr hnb_module_prop(hnb_module* m, hnb_prop property);
 /** `rand_value_type` is only read for HNB_BUILTIN_RAND. */

@@ -150,12 +150,39 @@ def _trunc_rem(a, b):
 _DT = {"f": F32, "u": U32, "i": np.int32, "b": np.bool_}
 
 
+# matCxR<f32> value-type codes -> (columns, rows) (MatrixType, reference src/attributes.rs:322-397)
+_MAT_DIMS = {16: (2, 2), 17: (3, 3), 18: (4, 4), 19: (2, 3), 20: (2, 4), 21: (3, 2), 22: (3, 4), 23: (4, 2), 24: (4, 3)}
+
+
 def _vt_elem(vt):
+    if vt >= 16:
+        return "f"
     return "bfiu"[vt] if vt < 4 else "bfiu"[(vt - 4) // 3]
 
 
 def _vt_count(vt):
+    if vt >= 16:
+        return _MAT_DIMS[vt][0] * _MAT_DIMS[vt][1]
     return 1 if vt < 4 else 2 + (vt - 4) % 3
+
+
+def _matrix_array(value, a, n, as_shader_text):
+    """A matrix value as an (n, C, R) array of columns.
+
+    A literal is the C*R components in storage order = column by column (MatrixValue::to_wgsl_string, reference
+    src/graph/mod.rs:1428-1441). A PROPERTY is uploaded as MatrixValue::as_bytes (graph/mod.rs:1387-1391): the first
+    C*AlignOf(vecR)/4 floats of that PACKED storage, which the shader then reads as array<vecR, C> — with a 16-byte
+    column stride when R = 3. For three-row matrices the two disagree, so the shader sees columns (s0 s1 s2),
+    (s4 s5 s6), (s8 s9 s10) ... of the packed storage s; that is the reference's behaviour and what is restated here."""
+    c, r = _MAT_DIMS[value.vt]
+    if as_shader_text:
+        m = a.reshape(c, r)
+    else:
+        stride = 2 if r == 2 else 4
+        s = np.zeros(16, dtype=F32)
+        s[:c * r] = a
+        m = s[:c * stride].reshape(c, stride)[:, :r]
+    return np.broadcast_to(m[None, :, :], (n, c, r)).copy()
 
 
 def literal_array(value, n, as_shader_text=True):
@@ -175,6 +202,8 @@ def literal_array(value, n, as_shader_text=True):
         a = w != 0
     else:
         a = w
+    if value.vt >= 16:
+        return _matrix_array(value, a, n, as_shader_text)
     if cnt == 1:
         return np.broadcast_to(a[0], (n,)).copy()
     return np.broadcast_to(a[None, :], (n, cnt)).copy()
@@ -318,7 +347,29 @@ def _unary(op, a):
     raise ValueError(op)
 
 
+def _matrix_mul(a, b):
+    """WGSL `*` with a matrix operand ((n, C, R) arrays of columns); sums run over the columns from left to right."""
+    if a.ndim == 3 and b.ndim == 1:
+        return a * b[:, None, None]
+    if a.ndim == 1 and b.ndim == 3:
+        return a[:, None, None] * b
+    if a.ndim == 3 and b.ndim == 2:                      # matCxR * vecC -> vecR
+        acc = a[:, 0, :] * b[:, 0:1]
+        for j in range(1, a.shape[1]):
+            acc = acc + a[:, j, :] * b[:, j:j + 1]
+        return acc
+    if a.ndim == 2 and b.ndim == 3:                      # vecR * matCxR -> vecC
+        return np.stack([dot(a, b[:, j, :]) for j in range(b.shape[1])], axis=1)
+    return np.stack([_matrix_mul(a, b[:, j, :]) for j in range(b.shape[1])], axis=1)   # matKxR * matCxK -> matCxR
+
+
 def _binary(op, a, b):
+    if a.ndim == 3 or b.ndim == 3:
+        if op == "mul":
+            return _matrix_mul(a, b)
+        if op in ("add", "sub") and a.shape == b.shape:
+            return a + b if op == "add" else a - b
+        raise ValueError(f"operator '{op}' is not defined for matrices")
     if op in ("add", "sub", "mul", "div", "rem", "gt", "ge", "lt", "le", "max", "min", "atan2", "step"):
         a, b = _bc(a, b)
     if op == "add":

@@ -460,3 +460,61 @@ def test_value_bytes_and_text_reference_vectors():
     # magnitudes the reference prints in full ("{:.6}" never switches to an exponent)
     assert G.format_f32(1e20) == "100000002004087734272.f" and G.format_f32(100.0) == "100.f"
     assert G.format_f32(-0.0) == "-0.f" and G.format_f32(5.1e-7) == "0.000001f"
+
+
+# ---- matrices (reference src/attributes.rs MatrixType :322-397, src/graph/mod.rs MatrixValue :1271-1470) ---------
+def test_matrix_types_literals_and_bytes():
+    m = G.Module()
+    text = lambda v: m.eval(m.lit(v))[0]
+    # graph/mod.rs `to_wgsl_string` (:1953-1976): components column by column (`mat3x3<f32>(1.,0.,…)` there)
+    assert text(G.Mat3(1, 0, 0, 0, 1, 0, 0, 0, 1)) == "mat3x3f(1.f,0.f,0.f,0.f,1.f,0.f,0.f,0.f,1.f)"
+    assert text(G.Mat3(*[0.] * 9)) == "mat3x3f(0.f,0.f,0.f,0.f,0.f,0.f,0.f,0.f,0.f)"
+    assert text(G.Mat3((1., 2., 3.), (4., 5., 6.), (7., 8., 9.))) == "mat3x3f(1.f,2.f,3.f,4.f,5.f,6.f,7.f,8.f,9.f)"
+    assert text(G.Mat(3, 2, [0., 1., 2., 1., 2., 3.])) == "mat3x2f(0.f,1.f,2.f,1.f,2.f,3.f)"      # MatrixValue::new doc example
+    assert G.vt_matrix_dims(G.vt_matrix(3, 2)) == (3, 2) and G.vt_count(G.vt_matrix(4, 3)) == 12
+    with pytest.raises(ValueError):
+        G.Mat(5, 2, [0.] * 10)
+    with pytest.raises(ValueError):
+        G.Mat(2, 2, [0.] * 3)
+    # `as_bytes` (:1746-1758): 16, 48 (= 3 x sizeof(vec4)) and 64 bytes; size / align of every matCxR (attributes.rs:377-397)
+    for cols in (2, 3, 4):
+        for rows in (2, 3, 4):
+            value = G.Mat(cols, rows, [float(i + 1) for i in range(cols * rows)])
+            blob = _asset_with_props([("m", value)]).serialize_properties({})
+            assert len(blob) == cols * (8 if rows == 2 else 16)
+            packed = struct.unpack(f"<{len(blob) // 4}f", blob)
+            n = min(cols * rows, len(packed))
+            assert packed[:n] == tuple(float(i + 1) for i in range(n)) and not any(packed[n:])   # the PACKED storage, zero tail
+    # casts: matrix <-> matrix only (CastExpr::is_valid, expr.rs:1480-1508; tests `invalid_cast_*`, :4690-4720)
+    x = m.lit(G.Mat4(*[0.] * 16))
+    for target in (G.FLOAT, G.VEC3):
+        with pytest.raises(HanabiError):
+            m.cast(x, target)
+    with pytest.raises(HanabiError):
+        m.cast(m.lit(1.0), G.MAT3)
+    with pytest.raises(HanabiError):
+        m.cast(m.lit(G.Vec3(0, 0, 0)), G.vt_matrix(2, 4))
+    assert m.eval(m.cast(x, G.MAT4))[0].startswith("mat4x4f(mat4x4f(")
+    with pytest.raises(HanabiError):     # BuiltInOperator::Rand(ValueType::Matrix) panics in the reference (expr.rs:1700)
+        m.builtin("rand", G.MAT3)
+
+
+def test_matrix_property_layout_limits():
+    """PropertyLayout::new (properties.rs:561-699) advances 16 bytes per property of 16 bytes or more: a mat2x2 is laid
+    out like a vec4; a larger matrix only fits as the last entry. The reference would overlap the next field silently."""
+    a = _asset_with_props([("twist", G.Mat2(1, 0, 0, 1)), ("tint", G.Vec4(1, 1, 1, 1)), ("basis", G.Mat4(*[0.] * 16))])
+    fields, size = a.property_layout()
+    assert [(f.offset, f.name) for f in fields] == [(0, "twist"), (16, "tint"), (32, "basis")] and size == 96
+    assert "mat2x2f twist;" in a.generate().generate_source() and "mat4x4f basis;" in a.generate().generate_source()
+    for bad in ([("basis", G.Mat4(*[0.] * 16)), ("gain", 1.0)],                       # a scalar lands inside the matrix
+                [("a", G.Mat3(*[0.] * 9)), ("b", G.Mat4(*[0.] * 16))]):              # two large matrices
+        with pytest.raises(HanabiError, match="overlaps the matrix property"):
+            _asset_with_props(bad).generate()
+
+
+def test_matrix_effect_compiles_for_sm100a():
+    from tests.test_host_exec_cpu import _matrix_asset
+    src = _matrix_asset(1024).generate().generate_source()
+    assert "mat2x3f(1.f,0.5f,0.25f,-0.5f,1.f,2.f)" in src
+    size, log = R.nvrtc_check(src)
+    assert size > 0 and "error" not in log.lower() and " 0 bytes spill stores" in log

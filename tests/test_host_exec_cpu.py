@@ -94,3 +94,59 @@ def test_operator_table_generated_code(orc):
                                             + w.is_alive().cast(G.FLOAT) + w.time() * w.delta_time())))
     ci, cu, deaths = _run(orc, asset, 12, lambda f: 400 if f == 0 else 15, capacity=512)
     assert ci > 400 and cu > 2000 and deaths > 50
+
+
+def _matrix_asset(capacity):
+    """Matrix values (reference src/graph/mod.rs MatrixValue, src/attributes.rs MatrixType) in literals and
+    properties, through every WGSL matrix product and sum. Also used by the pending GPU test."""
+    w = G.ExprWriter()
+    rot = w.lit(G.Mat3((0., 1., 0.), (-1., 0., 0.), (0., 0., 1.)))            # quarter turn about z
+    lift = w.lit(G.Mat(2, 3, [1., 0.5, 0.25, -0.5, 1., 2.]))                   # mat2x3: vec2 -> vec3
+    squash = w.lit(G.Mat(3, 2, [0.5, 0.125, -0.25, 1., 0.75, -1.5]))           # mat3x2: vec3 -> vec2
+    twist = w.prop(w.add_property("twist", G.Mat2(0.8, 0.6, -0.6, 0.8)))       # 16 bytes: laid out like a vec4
+    gain = w.prop(w.add_property("gain", G.Vec4(1.5, 0., 0., 0.))).x()
+    # 64 bytes: must be the last entry of the layout (PropertyLayout::new advances 16 bytes per property of 16 bytes or
+    # more and places smaller properties after them, properties.rs:572-580), so no scalar / vec2 / vec3 property here
+    basis = w.prop(w.add_property("basis", G.Mat4(*[float(i) for i in range(16)])))
+    v, p = w.attr(A.VELOCITY), w.attr(A.POSITION)
+    return (G.EffectAsset(capacity, w.module, name="matrices")
+            .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(4.) - w.lit(2.)))
+            .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) - w.lit(0.5)))
+            .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+            .init(G.SetAttributeModifier(A.LIFETIME, w.lit(0.3).uniform(w.lit(0.9))))
+            .init(G.SetAttributeModifier(A.F32X2_0, squash * (rot * (w.rand(G.VEC3) * gain))))                  # m*v twice, at init
+            .update(G.SetAttributeModifier(A.F32X3_0, (rot * v) * w.lit(0.875) + lift * (twist * v.x().vec2(v.y()))))    # m*v, prop m*v
+            .update(G.SetAttributeModifier(A.F32X3_1, v * (rot * rot + rot * w.lit(0.5)) - p * (w.lit(2.) * rot - rot)))  # v*m, m*m, m+m, m-m, m*s, s*m
+            .update(G.SetAttributeModifier(A.F32X3_2, (lift * squash) * p))                                     # mat2x3 * mat3x2 -> mat3x3
+            .update(G.SetAttributeModifier(A.F32X2_1, (squash * lift) * w.attr(A.F32X2_0) + p * lift))          # -> mat2x2; vec3 * mat2x3 -> vec2
+            .update(G.SetAttributeModifier(A.F32X4_0, basis * p.vec4_xyz_w(gain) + v.vec4_xyz_w(w.lit(1.)) * basis)))
+
+
+_MATRIX_PROPS = {"twist": G.Mat2(0.28, 0.96, -0.96, 0.28), "gain": G.Vec4(0.75, 9., 9., 9.),
+                 "basis": G.Mat4((1., 0., 0., 0.), (0., 2., 0., 0.), (0., 0., -1., 0.), (0.5, -0.25, 3., 1.))}
+
+
+def test_matrix_values_generated_code_equals_interpreter(orc):
+    """Every product only multiplies and adds in a fixed order, so the lowered text and the interpreter agree bit for bit."""
+    ci, cu, deaths = _run(orc, _matrix_asset(1024), 10, lambda f: 500 if f == 0 else 25, props=_MATRIX_PROPS, capacity=1024)
+    assert ci > 500 and cu > 3000 and deaths > 20
+    # and with the default property values
+    ci, cu, _ = _run(orc, _matrix_asset(1024), 3, lambda f: 200, props={}, capacity=1024)
+    assert ci == 600
+
+
+def test_three_row_matrix_property_keeps_the_reference_byte_image(orc):
+    """MatrixValue::as_bytes (graph/mod.rs:1387-1391) uploads the PACKED column-major storage, which the shader reads with
+    WGSL's 16-byte column stride: a mat3x3 / mat2x3 / mat4x3 property is seen with shifted columns. Same bytes, same
+    read here (tests/test_authoring_cpu.py pins the bytes); this checks the lowered code against the interpreter."""
+    w = G.ExprWriter()
+    m = w.prop(w.add_property("m", G.Mat3(*[float(i + 1) for i in range(9)])))
+    asset = (G.EffectAsset(256, w.module, name="mat3prop")
+             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.))).init(G.SetAttributeModifier(A.LIFETIME, w.lit(10.)))
+             .update(G.SetAttributeModifier(A.F32X3_0, m * w.attr(A.POSITION))))
+    _run(orc, asset, 2, lambda f: 100, props={}, capacity=256)
+    # the columns the shader sees: (1 2 3) (5 6 7) (9 0 0), not (1 2 3) (4 5 6) (7 8 9)
+    from oracle.hanabi_oracle import literal_array
+    seen = literal_array(G.Mat3(*[float(i + 1) for i in range(9)]), 1, as_shader_text=False)[0]
+    np.testing.assert_array_equal(seen, np.array([[1, 2, 3], [5, 6, 7], [9, 0, 0]], dtype=np.float32))

@@ -566,3 +566,30 @@ def test_sector_plane_layout(orc, name):
         eo.frame(ref, orc)
         emu.frame_step(orc, ref.sim, spawn, seed)
         _assert_same(ref, emu.pull(), f"{name} (stride {size}) frame {f}")
+
+
+def test_kernels_with_matrix_values(orc):
+    """Matrix literals and properties (matCxR<f32>; a 96-byte Properties record holding a mat2x2, a vec4 and a mat4x4)
+    through the real hnb_init / hnb_update: two instances with different property records. Products only multiply
+    and add in a fixed order: bit-exact against the interpreter."""
+    from tests.test_host_exec_cpu import _MATRIX_PROPS, _matrix_asset
+    asset = _matrix_asset(1024)
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(2048, size // 4, [Instance(0, 1024, alive=0, seed=21), Instance(1024, 1024, alive=0, seed=22)], dt=1 / 20)
+    props = [_MATRIX_PROPS, {}]
+    for i in range(2):
+        ref.metadata[i].properties_array_index = i
+    eo = EffectOracle(asset, {0: props[0], 1: props[1]})
+    emu = EmuWorld(ref, asset.generate(), chunks=1, update_ctas=2, property_blobs=[asset.serialize_properties(p) for p in props])
+    for f in range(5):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn = [600 if f == 0 else 30, 250 if f % 2 == 0 else 0]
+        seed = [int(x) for x in pcg_hash(np.array([2 * f, 2 * f + 1], dtype=np.uint32))]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        got = emu.pull()
+        np.testing.assert_array_equal(got["metadata"], ref.metadata_rows())
+        np.testing.assert_array_equal(got["indirect"], ref.indirect)
+        np.testing.assert_array_equal(got["particles"], ref.particles, err_msg=f"frame {f}")
+    assert ref.metadata[0].alive_count > 300 and ref.metadata[1].alive_count > 100
