@@ -1,5 +1,8 @@
 """Long-running fuzz of the kernels under the CPU emulation (tests/kernel_emu.py): random worlds, effects, tile sizes and
-grids for a time budget; stops at the first mismatch with the oracle and prints the seed.   python tools/emu_fuzz.py [seconds] [first_seed]"""
+grids for a time budget; stops at the first mismatch with the oracle and prints the seed.
+
+    python tools/emu_fuzz.py [seconds] [first_seed] [sector]     # "sector": half of the worlds on HNB_SLAB_SECTOR_PLANES slabs
+"""
 import sys
 import time
 from pathlib import Path
@@ -19,7 +22,7 @@ from tests.test_gpu_scene import _drifting_sparks, _growing_dust  # noqa: E402
 from tests.test_kernel_emu_cpu import _assert_same  # noqa: E402
 
 
-def one(seed, orc, slib):
+def one(seed, orc, slib, sector_mix=False):
     rng = np.random.default_rng(seed)
     kind = int(rng.integers(0, 4))
     asset = [_drifting_sparks, _firework_trails, _growing_dust, _ribbon_asset][kind](1)
@@ -36,7 +39,8 @@ def one(seed, orc, slib):
         ref.set_sort_keys(fields)
     eo = EffectOracle(asset)
     chunks, ctas = int(rng.choice([1, 2, 4])), int(rng.integers(1, 4))
-    fx = asset.generate()
+    sector = sector_mix and bool(int(pcg_hash(np.array([seed], dtype=np.uint32))[0]) & 1)   # independent of `rng`: same worlds as without the option
+    fx = asset.generate(sector_planes=sector)
     k = {32: 4, 48: 2}.get(size, 1)
     if chunks * k > 16:
         chunks = 1
@@ -50,22 +54,23 @@ def one(seed, orc, slib):
         ref.set_spawns(spawns, seeds)
         eo.frame(ref, orc)
         emu.frame_step(orc, ref.sim, spawns, seeds)
-        _assert_same(ref, emu.pull(), f"seed {seed} kind {kind} caps {caps} chunks {chunks} ctas {ctas} frame {f}")
+        _assert_same(ref, emu.pull(), f"seed {seed} kind {kind} caps {caps} chunks {chunks} ctas {ctas} sector {sector} frame {f}")
     return kind
 
 
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    sector_mix = len(sys.argv) > 3 and sys.argv[3] == "sector"
     orc, slib = c_oracle.load(), static_emu.build()
     t0, n, kinds = time.time(), 0, [0, 0, 0, 0]
     while time.time() - t0 < budget:
-        kinds[one(seed, orc, slib)] += 1
+        kinds[one(seed, orc, slib, sector_mix)] += 1
         seed += 1
         n += 1
         if n % 25 == 0:
             print(f"{n} worlds ok ({time.time() - t0:.0f} s), next seed {seed}, per effect {kinds}", flush=True)
-    print(f"done: {n} random worlds bit-exact against the oracle, seeds up to {seed - 1}, per effect {kinds}")
+    print(f"done: {n} random worlds bit-exact against the oracle, seeds up to {seed - 1}, per effect {kinds}" + (", half of them on sector-plane slabs" if sector_mix else ""))
 
 
 if __name__ == "__main__":
