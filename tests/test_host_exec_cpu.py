@@ -108,7 +108,12 @@ def _matrix_asset(capacity):
     # 64 bytes: must be the last entry of the layout (PropertyLayout::new advances 16 bytes per property of 16 bytes or
     # more and places smaller properties after them, properties.rs:572-580), so no scalar / vec2 / vec3 property here
     basis = w.prop(w.add_property("basis", G.Mat4(*[float(i) for i in range(16)])))
+    wide = w.lit(G.Mat(2, 4, [0.5, -1., 2., 0.25, 1.5, 0.75, -0.5, 1.]))     # mat2x4: vec2 -> vec4
+    tall = w.lit(G.Mat(4, 2, [1., -2., 0.5, 0.25, -0.75, 1.25, 2., -0.125]))  # mat4x2: vec4 -> vec2
+    m34 = w.lit(G.Mat(3, 4, [0.1 * (i - 5) for i in range(12)]))              # mat3x4: vec3 -> vec4 (literals rounded to 1e-6)
+    m43 = w.lit(G.Mat(4, 3, [0.3 * (7 - i) for i in range(12)]))              # mat4x3: vec4 -> vec3
     v, p = w.attr(A.VELOCITY), w.attr(A.POSITION)
+    q = w.attr(A.F32X4_1)
     return (G.EffectAsset(capacity, w.module, name="matrices")
             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(4.) - w.lit(2.)))
             .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) - w.lit(0.5)))
@@ -117,9 +122,11 @@ def _matrix_asset(capacity):
             .init(G.SetAttributeModifier(A.F32X2_0, squash * (rot * (w.rand(G.VEC3) * gain))))                  # m*v twice, at init
             .update(G.SetAttributeModifier(A.F32X3_0, (rot * v) * w.lit(0.875) + lift * (twist * v.x().vec2(v.y()))))    # m*v, prop m*v
             .update(G.SetAttributeModifier(A.F32X3_1, v * (rot * rot + rot * w.lit(0.5)) - p * (w.lit(2.) * rot - rot)))  # v*m, m*m, m+m, m-m, m*s, s*m
-            .update(G.SetAttributeModifier(A.F32X3_2, (lift * squash) * p))                                     # mat2x3 * mat3x2 -> mat3x3
+            .update(G.SetAttributeModifier(A.F32X4_1, wide * v.x().vec2(v.y()) + m34 * p + v * m43))           # the other four shapes, m*v and v*m
+            .update(G.SetAttributeModifier(A.F32X3_2, (lift * squash) * p + m43 * q + q * m34))                 # mat2x3 * mat3x2 -> mat3x3
             .update(G.SetAttributeModifier(A.F32X2_1, (squash * lift) * w.attr(A.F32X2_0) + p * lift))          # -> mat2x2; vec3 * mat2x3 -> vec2
-            .update(G.SetAttributeModifier(A.F32X4_0, basis * p.vec4_xyz_w(gain) + v.vec4_xyz_w(w.lit(1.)) * basis)))
+            .update(G.SetAttributeModifier(A.F32X4_0, basis * p.vec4_xyz_w(gain) + v.vec4_xyz_w(w.lit(1.)) * basis))
+            .update(G.SetAttributeModifier(A.F32X2_2, tall * q + q * wide)))
 
 
 _MATRIX_PROPS = {"twist": G.Mat2(0.28, 0.96, -0.96, 0.28), "gain": G.Vec4(0.75, 9., 9., 9.),
