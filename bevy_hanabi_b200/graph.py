@@ -372,6 +372,9 @@ class WriterExpr:
     def __mul__(self, o): return self._bin("mul", o)
     def __truediv__(self, o): return self._bin("div", o)
     def __mod__(self, o): return self._bin("rem", o)
+    # the reference's method names for the same operators (WriterExpr::add / sub / mul / div / rem, expr.rs)
+    add, sub, mul, div, rem = __add__, __sub__, __mul__, __truediv__, __mod__
+
     def __radd__(self, o): return self._wrap(o)._bin("add", self)
     def __rsub__(self, o): return self._wrap(o)._bin("sub", self)
     def __rmul__(self, o): return self._wrap(o)._bin("mul", self)
@@ -415,6 +418,7 @@ class WriterExpr:
 for _op in UNARY:
     if not hasattr(WriterExpr, _op):
         setattr(WriterExpr, _op, (lambda op: lambda self: self._un(op))(_op))
+WriterExpr.normalized = WriterExpr.normalize   # the reference's name (WriterExpr::normalized)
 
 
 class ExprWriter:
@@ -435,6 +439,14 @@ class ExprWriter:
 
     def prop(self, handle: int) -> WriterExpr:
         return WriterExpr(self, self.module.prop(handle))
+
+    def push(self, expr) -> WriterExpr:
+        """ExprWriter::push: wrap an expression handle of this writer's module."""
+        return WriterExpr(self, _h(expr))
+
+    def alpha_cutoff(self) -> WriterExpr:
+        """BuiltInOperator::AlphaCutoff only exists in the render context; the simulation lowering rejects it at generate()."""
+        return WriterExpr(self, self.module.builtin("alpha_cutoff"))
 
     def time(self) -> WriterExpr:
         return WriterExpr(self, self.module.builtin("time"))

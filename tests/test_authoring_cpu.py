@@ -518,3 +518,16 @@ def test_matrix_effect_compiles_for_sm100a():
     assert "mat2x3f(1.f,0.5f,0.25f,-0.5f,1.f,2.f)" in src
     size, log = R.nvrtc_check(src)
     assert size > 0 and "error" not in log.lower() and " 0 bytes spill stores" in log
+
+
+def test_writer_method_names_of_the_reference():
+    """WriterExpr::{add,sub,mul,div,rem,normalized}, ExprWriter::{push,alpha_cutoff} (graph/expr.rs): same names, same text
+    as the operator forms."""
+    w = G.ExprWriter()
+    v = w.attr(A.VELOCITY)
+    named = v.add(v).sub(v).mul(w.lit(2.)).div(w.lit(3.)).rem(w.lit(1.)).normalized()
+    infix = ((((v + v) - v) * w.lit(2.)) / w.lit(3.) % w.lit(1.)).normalize()
+    assert w.module.eval(named.h)[0] == w.module.eval(infix.h)[0]
+    assert w.module.eval(w.push(named).h)[0] == w.module.eval(named.h)[0]
+    with pytest.raises(HanabiError, match="render-only"):
+        w.module.eval(w.alpha_cutoff().h)
