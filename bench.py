@@ -456,7 +456,10 @@ def run_b200(args):
         prof = ROOT / "profiles" / "traffic.json"
         if prof.exists():
             try:
-                line["roofline"]["traffic"] = json.loads(prof.read_text()).get("hnb_update_dram_bytes_per_launch")
+                rec = json.loads(prof.read_text())
+                # the ncu capture is of one launch over `particles_per_launch` particles: only quote it for that launch size
+                if int(rec.get("particles_per_launch", 0)) == per_rank:
+                    line["roofline"]["traffic"] = rec.get("hnb_update_dram_bytes_per_launch")
             except Exception:
                 pass
         if not args.no_cpu_baseline and n_gpus == 1:
