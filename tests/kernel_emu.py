@@ -28,6 +28,7 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "build" / "kernel_emu"
 
 PRELUDE = r"""
+#include <algorithm>
 #include <math.h>
 #include <pthread.h>
 #include <sched.h>
@@ -146,31 +147,37 @@ static hnb::BatchParams make_params(const EmuBatch* b) {
     for (int i = 0; i < 4; ++i) P.event_counts[i] = b->event_counts[i];
     return P;
 }
-template <typename K> static void emu_launch(K kernel, const hnb::BatchParams& P, unsigned grid, size_t smem) {
-    std::vector<emu::Cta> ctas(grid);
-    std::vector<std::vector<unsigned char>> dyn(grid, std::vector<unsigned char>(smem + 64));
-    for (unsigned b = 0; b < grid; ++b) {
-        pthread_barrier_init(&ctas[b].bar, nullptr, HNB_BLOCK);
-        ctas[b].dyn = (unsigned char*)(((uintptr_t)dyn[b].data() + 15) & ~(uintptr_t)15);
-        memset(ctas[b].statics, 0, sizeof(ctas[b].statics));
-        for (int w = 0; w < HNB_BLOCK / 32; ++w) pthread_barrier_init(&ctas[b].warps[w].bar, nullptr, 32);
-    }
-    std::vector<std::thread> threads;
-    threads.reserve(size_t(grid) * HNB_BLOCK);
-    for (unsigned b = 0; b < grid; ++b)
-        for (unsigned t = 0; t < HNB_BLOCK; ++t)
-            threads.emplace_back([&, b, t] {
-                emu::tls.tid = t; emu::tls.bid = b; emu::tls.lane = t & 31u;
-                emu::tls.cta = &ctas[b]; emu::tls.warp = &ctas[b].warps[t >> 5];
-                kernel(P);
-            });
-    for (auto& th : threads) th.join();
-    for (unsigned b = 0; b < grid; ++b) {
-        pthread_barrier_destroy(&ctas[b].bar);
-        for (int w = 0; w < HNB_BLOCK / 32; ++w) pthread_barrier_destroy(&ctas[b].warps[w].bar);
+// `wave`: CTAs running at the same time. hnb_update gets its whole (small) grid at once; hnb_init's CTAs never wait for
+// one another, so a large spawn burst runs as successive waves instead of one OS thread per requested spawn.
+template <typename K> static void emu_launch(K kernel, const hnb::BatchParams& P, unsigned grid, size_t smem, unsigned wave = 0) {
+    if (wave == 0 || wave > grid) wave = grid;
+    std::vector<emu::Cta> ctas(wave);
+    std::vector<std::vector<unsigned char>> dyn(wave, std::vector<unsigned char>(smem + 64));
+    for (unsigned first = 0; first < grid; first += wave) {
+        const unsigned n = std::min(wave, grid - first);
+        for (unsigned b = 0; b < n; ++b) {
+            pthread_barrier_init(&ctas[b].bar, nullptr, HNB_BLOCK);
+            ctas[b].dyn = (unsigned char*)(((uintptr_t)dyn[b].data() + 15) & ~(uintptr_t)15);
+            memset(ctas[b].statics, 0, sizeof(ctas[b].statics));
+            for (int w = 0; w < HNB_BLOCK / 32; ++w) pthread_barrier_init(&ctas[b].warps[w].bar, nullptr, 32);
+        }
+        std::vector<std::thread> threads;
+        threads.reserve(size_t(n) * HNB_BLOCK);
+        for (unsigned b = 0; b < n; ++b)
+            for (unsigned t = 0; t < HNB_BLOCK; ++t)
+                threads.emplace_back([&, b, t] {
+                    emu::tls.tid = t; emu::tls.bid = first + b; emu::tls.lane = t & 31u;
+                    emu::tls.cta = &ctas[b]; emu::tls.warp = &ctas[b].warps[t >> 5];
+                    kernel(P);
+                });
+        for (auto& th : threads) th.join();
+        for (unsigned b = 0; b < n; ++b) {
+            pthread_barrier_destroy(&ctas[b].bar);
+            for (int w = 0; w < HNB_BLOCK / 32; ++w) pthread_barrier_destroy(&ctas[b].warps[w].bar);
+        }
     }
 }
-extern "C" void emu_init(const EmuBatch* b, uint32_t blocks) { emu_launch(hnb::hnb_init, make_params(b), blocks, 0); }
+extern "C" void emu_init(const EmuBatch* b, uint32_t blocks) { emu_launch(hnb::hnb_init, make_params(b), blocks, 0, 8); }
 extern "C" void emu_update(const EmuBatch* b, uint32_t blocks, uint32_t smem) { emu_launch(hnb::hnb_update, make_params(b), blocks, smem); }
 extern "C" void emu_aos_to_planes(const EmuBatch* b, const uint8_t* aos, uint32_t first, uint32_t count, uint32_t stride) {
     hnb::BatchParams P = make_params(b);

@@ -593,3 +593,55 @@ def test_kernels_with_matrix_values(orc):
         np.testing.assert_array_equal(got["indirect"], ref.indirect)
         np.testing.assert_array_equal(got["particles"], ref.particles, err_msg=f"frame {f}")
     assert ref.metadata[0].alive_count > 300 and ref.metadata[1].alive_count > 100
+
+
+def test_c2_firework_at_its_baseline_size(orc):
+    """BASELINE.json configs[1] ("firework.rs effect, 32768 capacity") at its quoted size: 50 frames of bursts into recycled
+    slots through the emulated init / bookkeeping / update kernels with the 4-chunk tiles large slabs get. Zero tolerance."""
+    from tests import static_emu
+    asset = _firework_trails(32768)
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(32768, size // 4, [Instance(0, 32768, alive=0)], dt=1 / 20)
+    eo = EffectOracle(asset)
+    emu = EmuWorld(ref, asset.generate(), chunks=4, update_ctas=3, static_lib=static_emu.build())
+    for f in range(50):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn, seed = [9000 if f % 20 == 0 else 150], [int(pcg_hash(np.array([0x4321 + f], dtype=np.uint32))[0])]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        if f % 5 == 0 or f == 49:
+            _assert_same(ref, emu.pull(), f"frame {f}")
+    assert ref.metadata[0].particle_counter == 34050 and ref.metadata[0].alive_count == 11768
+
+
+def test_c3_force_field_at_its_baseline_size(orc):
+    """BASELINE.json configs[2] ("force_field.rs: 1M particles") at its quoted size through the emulated kernels (a burst of
+    1 Mi - 4096 spawns run as waves of init CTAs, then 4-chunk update tiles over the whole slab): integer structures
+    exact, fp32 attributes within 1e-5 of their magnitude per step (host libm vs numpy)."""
+    from tests import static_emu
+    from tests.helpers import assert_float_attributes_close
+    from tests.test_gpu_effects import _float_word_mask, _force_field
+    n = 1 << 20
+    asset = _force_field(n)
+    _, size, _ = asset.particle_layout()
+    props = {"attraction_accel": 18.0, "repulsor_position": G.Vec3(0.25, 0.5, 0.1)}
+    ref = RefWorld(n, size // 4, [Instance(0, n, alive=0, seed=77)])
+    ref.metadata[0].properties_array_index = 0
+    eo = EffectOracle(asset, {0: props})
+    emu = EmuWorld(ref, asset.generate(), chunks=4, update_ctas=3, static_lib=static_emu.build(), property_blobs=[asset.serialize_properties(props)])
+    mask, fattrs = _float_word_mask(asset)
+    for f in range(2):
+        ref.sim.time = np.float32(f) * ref.sim.delta_time
+        spawn, seed = [n - 4096 if f == 0 else 500], [int(pcg_hash(np.array([f], dtype=np.uint32))[0])]
+        ref.set_spawns(spawn, seed)
+        eo.frame(ref, orc)
+        emu.frame_step(orc, ref.sim, spawn, seed)
+        got = emu.pull()
+        np.testing.assert_array_equal(got["metadata"], ref.metadata_rows())
+        np.testing.assert_array_equal(got["indirect"], ref.indirect)
+        np.testing.assert_array_equal(got["particles"][:, ~mask], ref.particles[:, ~mask])
+        assert_float_attributes_close(got["particles"], ref.particles, fattrs, 1e-5, f"frame {f}")
+        aos = np.ascontiguousarray(ref.particles)
+        emu.lib.emu_aos_to_planes(C.byref(emu.b), aos.ctypes.data, 0, emu.rows, emu.stride)
+    assert ref.metadata[0].alive_count == n - 4096 + 500
