@@ -177,3 +177,93 @@ def test_random_exact_graphs_generated_code_equals_interpreter(orc, data):
             np.testing.assert_array_equal(*canon(ih, io), err_msg="init records\n" + fx.init_code)
             np.testing.assert_array_equal(*canon(uh, uo), err_msg="update records\n" + fx.update_code)
             np.testing.assert_array_equal(ah, ao)
+
+
+def build_linear(draw, w, depth, kind):
+    """Random graphs over matCxR / vecN / f32 values joined by the WGSL linear-algebra operators only (+, -, *, dot):
+    every operation is one IEEE rounding, so generated code and interpreter must agree bit for bit.
+    kind: "f" | ("v", n) | ("m", cols, rows)"""
+    i = lambda n: draw(st.integers(0, n))
+    dim = lambda: draw(st.integers(2, 4))
+    lit = lambda: float(np.float32(draw(st.floats(-2.0, 2.0, allow_nan=False, width=32))))
+    sub = lambda k: build_linear(draw, w, depth - 1, k)
+    if kind == "f":
+        if depth == 0:
+            return [lambda: w.lit(lit()), lambda: w.attr(A.AGE), lambda: w.attr(A.F32_1)][i(2)]()
+        c, n = i(2), dim()
+        if c == 0: return sub("f") * sub("f") - sub("f")
+        if c == 1: return sub(("v", n)).dot(sub(("v", n)))
+        return (sub(("v", n)) * sub(("m", 3, n))).y()                      # component of an infix product
+    if kind[0] == "v":
+        n = kind[1]
+        if depth == 0:
+            attr = {2: A.SIZE2, 3: [A.POSITION, A.VELOCITY][i(1)], 4: A.HDR_COLOR}[n]
+            return [lambda: w.lit(Value_vec(n, [lit() for _ in range(n)])), lambda: w.attr(attr)][i(1)]()
+        c, k = i(3), dim()
+        if c == 0: return sub(("m", k, n)) * sub(("v", k))                 # matKxN * vecK -> vecN
+        if c == 1: return sub(("v", k)) * sub(("m", n, k))                 # vecK * matNxK -> vecN
+        if c == 2: return sub(kind) * sub("f") + sub(kind)
+        return sub(kind) - sub(kind) * sub(kind)
+    _, cols, rows = kind
+    if depth == 0:
+        return w.lit(G.Mat(cols, rows, [lit() for _ in range(cols * rows)]))
+    c, k = i(4), dim()
+    if c == 0: return sub(("m", k, rows)) * sub(("m", cols, k))            # matKxR * matCxK -> matCxR
+    if c == 1: return sub(kind) + sub(kind)
+    if c == 2: return sub(kind) - sub(kind)
+    if c == 3: return sub(kind) * sub("f")
+    return sub("f") * sub(kind)
+
+
+def Value_vec(n, xs):
+    return {2: G.Vec2, 3: G.Vec3, 4: G.Vec4}[n](*xs)
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), phases=[Phase.generate], derandomize=True)
+@given(st.data())
+def test_random_matrix_graphs_generated_code_equals_interpreter(orc, data):
+    """Matrix values (all nine matCxR shapes, chosen at random) in random product / sum graphs: the generated code must
+    compile for sm_100a and, run on the CPU, equal the interpreter bit for bit."""
+    from tests.host_exec import HostEffect, replay_frame
+    w = G.ExprWriter()
+    depth = lambda: data.draw(st.integers(1, 3))
+    exprs = {"f": build_linear(data.draw, w, depth(), "f"), 2: build_linear(data.draw, w, depth(), ("v", 2)),
+             3: build_linear(data.draw, w, depth(), ("v", 3)), 4: build_linear(data.draw, w, depth(), ("v", 4))}
+    asset = (G.EffectAsset(128, w.module, name="matrix_fuzz")
+             .init(G.SetAttributeModifier(A.POSITION, w.rand(G.VEC3) * w.lit(4.) - w.lit(2.)))
+             .init(G.SetAttributeModifier(A.VELOCITY, w.rand(G.VEC3) - w.lit(0.5)))
+             .init(G.SetAttributeModifier(A.AGE, w.lit(0.)))
+             .init(G.SetAttributeModifier(A.LIFETIME, w.lit(0.05).uniform(w.lit(0.2))))
+             .init(G.SetAttributeModifier(A.F32_1, w.rand() * w.lit(3.)))
+             .init(G.SetAttributeModifier(A.SIZE2, w.rand(G.VEC2)))
+             .init(G.SetAttributeModifier(A.HDR_COLOR, w.rand(G.VEC4)))
+             .update(G.SetAttributeModifier(A.F32_0, exprs["f"]))
+             .update(G.SetAttributeModifier(A.F32X2_0, exprs[2]))
+             .update(G.SetAttributeModifier(A.F32X3_0, exprs[3]))
+             .update(G.SetAttributeModifier(A.F32X4_0, exprs[4])))
+    fx = asset.generate()
+    try:
+        R.nvrtc_check(fx.generate_source())
+    except Exception as e:
+        raise AssertionError(f"generated update code does not compile:\n{fx.update_code}\n{str(e)[:2000]}") from None
+    host = HostEffect(fx)
+    _, size, _ = asset.particle_layout()
+    ref = RefWorld(128, size // 4, [Instance(0, 128, alive=0, seed=data.draw(st.integers(0, 2**32 - 1)))])
+    eo = EffectOracle(asset)
+
+    def canon(a, b):
+        a, b = a.copy(), b.copy()
+        fa, fb = a.view(np.float32), b.view(np.float32)
+        same = np.isnan(fa) & np.isnan(fb)
+        a[same] = 0
+        b[same] = 0
+        return a, b
+
+    with np.errstate(all="ignore"):
+        for f in range(2):
+            ref.sim.time = np.float32(f) * ref.sim.delta_time
+            ref.set_spawns([80 if f == 0 else 20])
+            ih, io, uh, uo, ah, ao = replay_frame(host, eo, ref, orc)
+            np.testing.assert_array_equal(*canon(ih, io), err_msg="init records\n" + fx.init_code)
+            np.testing.assert_array_equal(*canon(uh, uo), err_msg="update records\n" + fx.update_code)
+            np.testing.assert_array_equal(ah, ao)
