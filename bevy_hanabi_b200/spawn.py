@@ -1,5 +1,6 @@
-"""Binding of the CPU producers (SpawnerSettings / EffectSpawner::tick, Batcher::push) — reference src/spawn.rs,
-src/render/batch.rs — implemented natively in csrc/graph/spawn_batch.cpp."""
+"""Binding of the CPU producers (SpawnerSettings / EffectSpawner::tick, Batcher::push, the EffectSimulation clock) —
+reference src/spawn.rs, src/render/batch.rs, src/time.rs — implemented natively in csrc/graph/spawn_batch.cpp and
+csrc/graph/sim_clock.cpp."""
 from __future__ import annotations
 
 import ctypes as C
@@ -25,7 +26,29 @@ class BatchKey(C.Structure):
                 ("uses_gpu_events", u32), ("is_cpu_spawner", u32)]
 
 
+class SimClockState(C.Structure):
+    _fields_ = [("real_elapsed_ns", C.c_uint64), ("real_delta_ns", C.c_uint64), ("virtual_elapsed_ns", C.c_uint64),
+                ("virtual_delta_ns", C.c_uint64), ("sim_elapsed_ns", C.c_uint64), ("sim_delta_ns", C.c_uint64),
+                ("virtual_effective_speed", C.c_double), ("sim_effective_speed", C.c_double)]
+
+
 SPAWN_SIGNATURES = {
+    "hnb_sim_clock_create": (C.c_void_p, []),
+    "hnb_sim_clock_destroy": (None, [C.c_void_p]),
+    "hnb_sim_clock_set_virtual_relative_speed": (C.c_int32, [C.c_void_p, C.c_double]),
+    "hnb_sim_clock_set_virtual_paused": (None, [C.c_void_p, u32]),
+    "hnb_sim_clock_set_max_delta_ns": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "hnb_sim_clock_set_relative_speed": (C.c_int32, [C.c_void_p, C.c_double]),
+    "hnb_sim_clock_pause": (None, [C.c_void_p]),
+    "hnb_sim_clock_unpause": (None, [C.c_void_p]),
+    "hnb_sim_clock_is_paused": (u32, [C.c_void_p]),
+    "hnb_sim_clock_was_paused": (u32, [C.c_void_p]),
+    "hnb_sim_clock_relative_speed": (C.c_double, [C.c_void_p]),
+    "hnb_sim_clock_effective_speed": (C.c_double, [C.c_void_p]),
+    "hnb_sim_clock_advance": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "hnb_sim_clock_sim_params": (C.c_int32, [C.c_void_p, u32, P(N.SimParams)]),
+    "hnb_sim_params_default": (None, [P(N.SimParams)]),
+    "hnb_sim_clock_state": (C.c_int32, [C.c_void_p, P(SimClockState)]),
     "hnb_spawner_settings_new": (C.c_int32, [f32, f32, f32, f32, f32, f32, u32, P(SpawnerSettingsC)]),
     "hnb_spawner_settings_once": (C.c_int32, [f32, P(SpawnerSettingsC)]),
     "hnb_spawner_settings_rate": (C.c_int32, [f32, P(SpawnerSettingsC)]),
@@ -185,3 +208,74 @@ class EffectSorter:
 
     def entities(self) -> list[int]:
         return [lib.hnb_effect_sorter_get(self._h, i) for i in range(lib.hnb_effect_sorter_len(self._h))]
+
+
+class EffectSimulationClock:
+    """Time<EffectSimulation> with its Real and Virtual parents (reference src/time.rs, bevy_time): the host-side
+    producer of GpuSimParams. Method names follow EffectSimulationTime (time.rs:48-108)."""
+
+    def __init__(self):
+        self._h = lib.hnb_sim_clock_create()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.hnb_sim_clock_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # EffectSimulationTime
+    def relative_speed(self) -> float:
+        return lib.hnb_sim_clock_relative_speed(self._h)
+
+    def effective_speed(self) -> float:
+        return lib.hnb_sim_clock_effective_speed(self._h)
+
+    def set_relative_speed(self, ratio: float):
+        check(lib.hnb_sim_clock_set_relative_speed(self._h, float(ratio)))
+
+    def pause(self):
+        lib.hnb_sim_clock_pause(self._h)
+
+    def unpause(self):
+        lib.hnb_sim_clock_unpause(self._h)
+
+    def is_paused(self) -> bool:
+        return bool(lib.hnb_sim_clock_is_paused(self._h))
+
+    def was_paused(self) -> bool:
+        return bool(lib.hnb_sim_clock_was_paused(self._h))
+
+    # Time<Virtual>
+    def set_virtual_relative_speed(self, ratio: float):
+        check(lib.hnb_sim_clock_set_virtual_relative_speed(self._h, float(ratio)))
+
+    def set_virtual_paused(self, paused: bool):
+        lib.hnb_sim_clock_set_virtual_paused(self._h, int(paused))
+
+    def set_max_delta_ns(self, ns: int):
+        check(lib.hnb_sim_clock_set_max_delta_ns(self._h, int(ns)))
+
+    def advance(self, real_delta_ns: int):
+        """time_system + effect_simulation_time_system (time.rs:164-183) for one frame."""
+        check(lib.hnb_sim_clock_advance(self._h, int(real_delta_ns)))
+
+    def sim_params(self, num_effects: int = 0) -> "N.SimParams":
+        """extract_sim_params + GpuSimParams::from (mod.rs:2796-2811, :266-279)."""
+        out = N.SimParams()
+        check(lib.hnb_sim_clock_sim_params(self._h, num_effects, C.byref(out)))
+        return out
+
+    @property
+    def state(self) -> SimClockState:
+        s = SimClockState()
+        check(lib.hnb_sim_clock_state(self._h, C.byref(s)))
+        return s
+
+
+def default_sim_params() -> "N.SimParams":
+    """GpuSimParams::default (mod.rs:244-256)."""
+    out = N.SimParams()
+    lib.hnb_sim_params_default(C.byref(out))
+    return out

@@ -60,7 +60,6 @@ static int32_t set_attribute(hnb_asset* a, uint32_t context, const char* attr, h
 int main(int argc, char** argv) {
     const int frames = argc > 1 ? atoi(argv[1]) : 120;
     const uint32_t capacity = 32768;
-    const float dt = 1.0f / 60.0f;
     printf("%s\n", hnb_version());
 
     /* ---- authoring (CPU only) */
@@ -118,8 +117,14 @@ int main(int argc, char** argv) {
     hnb_draw_indexed_indirect_args draw0 = {6, 0, 0, 0, 0}; /* a quad: index_count 6, instance_count filled by the simulation */
     CHECK(hnb_draw_args_insert(ctx, 0, &draw0));
 
+    /* Time<EffectSimulation> (reference src/time.rs): real frame times in, GpuSimParams out */
+    hnb_sim_clock* clock = hnb_sim_clock_create();
     uint32_t peak = 0;
     for (int f = 0; f < frames; ++f) {
+        hnb_sim_params sim;
+        CHECK(hnb_sim_clock_advance(clock, 16666667ull)); /* a 60 Hz frame */
+        CHECK(hnb_sim_clock_sim_params(clock, 1, &sim));
+        const float dt = sim.delta_time; /* tick_spawners reads the same clock (spawn.rs:948, :963) */
         uint32_t spawn = 0;
         CHECK(hnb_effect_spawner_tick(spawner, dt, &spawn));
         hnb_spawner row;
@@ -141,7 +146,6 @@ int main(int argc, char** argv) {
         uint32_t n_batches, n_prefix, totals[1];
         CHECK(hnb_batcher_finish(batcher, &infos, &n_batches, &prefix, &n_prefix, totals, 1));
 
-        hnb_sim_params sim = {dt, f * dt, dt, f * dt, dt, f * dt, 1};
         CHECK(hnb_set_sim_params(ctx, &sim));
         CHECK(hnb_upload_spawners(ctx, &row, 1));
         CHECK(hnb_upload_batches(ctx, infos, n_batches, prefix, n_prefix));
@@ -160,6 +164,7 @@ int main(int argc, char** argv) {
     hnb_effect_destroy(ctx, effect);
     hnb_ctx_destroy(ctx);
     hnb_batcher_destroy(batcher);
+    hnb_sim_clock_destroy(clock);
     hnb_effect_spawner_destroy(spawner);
     hnb_generated_destroy(gen);
     hnb_asset_destroy(asset);

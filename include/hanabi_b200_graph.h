@@ -150,6 +150,41 @@ HNB_API void hnb_effect_spawner_reset(hnb_effect_spawner* s);
 HNB_API void hnb_effect_spawner_set_active(hnb_effect_spawner* s, uint32_t active);
 HNB_API int32_t hnb_effect_spawner_state(const hnb_effect_spawner* s, hnb_effect_spawner_state_t* out);
 
+/* ---- Simulation clock -> GpuSimParams (reference src/time.rs, src/render/mod.rs:193-279, :2796-2811) ---- */
+/** Time<Real>, Time<Virtual> (bevy_time 0.19, restated) and Time<EffectSimulation> (time.rs:30-46), in integer
+ *  nanoseconds like Rust's Duration. */
+typedef struct hnb_sim_clock hnb_sim_clock;
+typedef struct hnb_sim_clock_state_t {
+    uint64_t real_elapsed_ns, real_delta_ns;
+    uint64_t virtual_elapsed_ns, virtual_delta_ns;
+    uint64_t sim_elapsed_ns, sim_delta_ns;
+    double virtual_effective_speed; /* Time<Virtual>::effective_speed_f64 */
+    double sim_effective_speed;     /* EffectSimulationTime::effective_speed_f64 (time.rs:127) */
+} hnb_sim_clock_state_t;
+HNB_API hnb_sim_clock* hnb_sim_clock_create(void);
+HNB_API void hnb_sim_clock_destroy(hnb_sim_clock* c);
+/** Time<Virtual>::set_relative_speed_f64 / pause / unpause / set_max_delta (default 250 ms). */
+HNB_API int32_t hnb_sim_clock_set_virtual_relative_speed(hnb_sim_clock* c, double ratio);
+HNB_API void hnb_sim_clock_set_virtual_paused(hnb_sim_clock* c, uint32_t paused);
+HNB_API int32_t hnb_sim_clock_set_max_delta_ns(hnb_sim_clock* c, uint64_t ns);
+/** EffectSimulationTime (time.rs:48-162). Where the reference asserts (non-finite or negative ratio,
+ *  time.rs:138-139) the call returns HNB_ERR_INVALID_ARG with the same message and changes nothing. */
+HNB_API int32_t hnb_sim_clock_set_relative_speed(hnb_sim_clock* c, double ratio);
+HNB_API void hnb_sim_clock_pause(hnb_sim_clock* c);
+HNB_API void hnb_sim_clock_unpause(hnb_sim_clock* c);
+HNB_API uint32_t hnb_sim_clock_is_paused(const hnb_sim_clock* c);
+HNB_API uint32_t hnb_sim_clock_was_paused(const hnb_sim_clock* c);
+HNB_API double hnb_sim_clock_relative_speed(const hnb_sim_clock* c);
+HNB_API double hnb_sim_clock_effective_speed(const hnb_sim_clock* c);
+/** One frame: time_system (Real, Virtual) then effect_simulation_time_system (time.rs:164-183), given the real
+ *  time that passed since the previous frame. */
+HNB_API int32_t hnb_sim_clock_advance(hnb_sim_clock* c, uint64_t real_delta_ns);
+/** extract_sim_params (mod.rs:2796-2811) + From<&SimParams> for GpuSimParams (mod.rs:266-279): the record to hand
+ *  to hnb_set_sim_params. */
+HNB_API int32_t hnb_sim_clock_sim_params(const hnb_sim_clock* c, uint32_t num_effects, hnb_sim_params* out);
+HNB_API void hnb_sim_params_default(hnb_sim_params* out); /* GpuSimParams::default, mod.rs:244-256 */
+HNB_API int32_t hnb_sim_clock_state(const hnb_sim_clock* c, hnb_sim_clock_state_t* out);
+
 /** What EffectBatch::try_merge compares (reference src/render/batch.rs:153-173). */
 typedef struct hnb_batch_key {
     uint64_t asset_id;       /* handle */
