@@ -531,3 +531,49 @@ def test_writer_method_names_of_the_reference():
     assert w.module.eval(w.push(named).h)[0] == w.module.eval(named.h)[0]
     with pytest.raises(HanabiError, match="render-only"):
         w.module.eval(w.alpha_cutoff().h)
+
+
+# ---- asset.rs: add_modifiers, test_apply_modifiers (simulation half), transitive_attr ------------------------
+def test_asset_add_modifiers_contexts():
+    """asset.rs:1191-1216 `add_modifiers`: SetAttributeModifier is accepted in the init and in the update context
+    (the render context is outside the simulation path)."""
+    for add in ("init", "update"):
+        w = G.ExprWriter()
+        asset = G.EffectAsset(8, w.module)
+        getattr(asset, add)(G.SetAttributeModifier(A.POSITION, w.lit(G.Vec3(3., 3., 3.))))
+        assert len(asset.init_modifiers) + len(asset.update_modifiers) == 1
+        asset._native()   # hnb_asset_add_modifier checks Modifier::context() like EffectAsset::add_modifier
+        names = [f.name for f in asset.particle_layout()[0]]
+        assert "position" in names
+
+
+def test_asset_apply_modifiers():
+    """asset.rs:1218-1300 `test_apply_modifiers`, init and update contexts: every modifier applies without error on
+    the asset, capacity is kept, and the generated translation unit compiles."""
+    w = G.ExprWriter()
+    origin, one = w.lit(G.Vec3(0., 0., 0.)), w.lit(1.)
+    asset = (G.EffectAsset(4096, w.module, name="apply_modifiers")
+             .init(G.SetPositionSphereModifier(w.lit(G.Vec3(0., 0., 0.)), w.lit(1.), G.VOLUME))
+             .init(G.SetVelocitySphereModifier(w.lit(G.Vec3(0., 0., 0.)), w.lit(1.)))
+             .init(G.SetAttributeModifier(A.AGE, one))
+             .init(G.SetAttributeModifier(A.LIFETIME, one))
+             .update(G.AccelModifier(w.lit(G.Vec3(1., 1., 1.))))          # AccelModifier::constant(module, Vec3::ONE)
+             .update(G.LinearDragModifier(w.lit(3.5)))                    # LinearDragModifier::constant(module, 3.5)
+             .update(G.ConformToSphereModifier(origin, one, one, one, one)))
+    assert asset.capacity == 4096
+    fx = asset.generate()
+    for needle in ("particle.position", "particle.velocity", "particle.age", "particle.lifetime"):
+        assert needle in fx.init_code + fx.init_extra
+    assert "particle.velocity" in fx.update_code + fx.update_extra
+    size, log = R.nvrtc_check(fx.generate_source())
+    assert size > 0, log
+
+
+def test_asset_transitive_attr():
+    """asset.rs:1403-1413 `transitive_attr` (regression test for #440): an attribute only *read* by an expression
+    is part of the particle layout, like the attribute the modifier writes."""
+    w = G.ExprWriter()
+    asset = G.EffectAsset(32, w.module).init(G.SetAttributeModifier(A.AGE, w.attr(A.F32_0)))
+    names = [f.name for f in asset.particle_layout()[0]]
+    assert "age" in names        # direct
+    assert "f32_0" in names      # transitive
