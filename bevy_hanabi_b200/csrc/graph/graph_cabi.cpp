@@ -1,4 +1,5 @@
 // graph_cabi.cpp — extern "C" surface of the authoring layer (include/hanabi_b200_graph.h).
+#include <set>
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -303,5 +304,133 @@ int32_t hnb_generated_desc(const hnb_generated* g, hnb_effect_desc* d) {
     });
 }
 void hnb_generated_destroy(hnb_generated* g) { delete g; }
+
+// ---- EffectProperties: the per-instance property store (reference src/properties.rs:205-454) ----------------
+// The ECS component is Bevy's; what reaches the kernels is the byte blob of `serialize`, and which values it
+// holds is decided by `set` / `update`. Change detection (`Mut<>`) is reported through `*changed`.
+}  // extern "C" (struct with C++ members)
+
+struct hnb_effect_properties {
+    struct Instance {  // PropertyInstance (properties.rs:183-190)
+        Property def;
+        Value value;
+    };
+    std::vector<Instance> properties;
+    int find(const char* name) const {
+        for (size_t i = 0; i < properties.size(); ++i)
+            if (properties[i].def.name == name) return (int)i;
+        return -1;
+    }
+};
+
+namespace {
+bool same_value(const Value& a, const Value& b) {
+    return a.type == b.type && memcmp(a.bits, b.bits, sizeof(uint32_t) * (size_t)a.type.count()) == 0;
+}
+// EffectProperties::set / set_if_changed (properties.rs:319-376)
+void props_set(hnb_effect_properties* p, const char* name, uint32_t vt, const uint32_t* words, bool only_if_changed, uint32_t* changed) {
+    if (!p || !name) throw ExprError(ExprError::PropertyError, "NULL argument");
+    const Value value = value_from(vt, words);
+    if (changed) *changed = 1;
+    const int i = p->find(name);
+    if (i < 0) {
+        p->properties.push_back({Property{name, value}, value});
+        return;
+    }
+    auto& prop = p->properties[(size_t)i];
+    if (prop.def.default_value.type != value.type)
+        throw ExprError(ExprError::PropertyError, "Cannot assign value of type " + value.type.to_cuda_string() + " to property '" + prop.def.name +
+                                                      "' of type " + prop.def.default_value.type.to_cuda_string());
+    if (only_if_changed && same_value(prop.value, value)) {
+        if (changed) *changed = 0;
+        return;
+    }
+    prop.value = value;
+}
+}  // namespace
+
+extern "C" {
+
+hnb_effect_properties* hnb_effect_properties_create(void) { return new hnb_effect_properties(); }
+void hnb_effect_properties_destroy(hnb_effect_properties* p) { delete p; }
+uint32_t hnb_effect_properties_len(const hnb_effect_properties* p) { return p ? (uint32_t)p->properties.size() : 0; }
+
+int32_t hnb_effect_properties_set(hnb_effect_properties* p, const char* name, uint32_t value_type, const uint32_t* words) {
+    return guarded([&] { props_set(p, name, value_type, words, false, nullptr); });
+}
+int32_t hnb_effect_properties_set_if_changed(hnb_effect_properties* p, const char* name, uint32_t value_type, const uint32_t* words,
+                                             uint32_t* changed) {
+    return guarded([&] { props_set(p, name, value_type, words, true, changed); });
+}
+// EffectProperties::get_stored (properties.rs:305-310): 1 = found, 0 = no such property
+int32_t hnb_effect_properties_get_stored(const hnb_effect_properties* p, const char* name, uint32_t* value_type, uint32_t* words16) {
+    if (!p || !name) return 0;
+    const int i = p->find(name);
+    if (i < 0) return 0;
+    const Value& v = p->properties[(size_t)i].value;
+    if (value_type) *value_type = v.type.code;
+    if (words16) memcpy(words16, v.bits, sizeof(v.bits));
+    return 1;
+}
+int32_t hnb_effect_properties_get(const hnb_effect_properties* p, uint32_t index, const char** name, uint32_t* value_type,
+                                  uint32_t* value_words16, uint32_t* default_words16) {
+    return guarded([&] {
+        if (!p || index >= p->properties.size()) throw ExprError(ExprError::PropertyError, "property index out of range");
+        const auto& pi = p->properties[index];
+        if (name) *name = pi.def.name.c_str();
+        if (value_type) *value_type = pi.def.default_value.type.code;
+        if (value_words16) memcpy(value_words16, pi.value.bits, sizeof(pi.value.bits));
+        if (default_words16) memcpy(default_words16, pi.def.default_value.bits, sizeof(pi.def.default_value.bits));
+    });
+}
+// EffectProperties::update (properties.rs:378-417): drop the instances the asset does not declare, append the
+// asset's missing properties with their default value; stored values of known properties win.
+int32_t hnb_effect_properties_update(hnb_effect_properties* p, const hnb_asset* asset, uint32_t* changed) {
+    return guarded([&] {
+        if (!p || !asset) throw ExprError(ExprError::PropertyError, "NULL argument");
+        std::vector<hnb_effect_properties::Instance> fresh;
+        std::set<std::string> intersect;
+        for (const Property& prop : asset->a.module.properties()) {
+            if (p->find(prop.name.c_str()) >= 0) {
+                intersect.insert(prop.name);
+                continue;
+            }
+            fresh.push_back({prop, prop.default_value});
+        }
+        bool mutated = false;
+        if (intersect.size() != p->properties.size()) {
+            auto& v = p->properties;
+            v.erase(std::remove_if(v.begin(), v.end(), [&](const auto& pi) { return !intersect.count(pi.def.name); }), v.end());
+            mutated = true;
+        }
+        if (!fresh.empty()) {
+            p->properties.insert(p->properties.end(), fresh.begin(), fresh.end());
+            mutated = true;
+        }
+        if (changed) *changed = mutated ? 1u : 0u;
+    });
+}
+// EffectProperties::serialize (properties.rs:437-453): a zeroed record with every stored property the layout knows
+// written at its offset. The record is padded to the layout's min_binding_size, the size hnb_upload_properties takes.
+int32_t hnb_effect_properties_serialize(const hnb_effect_properties* p, const hnb_asset* asset, void* blob, uint32_t blob_cap,
+                                        uint32_t* blob_size) {
+    return guarded([&] {
+        if (!p || !asset) throw ExprError(ExprError::PropertyError, "NULL argument");
+        const PropertyLayout pl = asset->a.property_layout();
+        std::vector<uint8_t> data(pl.min_binding_size(), 0);
+        for (const auto& pi : p->properties) {
+            const auto off = pl.offset(pi.def.name);
+            if (!off) continue;
+            const uint32_t size = pi.def.default_value.type.size();
+            if (*off + size > data.size()) throw ExprError(ExprError::PropertyError, "property '" + pi.def.name + "' does not fit the asset's layout");
+            memcpy(&data[*off], pi.value.bits, size);
+        }
+        if (blob_size) *blob_size = (uint32_t)data.size();
+        if (blob) {
+            if (blob_cap < data.size()) throw ExprError(ExprError::PropertyError, "property blob buffer too small");
+            memcpy(blob, data.data(), data.size());
+        }
+    });
+}
 
 }  // extern "C"

@@ -47,6 +47,15 @@ _SIGS = {
     "hnb_asset_particle_layout": (C.c_int32, [C.c_void_p, P(N.AttrLayout), u32, P(u32), P(u32), P(u32)]),
     "hnb_asset_property_layout": (C.c_int32, [C.c_void_p, P(N.AttrLayout), u32, P(u32), P(u32)]),
     "hnb_asset_serialize_properties": (C.c_int32, [C.c_void_p, P(C.c_char_p), P(P(u32)), u32, C.c_void_p, u32, P(u32)]),
+    "hnb_effect_properties_create": (C.c_void_p, []),
+    "hnb_effect_properties_destroy": (None, [C.c_void_p]),
+    "hnb_effect_properties_len": (u32, [C.c_void_p]),
+    "hnb_effect_properties_set": (C.c_int32, [C.c_void_p, C.c_char_p, u32, P(u32)]),
+    "hnb_effect_properties_set_if_changed": (C.c_int32, [C.c_void_p, C.c_char_p, u32, P(u32), P(u32)]),
+    "hnb_effect_properties_get_stored": (C.c_int32, [C.c_void_p, C.c_char_p, P(u32), P(u32)]),
+    "hnb_effect_properties_get": (C.c_int32, [C.c_void_p, u32, P(C.c_char_p), P(u32), P(u32), P(u32)]),
+    "hnb_effect_properties_update": (C.c_int32, [C.c_void_p, C.c_void_p, P(u32)]),
+    "hnb_effect_properties_serialize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, u32, P(u32)]),
     "hnb_asset_generate": (C.c_int32, [C.c_void_p, C.c_void_p, u32, P(C.c_void_p)]),
     "hnb_generated_desc": (C.c_int32, [C.c_void_p, P(N.EffectDesc)]),
     "hnb_generated_destroy": (None, [C.c_void_p]),
@@ -691,6 +700,77 @@ class EffectAsset:
         finally:
             lib.hnb_generated_destroy(g)
         return fx
+
+
+@dataclass
+class PropertyInstance:
+    """PropertyInstance (properties.rs:183-190): definition (name, default) and current value."""
+    name: str
+    default_value: Value
+    value: Value
+
+
+class EffectProperties:
+    """Per-instance property values (reference src/properties.rs:205-454): what `hnb_upload_properties` receives is
+    `serialize(asset)`. Method names follow the reference; where it asserts, HanabiError is raised."""
+
+    def __init__(self):
+        self._h = lib.hnb_effect_properties_create()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.hnb_effect_properties_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _words(v: Value):
+        return (u32 * 16)(*v.words)
+
+    def with_properties(self, properties) -> "EffectProperties":
+        for name, value in properties:
+            self.set(name, value)
+        return self
+
+    def set(self, name: str, value) -> None:
+        v = Value.of(value)
+        check(lib.hnb_effect_properties_set(self._h, name.encode(), v.vt, self._words(v)))
+
+    def set_if_changed(self, name: str, value) -> bool:
+        v = Value.of(value)
+        changed = u32()
+        check(lib.hnb_effect_properties_set_if_changed(self._h, name.encode(), v.vt, self._words(v), C.byref(changed)))
+        return bool(changed.value)
+
+    def get_stored(self, name: str) -> Optional[Value]:
+        vt, words = u32(), (u32 * 16)()
+        if not lib.hnb_effect_properties_get_stored(self._h, name.encode(), C.byref(vt), words):
+            return None
+        return Value(vt.value, tuple(words[: vt_count(vt.value)]))
+
+    def properties(self) -> list:
+        out = []
+        for i in range(lib.hnb_effect_properties_len(self._h)):
+            name, vt, val, dflt = C.c_char_p(), u32(), (u32 * 16)(), (u32 * 16)()
+            check(lib.hnb_effect_properties_get(self._h, i, C.byref(name), C.byref(vt), val, dflt))
+            n = vt_count(vt.value)
+            out.append(PropertyInstance(name.value.decode(), Value(vt.value, tuple(dflt[:n])), Value(vt.value, tuple(val[:n]))))
+        return out
+
+    def update(self, asset: "EffectAsset") -> bool:
+        """EffectProperties::update against the asset's properties; returns whether the store changed."""
+        changed = u32()
+        check(lib.hnb_effect_properties_update(self._h, asset._native(), C.byref(changed)))
+        return bool(changed.value)
+
+    def serialize(self, asset: "EffectAsset") -> bytes:
+        size = u32()
+        check(lib.hnb_effect_properties_serialize(self._h, asset._native(), None, 0, C.byref(size)))
+        blob = C.create_string_buffer(max(1, size.value))
+        check(lib.hnb_effect_properties_serialize(self._h, asset._native(), blob, size.value, C.byref(size)))
+        return blob.raw[:size.value]
 
 
 def particle_layout_of(names: Sequence[str]) -> tuple[list[LayoutField], int, int]:

@@ -114,6 +114,31 @@ HNB_API int32_t hnb_asset_property_layout(const hnb_asset* a, hnb_attr_layout* o
 HNB_API int32_t hnb_asset_serialize_properties(const hnb_asset* a, const char* const* names, const uint32_t* const* words, uint32_t n,
                                                void* blob, uint32_t blob_cap, uint32_t* blob_size);
 
+/* ---- EffectProperties: per-instance property values (reference src/properties.rs:205-454) ---------- */
+typedef struct hnb_effect_properties hnb_effect_properties;
+HNB_API hnb_effect_properties* hnb_effect_properties_create(void);
+HNB_API void hnb_effect_properties_destroy(hnb_effect_properties* p);
+HNB_API uint32_t hnb_effect_properties_len(const hnb_effect_properties* p);
+/** EffectProperties::set (properties.rs:319-341): overwrite, or append a new property whose default is `value`.
+ *  Where the reference asserts (value of another type than the property's) the call returns HNB_ERR_EXPR with the
+ *  reference's message and changes nothing. `words`: the value's 32-bit lanes, as for hnb_module_lit. */
+HNB_API int32_t hnb_effect_properties_set(hnb_effect_properties* p, const char* name, uint32_t value_type, const uint32_t* words);
+/** EffectProperties::set_if_changed (properties.rs:343-376): *changed = 0 when the stored value was already equal. */
+HNB_API int32_t hnb_effect_properties_set_if_changed(hnb_effect_properties* p, const char* name, uint32_t value_type,
+                                                     const uint32_t* words, uint32_t* changed);
+/** EffectProperties::get_stored (properties.rs:305-310): 1 and the value (16 lanes) when present, else 0. */
+HNB_API int32_t hnb_effect_properties_get_stored(const hnb_effect_properties* p, const char* name, uint32_t* value_type, uint32_t* words16);
+/** The i-th PropertyInstance: name (valid until the store changes), type, current value, default value. */
+HNB_API int32_t hnb_effect_properties_get(const hnb_effect_properties* p, uint32_t index, const char** name, uint32_t* value_type,
+                                          uint32_t* value_words16, uint32_t* default_words16);
+/** EffectProperties::update (properties.rs:378-417) against the properties of the asset's module. *changed tells
+ *  whether the store was mutated (what Bevy's change detection would record). */
+HNB_API int32_t hnb_effect_properties_update(hnb_effect_properties* p, const hnb_asset* asset, uint32_t* changed);
+/** EffectProperties::serialize (properties.rs:437-453) with the asset's PropertyLayout: the blob for
+ *  hnb_upload_properties. Same output convention as hnb_asset_serialize_properties. */
+HNB_API int32_t hnb_effect_properties_serialize(const hnb_effect_properties* p, const hnb_asset* asset, void* blob, uint32_t blob_cap,
+                                                uint32_t* blob_size);
+
 typedef struct hnb_generated hnb_generated; /* EffectShaderSources for the simulation passes */
 /** EffectShaderSources::generate. `parent` (or NULL) provides the parent particle layout of a GPU-event child. */
 HNB_API int32_t hnb_asset_generate(const hnb_asset* a, const hnb_asset* parent, uint32_t num_event_bindings, hnb_generated** out);

@@ -577,3 +577,87 @@ def test_asset_transitive_attr():
     names = [f.name for f in asset.particle_layout()[0]]
     assert "age" in names        # direct
     assert "f32_0" in names      # transitive
+
+
+# ---- properties.rs: the EffectProperties store ------------------------------------------------------------------
+def _three_props():
+    return (G.EffectProperties()
+            .with_properties([("a", 3.0), ("b", G.Vec3(0, 0, 0))])
+            .with_properties([("a", 7.0), ("c", G.Vec2(1, 1))]))
+
+
+def test_effect_properties_with_properties():
+    """properties.rs:1166-1203: the second batch overwrites the *value* of `a`, keeps its default, appends `c`."""
+    ep = _three_props()
+    p = ep.properties()
+    assert [x.name for x in p] == ["a", "b", "c"]
+    assert p[0].default_value == G.Value.of(3.0) and p[0].value == G.Value.of(7.0)
+    assert p[1].default_value == p[1].value == G.Vec3(0, 0, 0)
+    assert p[2].default_value == p[2].value == G.Vec2(1, 1)
+
+
+def test_effect_properties_type_mismatches():
+    """properties.rs:1205-1211 `effect_properties_with_properties_type_mismatch`, :1243-1247
+    `effect_properties_set_type_mismatch`: the reference panics, the C ABI reports and changes nothing."""
+    ep = G.EffectProperties().with_properties([("a", 3.0)])
+    with pytest.raises(HanabiError, match="Cannot assign value of type"):
+        ep.with_properties([("a", G.Vec2(1, 1))])
+    with pytest.raises(HanabiError, match="property 'a'"):
+        ep.set("a", G.Vec3(0, 0, 0))
+    assert ep.get_stored("a") == G.Value.of(3.0)
+
+
+def test_effect_properties_get_stored_and_set():
+    """properties.rs:1213-1241 `effect_properties_get_stored`, `effect_properties_set`."""
+    ep = _three_props()
+    assert ep.get_stored("a") is not None and ep.get_stored("b") is not None and ep.get_stored("c") is not None
+    assert ep.get_stored("x") is None
+    ep.set("a", 7.0)
+    ep.set("x", 3.0)                      # unknown name: appended, default = the value
+    assert ep.get_stored("x") == G.Value.of(3.0) and len(ep.properties()) == 4
+    assert ep.set_if_changed("x", 3.0) is False and ep.set_if_changed("x", 4.0) is True
+    assert ep.get_stored("x") == G.Value.of(4.0) and ep.properties()[3].default_value == G.Value.of(3.0)
+
+
+def test_effect_properties_update_against_the_asset():
+    """properties.rs:1249-1392 `effect_properties_update_{empty,added,removed,override,mixed}`; the returned flag is
+    the `last_changed` tick those tests watch."""
+    empty = _asset_with_props([])
+    one = _asset_with_props([("prop1", 32.0)])
+    two = _asset_with_props([("prop1", 32.0), ("prop2", False)])
+    ep = G.EffectProperties()                                   # empty
+    assert ep.update(empty) is False and ep.properties() == []
+    ep = G.EffectProperties()                                   # added
+    assert ep.update(one) is True
+    assert [(p.name, p.default_value, p.value) for p in ep.properties()] == [("prop1", G.Value.of(32.0), G.Value.of(32.0))]
+    ep = G.EffectProperties()                                   # removed
+    ep.set("unknown", G.I32(3))
+    assert ep.update(empty) is True and ep.properties() == []
+    ep = G.EffectProperties()                                   # override: the runtime value wins, nothing changes
+    ep.set("prop1", 5.0)
+    assert ep.update(one) is False
+    assert [(p.name, p.value) for p in ep.properties()] == [("prop1", G.Value.of(5.0))]
+    ep = G.EffectProperties()                                   # mixed: one override, one default
+    ep.set("prop1", 5.0)
+    assert ep.update(two) is True
+    p = ep.properties()
+    assert [(x.name, x.value) for x in p] == [("prop1", G.Value.of(5.0)), ("prop2", G.Value.of(False))]
+    assert p[1].default_value == G.Value.of(False)
+
+
+def test_effect_properties_serialize_store():
+    """properties.rs:1394-1421 `effect_properties_serialize` through the store, and the store against the asset-side
+    serialiser: after update() both produce the same record."""
+    a = _asset_with_props([("a", 3.0), ("b", G.Vec3(1, 1, 1))])
+    ep = G.EffectProperties().with_properties([("a", 3.0), ("b", G.Vec3(1, 1, 1))])
+    blob = ep.serialize(a)
+    off = {f.name: f.offset for f in a.property_layout()[0]}
+    assert blob[off["a"]:off["a"] + 4] == struct.pack("<f", 3.0)
+    assert blob[off["b"]:off["b"] + 12] == struct.pack("<3f", 1.0, 1.0, 1.0)
+    assert blob == a.serialize_properties()
+    # a stored property the layout does not know is skipped; a missing one stays zero until update() adds its default
+    ep2 = G.EffectProperties().with_properties([("zzz", 9.0)])
+    assert ep2.serialize(a) == bytes(len(blob))
+    ep2.update(a)
+    ep2.set("a", 7.5)
+    assert ep2.serialize(a) == a.serialize_properties({"a": 7.5})
