@@ -661,3 +661,17 @@ def test_effect_properties_serialize_store():
     ep2.update(a)
     ep2.set("a", 7.5)
     assert ep2.serialize(a) == a.serialize_properties({"a": 7.5})
+
+
+def test_cast_validity_reference_cases():
+    """graph/expr.rs:4681-4687 `invalid_cast_vector_to_scalar`, :4721-4740 `cast_expr_new`: vector -> scalar is
+    rejected when the operand type is known; a cast of a property (type unknown to `is_valid`) is let through."""
+    m = G.Module()
+    with pytest.raises(HanabiError, match="invalid cast"):
+        m.cast(m.lit(G.Vec2(1, 1)), G.FLOAT)
+    x = m.attr(A.POSITION)
+    assert m.cast(x, G.VEC3) != 0                               # Some(true)
+    with pytest.raises(HanabiError, match="invalid cast"):
+        m.cast(x, G.BOOL)                                       # Some(false)
+    y = m.prop(m.add_property("my_prop", 3.0))
+    assert m.cast(y, G.vt_matrix(2, 3)) != 0                    # None: not decidable at authoring time
