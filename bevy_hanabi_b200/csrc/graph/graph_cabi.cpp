@@ -13,9 +13,6 @@ using namespace hnb_graph;
 
 extern "C" void hnb_set_last_error_(const char* msg);  // defined in runtime/context.cpp
 
-struct hnb_module {
-    Module m;
-};
 struct hnb_asset {
     EffectAsset a;
 };
@@ -98,6 +95,28 @@ void hnb_module_destroy(hnb_module* m) { delete m; }
 
 hnb_expr hnb_module_lit(hnb_module* m, uint32_t value_type, const uint32_t* words) {
     return handle_or_zero([&] { return m->m.lit(value_from(value_type, words)); });
+}
+// Module::get (expr.rs:607-612) flattened: read back one stored expression
+uint32_t hnb_module_len(const hnb_module* m) { return m ? (uint32_t)m->m.size() : 0; }
+int32_t hnb_module_get(const hnb_module* m, hnb_expr e, hnb_expr_info* out) {
+    return guarded([&] {
+        if (!m || !out) throw ExprError(ExprError::GraphEvalError, "NULL argument");
+        const Expr& x = m->m.try_get(e);
+        memset(out, 0, sizeof(*out));
+        out->kind = (uint32_t)x.kind;
+        out->value_type = x.kind == Expr::Literal ? x.literal.type.code : x.type.code;
+        switch (x.kind) {
+            case Expr::BuiltIn: out->op = (uint32_t)x.builtin; break;
+            case Expr::Literal: memcpy(out->literal_words, x.literal.bits, sizeof(out->literal_words)); break;
+            case Expr::Property: out->property = x.property; break;
+            case Expr::Attribute:
+            case Expr::ParentAttribute: out->attribute = attribute_info(x.attribute).name; break;
+            case Expr::Unary: out->op = x.op; out->operands[0] = x.a; break;
+            case Expr::Binary: out->op = x.op; out->operands[0] = x.a; out->operands[1] = x.b; break;
+            case Expr::Ternary: out->op = x.op; out->operands[0] = x.a; out->operands[1] = x.b; out->operands[2] = x.c; break;
+            case Expr::Cast: out->operands[0] = x.a; break;
+        }
+    });
 }
 hnb_expr hnb_module_attr(hnb_module* m, const char* name) {
     return handle_or_zero([&] { return m->m.attr(attr_or_throw(name)); });

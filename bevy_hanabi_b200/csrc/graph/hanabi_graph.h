@@ -288,3 +288,8 @@ struct EffectAsset {
 };
 
 }  // namespace hnb_graph
+
+// The C ABI's opaque module handle (include/hanabi_b200_graph.h), shared by graph_cabi.cpp and node_graph.cpp.
+struct hnb_module {
+    hnb_graph::Module m;
+};

@@ -47,6 +47,20 @@ _SIGS = {
     "hnb_asset_particle_layout": (C.c_int32, [C.c_void_p, P(N.AttrLayout), u32, P(u32), P(u32), P(u32)]),
     "hnb_asset_property_layout": (C.c_int32, [C.c_void_p, P(N.AttrLayout), u32, P(u32), P(u32)]),
     "hnb_asset_serialize_properties": (C.c_int32, [C.c_void_p, P(C.c_char_p), P(P(u32)), u32, C.c_void_p, u32, P(u32)]),
+    "hnb_module_len": (u32, [C.c_void_p]),
+    "hnb_module_get": (C.c_int32, [C.c_void_p, u32, C.c_void_p]),
+    "hnb_node_graph_create": (C.c_void_p, []),
+    "hnb_node_graph_destroy": (None, [C.c_void_p]),
+    "hnb_node_graph_add_node": (u32, [C.c_void_p, u32, C.c_char_p]),
+    "hnb_node_graph_node_count": (u32, [C.c_void_p]),
+    "hnb_node_graph_link": (C.c_int32, [C.c_void_p, u32, u32]),
+    "hnb_node_graph_unlink": (C.c_int32, [C.c_void_p, u32, u32]),
+    "hnb_node_graph_unlink_all": (C.c_int32, [C.c_void_p, u32]),
+    "hnb_node_graph_slots": (C.c_int32, [C.c_void_p, u32, u32, P(u32), u32, P(u32)]),
+    "hnb_node_graph_find_slot": (u32, [C.c_void_p, u32, u32, C.c_char_p]),
+    "hnb_node_graph_slot_info": (C.c_int32, [C.c_void_p, u32, P(C.c_char_p), P(u32), P(u32), P(C.c_int32), P(u32), u32, P(u32)]),
+    "hnb_node_graph_eval_node": (C.c_int32, [C.c_void_p, u32, C.c_void_p, P(u32), u32, P(u32), u32, P(u32)]),
+    "hnb_node_graph_eval_slot": (C.c_int32, [C.c_void_p, C.c_void_p, u32, P(u32)]),
     "hnb_effect_properties_create": (C.c_void_p, []),
     "hnb_effect_properties_destroy": (None, [C.c_void_p]),
     "hnb_effect_properties_len": (u32, [C.c_void_p]),
@@ -267,6 +281,11 @@ class Node:
     prop: str = ""
 
 
+class ExprInfo(C.Structure):
+    _fields_ = [("kind", u32), ("op", u32), ("value_type", u32), ("operands", u32 * 3), ("property", u32), ("attribute", C.c_char_p),
+                ("literal_words", u32 * 16)]
+
+
 class Module:
     """Expression module (reference src/graph/expr.rs:337). Handles are 1-based ints."""
 
@@ -288,6 +307,38 @@ class Module:
             raise HanabiError(N.HNB_ERR_EXPR, N.last_error())
         self.nodes.append(node)
         assert handle == len(self.nodes), "native and recorded graphs out of sync"
+        return handle
+
+    def get(self, handle: int) -> ExprInfo:
+        """Module::get (expr.rs:607-612): the stored expression behind a handle."""
+        info = ExprInfo()
+        check(lib.hnb_module_get(self._h, handle, C.byref(info)))
+        return info
+
+    def _adopt(self, handle: int) -> int:
+        """Bring the recorded mirror up to date with expressions created natively (node graph lowering)."""
+        if handle == 0:
+            raise HanabiError(N.HNB_ERR_EXPR, N.last_error())
+        for h in range(len(self.nodes) + 1, lib.hnb_module_len(self._h) + 1):
+            i = self.get(h)
+            a = tuple(i.operands)
+            if i.kind == 0:
+                node = Node("builtin", op=BUILTINS[i.op], vt=i.value_type)
+            elif i.kind == 1:
+                node = Node("lit", value=Value(i.value_type, tuple(i.literal_words[: vt_count(i.value_type)])))
+            elif i.kind == 2:
+                node = Node("prop", prop=self.properties[i.property - 1][0])
+            elif i.kind in (3, 4):
+                node = Node("attr" if i.kind == 3 else "parent_attr", attr=Attribute.by_name(i.attribute.decode()))
+            elif i.kind == 5:
+                node = Node("unary", op=UNARY[i.op], args=a[:1])
+            elif i.kind == 6:
+                node = Node("binary", op=BINARY[i.op], args=a[:2])
+            elif i.kind == 7:
+                node = Node("ternary", op=TERNARY[i.op], args=a[:3])
+            else:
+                node = Node("cast", args=a[:1], vt=i.value_type)
+            self.nodes.append(node)
         return handle
 
     def lit(self, value) -> int:
@@ -700,6 +751,105 @@ class EffectAsset:
         finally:
             lib.hnb_generated_destroy(g)
         return fx
+
+
+# ---------------------------------------------------------------------------------------------------
+# Node-graph front end (reference src/graph/node.rs)
+# ---------------------------------------------------------------------------------------------------
+NODE_ADD, NODE_SUB, NODE_MUL, NODE_DIV, NODE_ATTRIBUTE, NODE_TIME, NODE_NORMALIZE = range(1, 8)
+
+
+@dataclass(frozen=True)
+class NodeSpec:
+    kind: int
+    attribute: Optional[str] = None
+
+
+def AddNode() -> NodeSpec: return NodeSpec(NODE_ADD)
+def SubNode() -> NodeSpec: return NodeSpec(NODE_SUB)
+def MulNode() -> NodeSpec: return NodeSpec(NODE_MUL)
+def DivNode() -> NodeSpec: return NodeSpec(NODE_DIV)
+def TimeNode() -> NodeSpec: return NodeSpec(NODE_TIME)
+def NormalizeNode() -> NodeSpec: return NodeSpec(NODE_NORMALIZE)
+
+
+def AttributeNode(attr: Optional[AttributeDef] = None) -> NodeSpec:
+    return NodeSpec(NODE_ATTRIBUTE, attr.name if attr is not None else None)
+
+
+@dataclass
+class SlotInfo:
+    name: str
+    node: int
+    is_input: bool
+    value_type: Optional[int]
+    linked: list
+
+
+class Graph:
+    """Graph (node.rs:244-443): nodes, slots and links; NodeId / SlotId are the reference's 1-based ids."""
+
+    def __init__(self):
+        self._h = lib.hnb_node_graph_create()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.hnb_node_graph_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def add_node(self, node: NodeSpec) -> int:
+        nid = lib.hnb_node_graph_add_node(self._h, node.kind, node.attribute.encode() if node.attribute else None)
+        if not nid:
+            raise N.HanabiError(N.HNB_ERR_EXPR, N.last_error())
+        return nid
+
+    def link(self, output: int, input: int):
+        check(lib.hnb_node_graph_link(self._h, output, input))
+
+    def unlink(self, output: int, input: int):
+        check(lib.hnb_node_graph_unlink(self._h, output, input))
+
+    def unlink_all(self, slot: int):
+        check(lib.hnb_node_graph_unlink_all(self._h, slot))
+
+    def _slots(self, node: int, direction: int) -> list:
+        arr, n = (u32 * 8)(), u32()
+        check(lib.hnb_node_graph_slots(self._h, node, direction, arr, 8, C.byref(n)))
+        return list(arr[: n.value])
+
+    def slots(self, node: int) -> list: return self._slots(node, 0)
+    def input_slots(self, node: int) -> list: return self._slots(node, 1)
+    def output_slots(self, node: int) -> list: return self._slots(node, 2)
+
+    def input_slot(self, node: int, name: str) -> Optional[int]:
+        return lib.hnb_node_graph_find_slot(self._h, node, 1, name.encode()) or None
+
+    def output_slot(self, node: int, name: str) -> Optional[int]:
+        return lib.hnb_node_graph_find_slot(self._h, node, 2, name.encode()) or None
+
+    def get_slot_id(self, name: str) -> Optional[int]:
+        return lib.hnb_node_graph_find_slot(self._h, 0, 0, name.encode()) or None
+
+    def slot(self, slot: int) -> SlotInfo:
+        name, node, is_in, vt, linked, n = C.c_char_p(), u32(), u32(), C.c_int32(), (u32 * 64)(), u32()
+        check(lib.hnb_node_graph_slot_info(self._h, slot, C.byref(name), C.byref(node), C.byref(is_in), C.byref(vt), linked, 64, C.byref(n)))
+        return SlotInfo(name.value.decode(), node.value, bool(is_in.value), None if vt.value < 0 else vt.value, list(linked[: n.value]))
+
+    def eval_node(self, node: int, module: "Module", inputs: Sequence[int]) -> list:
+        """Node::eval: handles of the node's outputs in `module`."""
+        arr = (u32 * max(1, len(inputs)))(*inputs)
+        out, n = (u32 * 4)(), u32()
+        check(lib.hnb_node_graph_eval_node(self._h, node, module._h, arr, len(inputs), out, 4, C.byref(n)))
+        return [module._adopt(h) for h in out[: n.value]]
+
+    def eval_slot(self, module: "Module", output_slot: int) -> int:
+        """Lower everything `output_slot` depends on; returns the expression handle."""
+        out = u32()
+        check(lib.hnb_node_graph_eval_slot(self._h, module._h, output_slot, C.byref(out)))
+        return module._adopt(out.value)
 
 
 @dataclass

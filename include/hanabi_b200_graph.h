@@ -45,6 +45,19 @@ HNB_API void hnb_module_destroy(hnb_module* m);
 /** Literal of `value_type` (hnb_value_type); `words` holds its 32-bit lanes (bools: 0 / non-zero; a matCxR: C*R floats,
  *  column by column, like MatrixValue::new in the reference's src/graph/mod.rs:1283-1311). */
 HNB_API hnb_expr hnb_module_lit(hnb_module* m, uint32_t value_type, const uint32_t* words);
+/** One stored expression, as Module::get returns it (expr.rs:607-612). `kind`: 0 built-in, 1 literal, 2 property,
+ *  3 attribute, 4 parent attribute, 5 unary, 6 binary, 7 ternary, 8 cast (the order of the reference's Expr enum,
+ *  expr.rs:910-995, without TextureSample). `op`: the HNB_BUILTIN_* / HNB_UN_* / HNB_BIN_* / HNB_TER_* code. */
+typedef struct hnb_expr_info {
+    uint32_t kind, op;
+    uint32_t value_type;        /* literal type, rand type, cast target */
+    hnb_expr operands[3];
+    hnb_prop property;
+    const char* attribute;      /* static attribute name */
+    uint32_t literal_words[16];
+} hnb_expr_info;
+HNB_API uint32_t hnb_module_len(const hnb_module* m);
+HNB_API int32_t hnb_module_get(const hnb_module* m, hnb_expr e, hnb_expr_info* out);
 HNB_API hnb_expr hnb_module_attr(hnb_module* m, const char* attribute_name);
 HNB_API hnb_expr hnb_module_parent_attr(hnb_module* m, const char* attribute_name);
 /** A matrix property larger than 16 bytes must end up as the last entry of the property layout (the reference's
@@ -113,6 +126,41 @@ HNB_API int32_t hnb_asset_property_layout(const hnb_asset* a, hnb_attr_layout* o
 /** EffectProperties::serialize: `names[i]` is set to the value lanes `words[i]` (others keep their default). */
 HNB_API int32_t hnb_asset_serialize_properties(const hnb_asset* a, const char* const* names, const uint32_t* const* words, uint32_t n,
                                                void* blob, uint32_t blob_cap, uint32_t* blob_size);
+
+/* ---- Node-graph front end of the expression module (reference src/graph/node.rs) ------------------- */
+enum hnb_node_kind {
+    HNB_NODE_ADD = 1,   /* AddNode: lhs, rhs -> result (node.rs:467-506) */
+    HNB_NODE_SUB,       /* SubNode (node.rs:509-549) */
+    HNB_NODE_MUL,       /* MulNode (node.rs:552-592) */
+    HNB_NODE_DIV,       /* DivNode (node.rs:595-635) */
+    HNB_NODE_ATTRIBUTE, /* AttributeNode: -> <attribute name> (node.rs:638-694) */
+    HNB_NODE_TIME,      /* TimeNode: -> time, delta_time (node.rs:697-733) */
+    HNB_NODE_NORMALIZE  /* NormalizeNode: one input expression -> out (node.rs:736-775) */
+};
+typedef struct hnb_node_graph hnb_node_graph; /* Graph, node.rs:244 */
+HNB_API hnb_node_graph* hnb_node_graph_create(void);
+HNB_API void hnb_node_graph_destroy(hnb_node_graph* g);
+/** Graph::add_node (node.rs:284-310): NodeId (1-based), 0 on error. `attribute`: HNB_NODE_ATTRIBUTE only (NULL = position). */
+HNB_API uint32_t hnb_node_graph_add_node(hnb_node_graph* g, uint32_t kind, const char* attribute);
+HNB_API uint32_t hnb_node_graph_node_count(const hnb_node_graph* g);
+/** Graph::link / unlink / unlink_all (node.rs:313-352) on SlotIds (1-based). Where the reference asserts on the slot
+ *  direction the call returns HNB_ERR_EXPR. An input slot keeps one source: linking it again replaces the source. */
+HNB_API int32_t hnb_node_graph_link(hnb_node_graph* g, uint32_t output_slot, uint32_t input_slot);
+HNB_API int32_t hnb_node_graph_unlink(hnb_node_graph* g, uint32_t output_slot, uint32_t input_slot);
+HNB_API int32_t hnb_node_graph_unlink_all(hnb_node_graph* g, uint32_t slot);
+/** Graph::slots / input_slots / output_slots (node.rs:355-420): dir 0 = all, 1 = inputs, 2 = outputs. */
+HNB_API int32_t hnb_node_graph_slots(const hnb_node_graph* g, uint32_t node, uint32_t dir, uint32_t* out, uint32_t cap, uint32_t* n);
+/** Graph::input_slot (dir 1) / output_slot (dir 2) by name; node 0 and dir 0: Graph::get_slot_id. 0 = none. */
+HNB_API uint32_t hnb_node_graph_find_slot(const hnb_node_graph* g, uint32_t node, uint32_t dir, const char* name);
+/** Slot accessors (node.rs:144-198); *value_type = -1 for an untyped slot. */
+HNB_API int32_t hnb_node_graph_slot_info(const hnb_node_graph* g, uint32_t slot, const char** name, uint32_t* node, uint32_t* is_input,
+                                         int32_t* value_type, uint32_t* linked, uint32_t cap, uint32_t* n_linked);
+/** Node::eval (node.rs:458-463): lower one node into `m` from explicit input expressions. */
+HNB_API int32_t hnb_node_graph_eval_node(const hnb_node_graph* g, uint32_t node, hnb_module* m, const hnb_expr* inputs, uint32_t n_inputs,
+                                         hnb_expr* outputs, uint32_t cap, uint32_t* n_outputs);
+/** Lower everything an output slot depends on (each node once, in dependency order; unlinked inputs and cycles
+ *  are errors). The reference leaves this walk to the caller. */
+HNB_API int32_t hnb_node_graph_eval_slot(hnb_node_graph* g, hnb_module* m, uint32_t output_slot, hnb_expr* out);
 
 /* ---- EffectProperties: per-instance property values (reference src/properties.rs:205-454) ---------- */
 typedef struct hnb_effect_properties hnb_effect_properties;
