@@ -95,7 +95,7 @@ __global__ void k_prefix_sum(StaticTables T) {
         T.prefix_sum[i] = sum;
         T.tile_prefix[i] = tiles;
         sum += count;
-        tiles += (count + tile - 1u) / tile;
+        tiles += hnb_tile_count(count, tile);
     }
     bi->total_update_count = sum;
     T.dispatch_args[batch_index * 3u + 0u] = (sum + 63u) >> 6u;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T) {
         u32 a = 0u, t = 0u;
         if (i < count) {
             a = indirect_one_effect(T, offset + i);
-            t = (a + tile - 1u) / tile;
+            t = hnb_tile_count(a, tile);
         }
         // block-wide exclusive scan of (a, t)
         u32 ia = a, it = t;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_tile_prefix(StaticTables T, u32 
         u32 t = 0u;
         if (i < count) {
             const Spawner* sp = &T.spawners[bi->spawner_base + i];
-            t = (T.metadata[sp->effect_metadata_index].max_update + tile - 1u) / tile;
+            t = hnb_tile_count(T.metadata[sp->effect_metadata_index].max_update, tile);
         }
         u32 it = t;
 #pragma unroll

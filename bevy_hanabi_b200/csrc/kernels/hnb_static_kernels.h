@@ -15,7 +15,7 @@ struct StaticTables {
     u32* prefix_sum;
     u32* tile_prefix;
     BatchInfo* batch_infos;
-    const u32* batch_tile_size;  // per batch: rows per update tile of the batch's compiled effect
+    const u32* batch_tile_size;  // per batch: tile size word (hnb_tile_word) of the batch's compiled effect and launch
     u32* dispatch_args;      // DispatchIndirectArgs rows as u32[3]
     u32* batch_tiles;
     u32* tickets;

@@ -240,12 +240,24 @@ def build_emulated_effect(lowered, allow_events: bool = False) -> C.CDLL:
     return lib
 
 
+def tile_count(rows, word: int):
+    """hnb_tile_count (hnb_tables.cuh) restated: tiles of an instance with `rows` rows under a tile size word."""
+    S, f, w = word & 0xFFFF, (word >> 16) & 15, word >> 20
+    rows = np.asarray(rows, dtype=np.int64)
+    if w == 0:
+        return (rows + S - 1) // S
+    n_big = (rows - np.minimum(rows, w * S)) // S
+    s = S >> f
+    return n_big + (rows - n_big * S + s - 1) // s
+
+
 class EmuWorld:
     """One batch (all instances of `ref`) simulated by the emulated kernels, starting from `ref`'s current state."""
 
-    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None, static_lib=None):
+    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None, static_lib=None, taper=None):
         """`static_lib` (tests/static_emu.build()): run the real bookkeeping and ribbon-sort kernels too instead of their
-        restatements."""
+        restatements. `taper` = (taper length in big tiles, shift): tile size word with a taper (needs a source generated
+        under HNB_TILE_TAPER, i.e. `#define HNB_TILE_TAPER 1`)."""
         self.ref, self.lib = ref, build_emulated_effect(lowered)
         self.static_lib = static_lib
         self.ribbons = bool(lowered.flags & (1 << 5))  # HNB_EFFECT_RIBBONS
@@ -256,6 +268,11 @@ class EmuWorld:
         k = self.lib.emu_tile_k()
         assert chunks * k <= self.lib.emu_rows_per_lane()
         self.tile = 32 * k * chunks
+        self.tile_word, small = self.tile, self.tile
+        if taper:
+            w, f = taper
+            assert chunks % (1 << f) == 0 and "#define HNB_TILE_TAPER 1" in lowered.generate_source()
+            self.tile_word, small = self.tile | (f << 16) | (w << 20), self.tile >> f
         self.update_ctas = update_ctas
         u32 = np.uint32
         self.planes = [np.zeros(rows * 8, dtype=u32) for _ in range(16)]          # room for 32-byte-wide (sector) columns
@@ -270,11 +287,11 @@ class EmuWorld:
         self.batch_info = (O.BatchInfo * 1)(O.BatchInfo(0, 0, 0, 0, 0, n))
         self.batch_tiles = np.zeros(1, dtype=u32)
         self.ticket = np.zeros(1, dtype=u32)
-        self.tile_state = np.zeros(rows // self.tile + n + 2, dtype=np.uint64)
+        self.tile_state = np.zeros(rows // small + n + 2, dtype=np.uint64)
         self.frame = np.zeros(16, dtype=u32)                                       # FrameHeader: SimParams (7 words) | epoch | num_batches
         self.dispatch = np.zeros(3, dtype=u32)
         self.spawn_range = np.zeros(n, dtype=u32)
-        self.tile_size = np.array([self.tile], dtype=u32)
+        self.tile_size = np.array([self.tile_word], dtype=u32)
         self.epoch = 0
         self.props = None
         self.props_stride = 0
@@ -298,7 +315,7 @@ class EmuWorld:
         for p in range(16):
             b.planes[p] = ptr(self.planes[p])
         b.ping, b.pong, b.dead = ptr(self.cols[0]), ptr(self.cols[1]), ptr(self.cols[2])
-        b.capacity, b.properties_stride, b.tile_rows = self.rows, self.props_stride, self.tile
+        b.capacity, b.properties_stride, b.tile_rows = self.rows, self.props_stride, self.tile_word
 
     def frame_step(self, orc, sim, spawns, seeds):
         """One simulate(): init kernel -> bookkeeping (restated) -> update kernel. `sim`: the oracle world's SimParams."""
@@ -337,7 +354,7 @@ class EmuWorld:
                              self.prefix_sum.ctypes.data_as(u32p), None, 0)
             alive = self.prefix_sum.copy()
             orc.orc_prefix_sum(self.batch_info, 1, self.prefix_sum.ctypes.data_as(u32p), self.dispatch.ctypes.data_as(u32p))
-            tiles = (alive + self.tile - 1) // self.tile
+            tiles = tile_count(alive, self.tile_word)
             self.tile_prefix[:n] = np.concatenate([[0], np.cumsum(tiles)[:-1]]) if n else []
             self.tile_prefix[n] = tiles.sum()
             self.batch_tiles[0] = tiles.sum()
