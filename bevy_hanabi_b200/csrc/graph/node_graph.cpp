@@ -80,6 +80,11 @@ std::vector<ExprHandle> eval_node(const NodeRec& n, Module& m, const std::vector
     }
 }
 
+template <typename G> G& checked(G* g) {
+    if (!g) throw ExprError(ExprError::GraphEvalError, "graph is NULL");
+    return *g;
+}
+
 template <typename F> int32_t guarded(F&& f) {
     try {
         f();
@@ -166,7 +171,7 @@ uint32_t hnb_node_graph_node_count(const hnb_node_graph* g) { return g ? (uint32
 // Graph::link (node.rs:313-321); the reference asserts on the slot directions, here HNB_ERR_EXPR
 int32_t hnb_node_graph_link(hnb_node_graph* g, uint32_t output, uint32_t input) {
     return guarded([&] {
-        Slot& o = g->slot(output);
+        Slot& o = checked(g).slot(output);
         Slot& i = g->slot(input);
         if (o.def.is_input) throw ExprError(ExprError::GraphEvalError, "link: the first slot must be an output");
         if (!i.def.is_input) throw ExprError(ExprError::GraphEvalError, "link: the second slot must be an input");
@@ -177,7 +182,7 @@ int32_t hnb_node_graph_link(hnb_node_graph* g, uint32_t output, uint32_t input) 
 // Graph::unlink (node.rs:330-338)
 int32_t hnb_node_graph_unlink(hnb_node_graph* g, uint32_t output, uint32_t input) {
     return guarded([&] {
-        Slot& o = g->slot(output);
+        Slot& o = checked(g).slot(output);
         Slot& i = g->slot(input);
         if (o.def.is_input) throw ExprError(ExprError::GraphEvalError, "unlink: the first slot must be an output");
         auto it = std::find(o.linked.begin(), o.linked.end(), input);
@@ -191,7 +196,7 @@ int32_t hnb_node_graph_unlink(hnb_node_graph* g, uint32_t output, uint32_t input
 int32_t hnb_node_graph_unlink_all(hnb_node_graph* g, uint32_t slot_id) {
     return guarded([&] {
         std::vector<uint32_t> linked;
-        linked.swap(g->slot(slot_id).linked);
+        linked.swap(checked(g).slot(slot_id).linked);
         for (uint32_t r : linked) {
             Slot& remote = g->slot(r);
             if (remote.def.is_input) remote.linked.clear();
@@ -205,7 +210,7 @@ int32_t hnb_node_graph_unlink_all(hnb_node_graph* g, uint32_t slot_id) {
 // Graph::slots / input_slots / output_slots (node.rs:355-420): dir 0 = all, 1 = inputs, 2 = outputs
 int32_t hnb_node_graph_slots(const hnb_node_graph* g, uint32_t node, uint32_t dir, uint32_t* out, uint32_t cap, uint32_t* n) {
     return guarded([&] {
-        g->node(node);
+        checked(g).node(node);
         uint32_t k = 0;
         for (const Slot& s : g->slots) {
             if (s.node_id != node) continue;
@@ -230,7 +235,7 @@ uint32_t hnb_node_graph_find_slot(const hnb_node_graph* g, uint32_t node, uint32
 int32_t hnb_node_graph_slot_info(const hnb_node_graph* g, uint32_t slot_id, const char** name, uint32_t* node, uint32_t* is_input,
                                  int32_t* value_type, uint32_t* linked, uint32_t cap, uint32_t* n_linked) {
     return guarded([&] {
-        const Slot& s = g->slot(slot_id);
+        const Slot& s = checked(g).slot(slot_id);
         if (name) *name = s.def.name.c_str();
         if (node) *node = s.node_id;
         if (is_input) *is_input = s.def.is_input ? 1u : 0u;
@@ -245,7 +250,7 @@ int32_t hnb_node_graph_eval_node(const hnb_node_graph* g, uint32_t node, hnb_mod
     return guarded([&] {
         if (!m) throw ExprError(ExprError::GraphEvalError, "module is NULL");
         std::vector<ExprHandle> in(inputs, inputs + (inputs ? n_inputs : 0));
-        const std::vector<ExprHandle> out = eval_node(g->node(node), m->m, in);
+        const std::vector<ExprHandle> out = eval_node(checked(g).node(node), m->m, in);
         for (uint32_t i = 0; outputs && i < out.size() && i < cap; ++i) outputs[i] = out[i];
         if (n_outputs) *n_outputs = (uint32_t)out.size();
     });

@@ -104,7 +104,7 @@ int32_t hnb_sim_clock_set_virtual_relative_speed(hnb_sim_clock* c, double ratio)
     c->virt_relative_speed = ratio;
     return HNB_OK;
 }
-void hnb_sim_clock_set_virtual_paused(hnb_sim_clock* c, uint32_t paused) { c->virt_paused = paused != 0; }
+void hnb_sim_clock_set_virtual_paused(hnb_sim_clock* c, uint32_t paused) { if (c) c->virt_paused = paused != 0; }
 int32_t hnb_sim_clock_set_max_delta_ns(hnb_sim_clock* c, uint64_t ns) {
     if (!c) return bad("clock is NULL");
     if (ns == 0) return bad("tried to set max delta to zero");
@@ -120,12 +120,12 @@ int32_t hnb_sim_clock_set_relative_speed(hnb_sim_clock* c, double ratio) {
     c->relative_speed = ratio;
     return HNB_OK;
 }
-void hnb_sim_clock_pause(hnb_sim_clock* c) { c->paused = true; }     // time.rs:144
-void hnb_sim_clock_unpause(hnb_sim_clock* c) { c->paused = false; }  // time.rs:149
-uint32_t hnb_sim_clock_is_paused(const hnb_sim_clock* c) { return c->paused ? 1u : 0u; }                   // time.rs:154
-uint32_t hnb_sim_clock_was_paused(const hnb_sim_clock* c) { return c->effective_speed == 0.0 ? 1u : 0u; }  // time.rs:159
-double hnb_sim_clock_relative_speed(const hnb_sim_clock* c) { return c->relative_speed; }                  // time.rs:117
-double hnb_sim_clock_effective_speed(const hnb_sim_clock* c) { return c->effective_speed; }                // time.rs:127
+void hnb_sim_clock_pause(hnb_sim_clock* c) { if (c) c->paused = true; }     // time.rs:144
+void hnb_sim_clock_unpause(hnb_sim_clock* c) { if (c) c->paused = false; }  // time.rs:149
+uint32_t hnb_sim_clock_is_paused(const hnb_sim_clock* c) { return c && c->paused ? 1u : 0u; }                   // time.rs:154
+uint32_t hnb_sim_clock_was_paused(const hnb_sim_clock* c) { return c && c->effective_speed == 0.0 ? 1u : 0u; }  // time.rs:159
+double hnb_sim_clock_relative_speed(const hnb_sim_clock* c) { return c ? c->relative_speed : 0.0; }                  // time.rs:117
+double hnb_sim_clock_effective_speed(const hnb_sim_clock* c) { return c ? c->effective_speed : 0.0; }                // time.rs:127
 
 // One frame: bevy's time_system (Real, then Virtual from the real delta) followed by
 // effect_simulation_time_system (time.rs:164-183). Nothing is modified when a product overflows.
