@@ -380,6 +380,13 @@ class Module:
     def cast(self, e: int, vt: int) -> int:
         return self._push(lib.hnb_module_cast(self._h, e, vt), Node("cast", args=(e,), vt=vt))
 
+    def get_property_by_name(self, name: str) -> Optional[int]:
+        """Module::get_property_by_name: the property handle, or None."""
+        for i, (n, _) in enumerate(self.properties):
+            if n == name:
+                return i + 1
+        return None
+
     def is_const(self, e: int) -> bool:
         r = lib.hnb_module_is_const(self._h, e)
         if r < 0:
@@ -410,6 +417,23 @@ for _op in TERNARY:
 # ---------------------------------------------------------------------------------------------------
 # Fluent API (reference ExprWriter / WriterExpr, src/graph/expr.rs:2399-4127)
 # ---------------------------------------------------------------------------------------------------
+def _install_module_operator_methods():
+    """The reference generates one Module method per operator (`impl_module_unary!` / `_binary!` / `_ternary!`,
+    expr.rs: `m.add(l, r)`, `m.normalize(e)`, `m.mix(a, b, t)` ...). Same names here, on top of unary() / binary() / ternary()."""
+    for op in UNARY:
+        if not hasattr(Module, op):
+            setattr(Module, op, (lambda _op: lambda self, e: self.unary(_op, e))(op))
+    for op in BINARY:
+        if not hasattr(Module, op):
+            setattr(Module, op, (lambda _op: lambda self, l, r: self.binary(_op, l, r))(op))
+    for op in TERNARY:
+        if not hasattr(Module, op):
+            setattr(Module, op, (lambda _op: lambda self, a, b, c: self.ternary(_op, a, b, c))(op))
+
+
+_install_module_operator_methods()
+
+
 class WriterExpr:
     def __init__(self, writer: "ExprWriter", handle: int):
         self.writer = writer

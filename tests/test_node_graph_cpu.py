@@ -152,3 +152,21 @@ def test_graph_authored_effect_equals_the_hand_written_one():
     f1, f2 = a1.generate(), a2.generate()
     assert f1.update_code == f2.update_code and f1.init_code == f2.init_code
     assert "(particle.position) + ((particle.velocity) * (sim_params.delta_time))" in f1.update_code
+
+
+def test_module_operator_methods_like_the_reference():
+    """`impl_module_unary!` / `_binary!` / `_ternary!` (graph/expr.rs): one Module method per operator."""
+    m = G.Module()
+    a, b = m.lit(3.), m.lit(2.)
+    assert m.eval(m.add(a, b))[0] == "(3.f) + (2.f)"
+    assert m.eval(m.max(a, b))[0] == "max(3.f, 2.f)"
+    assert m.eval(m.mix(a, b, m.lit(0.5)))[0] == "mix(3.f, 2.f, 0.5f)"
+    v = m.lit(G.Vec3(1, 2, 3))
+    assert m.eval(m.normalize(v))[0] == "normalize(vec3<f32>(1.f,2.f,3.f))"
+    assert m.eval(m.y(v))[0] == "vec3<f32>(1.f,2.f,3.f).y"
+    for op in G.UNARY + G.BINARY + G.TERNARY:
+        assert callable(getattr(G.Module, op)), op
+    p = m.add_property("speed", 4.0)
+    assert m.get_property_by_name("speed") == p and m.get_property_by_name("nope") is None
+    info = m.get(a)
+    assert info.kind == 1 and info.value_type == G.FLOAT                 # Module::get: a literal
