@@ -4,6 +4,7 @@ csrc/graph/sim_clock.cpp."""
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 from . import _native as N
 from ._native import check, lib
@@ -108,6 +109,68 @@ class SpawnerSettings:
         self.c.emit_on_start = int(v)
         return self
 
+    # accessors of the reference (spawn.rs:362-615); CpuValue<f32> is a float (Single) or a (lo, hi) pair (Uniform)
+    @staticmethod
+    def _value(lo, hi):
+        return lo if lo == hi else (lo, hi)
+
+    def set_emit_on_start(self, v: bool):
+        self.c.emit_on_start = int(v)
+
+    def emits_on_start(self) -> bool:
+        return bool(self.c.emit_on_start)
+
+    def set_count(self, count):
+        self.c.count_lo, self.c.count_hi = _cv(count)
+
+    def with_count(self, count):
+        self.set_count(count)
+        return self
+
+    def count(self):
+        return self._value(self.c.count_lo, self.c.count_hi)
+
+    def set_spawn_duration(self, spawn_duration):
+        self.c.spawn_duration_lo, self.c.spawn_duration_hi = _cv(spawn_duration)
+
+    def with_spawn_duration(self, spawn_duration):
+        self.set_spawn_duration(spawn_duration)
+        return self
+
+    def spawn_duration(self):
+        return self._value(self.c.spawn_duration_lo, self.c.spawn_duration_hi)
+
+    def set_period(self, period):
+        """spawn.rs:538-545: only finiteness is asserted here (positivity is SpawnerSettings::new's check)."""
+        lo, hi = _cv(period)
+        if not (math.isfinite(lo) and math.isfinite(hi)):
+            raise N.HanabiError(N.HNB_ERR_INVALID_ARG, f"`period` {period!r} has an infinite bound. If upgrading from a previous version, "
+                                                        "use `cycle_count = 1` instead for a single-cycle burst.")
+        self.c.period_lo, self.c.period_hi = lo, hi
+
+    def with_period(self, period):
+        self.set_period(period)
+        return self
+
+    def period(self):
+        return self._value(self.c.period_lo, self.c.period_hi)
+
+    def set_cycle_count(self, cycle_count: int):
+        self.c.cycle_count = int(cycle_count)
+
+    def with_cycle_count(self, cycle_count: int):
+        self.set_cycle_count(cycle_count)
+        return self
+
+    def cycle_count(self) -> int:
+        return self.c.cycle_count
+
+    def set_starts_active(self, v: bool):
+        self.c.starts_active = int(v)
+
+    def starts_active(self) -> bool:
+        return bool(self.c.starts_active)
+
     def is_once(self):
         return self.c.cycle_count == 1
 
@@ -134,6 +197,18 @@ class EffectSpawner:
 
     def reset(self):
         lib.hnb_effect_spawner_reset(self._h)
+
+    def with_active(self, active: bool) -> "EffectSpawner":   # spawn.rs:723
+        lib.hnb_effect_spawner_set_active(self._h, int(active))
+        return self
+
+    # per-cycle accessors of the reference (spawn.rs:730-800)
+    def cycle_time(self) -> float: return self.state.cycle_time
+    def cycle_spawn_duration(self) -> float: return self.state.cycle_spawn_duration
+    def cycle_period(self) -> float: return self.state.cycle_period
+    def cycle_ratio(self) -> float: return self.state.cycle_ratio
+    def cycle_spawn_count(self) -> float: return self.state.cycle_spawn_count
+    def completed_cycle_count(self) -> int: return self.state.completed_cycle_count
 
     @property
     def state(self) -> SpawnerState:

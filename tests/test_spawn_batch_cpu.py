@@ -202,3 +202,25 @@ def test_uniform_range_is_ordered():
         sp = EffectSpawner(SpawnerSettings.once(bounds), rng_seed=5)
         n = sp.tick(1.0)
         assert 1 <= n <= 3
+
+
+def test_spawner_settings_accessors_of_the_reference():
+    """spawn.rs:362-615: with_* / set_* / getters of SpawnerSettings, spawn.rs:723-800 on EffectSpawner."""
+    s = SpawnerSettings.rate(5.0)
+    assert s.count() == 5.0 and s.spawn_duration() == 1.0 and s.period() == 1.0 and s.cycle_count() == 0 and s.is_forever()
+    s = s.with_count((2.0, 4.0)).with_spawn_duration(0.5).with_period((1.0, 3.0)).with_cycle_count(2)
+    assert s.count() == (2.0, 4.0) and s.spawn_duration() == 0.5 and s.period() == (1.0, 3.0) and s.cycle_count() == 2
+    assert not s.is_once() and not s.is_forever()
+    assert s.starts_active() and s.emits_on_start()
+    s.set_starts_active(False); s.set_emit_on_start(False)
+    assert not s.starts_active() and not s.emits_on_start()
+    with pytest.raises(HanabiError, match="infinite bound"):        # spawn.rs:518-545
+        s.with_period(float("inf"))
+    with pytest.raises(HanabiError, match="infinite bound"):
+        s.set_period((1.0, float("inf")))
+    assert s.period() == (1.0, 3.0)
+    sp = EffectSpawner(SpawnerSettings(3.0, 3.0, 10.0, 2)).with_active(True)
+    assert sp.tick(2.0) == 2
+    assert (sp.cycle_time(), sp.cycle_spawn_duration(), sp.cycle_period(), sp.cycle_spawn_count(), sp.completed_cycle_count()) == (2.0, 3.0, 10.0, 3.0, 0)
+    assert abs(sp.cycle_ratio() - 0.2) < 1e-7
+    assert EffectSpawner(SpawnerSettings.once(3.0)).with_active(False).tick(1.0) == 0
