@@ -649,6 +649,7 @@ def EmitSpawnEventModifier(condition: int, count, child_index: int) -> Modifier:
 # EffectAsset
 # ---------------------------------------------------------------------------------------------------
 GLOBAL, LOCAL = 0, 1
+WHEN_VISIBLE, ALWAYS = 0, 1  # SimulationCondition (asset.rs:54-68); WhenVisible is the default
 MOTION_NONE, MOTION_PRE_UPDATE, MOTION_POST_UPDATE = 0, 1, 2
 
 
@@ -672,6 +673,7 @@ class EffectAsset:
         self.motion_integration = motion_integration
         self.init_modifiers: list[Modifier] = []
         self.update_modifiers: list[Modifier] = []
+        self.simulation_condition = WHEN_VISIBLE
         self._h = None
 
     # builder API like the reference (`.init(m)`, `.update(m)`)
@@ -683,6 +685,32 @@ class EffectAsset:
     def update(self, m: Modifier) -> "EffectAsset":
         self.update_modifiers.append(m)
         self._drop_native()
+        return self
+
+    def add_modifier(self, context: str, m: Modifier) -> "EffectAsset":
+        """EffectAsset::add_modifier (asset.rs:506-520): `context` is "init" or "update" (render modifiers are outside
+        the simulation path); the modifier's allowed contexts are checked when the native asset is built."""
+        if context not in ("init", "update"):
+            raise ValueError("context must be 'init' or 'update'")
+        return self.init(m) if context == "init" else self.update(m)
+
+    def modifiers(self) -> list:
+        """EffectAsset::modifiers: init modifiers, then update modifiers."""
+        return list(self.init_modifiers) + list(self.update_modifiers)
+
+    def properties(self) -> list:
+        """EffectAsset::properties: (name, default value) of the module's properties."""
+        return list(self.module.properties)
+
+    def with_name(self, name: str) -> "EffectAsset":
+        self.name = name
+        self._drop_native()
+        return self
+
+    def with_simulation_condition(self, condition: int) -> "EffectAsset":
+        """SimulationCondition (asset.rs:54): WHEN_VISIBLE / ALWAYS. Read by the host's spawner tick (spawn.rs:970-979:
+        an invisible WHEN_VISIBLE effect is not ticked); it does not change the generated code."""
+        self.simulation_condition = condition
         return self
 
     def with_simulation_space(self, space: int) -> "EffectAsset":

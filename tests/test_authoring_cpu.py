@@ -675,3 +675,19 @@ def test_cast_validity_reference_cases():
         m.cast(x, G.BOOL)                                       # Some(false)
     y = m.prop(m.add_property("my_prop", 3.0))
     assert m.cast(y, G.vt_matrix(2, 3)) != 0                    # None: not decidable at authoring time
+
+
+def test_effect_asset_builder_names_of_the_reference():
+    """asset.rs:430-600: with_name / with_simulation_condition / add_modifier / modifiers / properties."""
+    w = G.ExprWriter()
+    w.add_property("speed", 2.0)
+    zero = w.lit(G.Vec3(0, 0, 0))
+    a = (G.EffectAsset(32, w.module).with_name("named").with_simulation_condition(G.ALWAYS)
+         .add_modifier("init", G.SetAttributeModifier(A.POSITION, zero))
+         .add_modifier("update", G.AccelModifier(w.lit(G.Vec3(0, -1, 0)))))
+    assert a.name == "named" and a.simulation_condition == G.ALWAYS
+    assert [m.kind for m in a.modifiers()] == ["set_attribute", "accel"]
+    assert a.properties() == [("speed", G.Value.of(2.0))]
+    assert a.generate().name == "named"
+    with pytest.raises(ValueError):
+        a.add_modifier("render", G.AccelModifier(zero))
