@@ -22,9 +22,12 @@ MAIN = r"""
 int main(int argc, char** argv) {
     const uint32_t rows = 6000, chunks = argc > 1 ? atoi(argv[1]) : 2, ctas = argc > 2 ? atoi(argv[2]) : 2, frames = 4;
     const uint32_t tile = 32u * HNB_TILE_K * chunks;
+    // argv[3], argv[4]: taper length (big tiles) and shift of the tile size word (kernel generated under HNB_TILE_TAPER)
+    const uint32_t taper_tiles = argc > 4 ? atoi(argv[3]) : 0, shift = argc > 4 ? atoi(argv[4]) : 0;
+    const uint32_t tile_word = hnb::hnb_tile_word(tile, shift, taper_tiles), small = tile >> shift;
     std::vector<float4> plane0(rows), plane1(rows);
     std::vector<uint32_t> ping(rows), pong(rows), dead(rows), tile_prefix(2), prefix_sum(1), spawn_prefix(1), batch_tiles(1), ticket(1), draw(5);
-    std::vector<unsigned long long> states(rows / tile + 4);
+    std::vector<unsigned long long> states(rows / small + 4);
     uint32_t s = 12345u;
     auto rnd = [&] { s = s * 1664525u + 1013904223u; return float(s >> 8) / 16777216.0f; };
     const uint32_t alive0 = 5600;
@@ -47,14 +50,14 @@ int main(int argc, char** argv) {
     b.frame = &frame; b.spawners = &sp; b.spawn_prefix = spawn_prefix.data(); b.prefix_sum = prefix_sum.data(); b.tile_prefix = tile_prefix.data();
     b.batch_info = &bi; b.batch_tiles = batch_tiles.data(); b.ticket = ticket.data(); b.tile_state = states.data(); b.metadata = &md; b.draw_args = draw.data();
     b.planes[0] = plane0.data(); b.planes[1] = plane1.data(); b.ping = ping.data(); b.pong = pong.data(); b.dead = dead.data();
-    b.capacity = rows; b.tile_rows = tile;
+    b.capacity = rows; b.tile_rows = tile_word;
     for (uint32_t f = 0; f < frames; ++f) {
         frame.epoch = f + 1; frame.sim.time = f * frame.sim.delta_time;
         // vfx_indirect + vfx_prefix_sum for one instance (restated; the emulation covers the per-particle kernels)
         draw[1] = 0; md.max_update = md.alive_count; md.max_spawn = md.capacity - md.alive_count;
         md.indirect_write_index = 1u - md.indirect_write_index; sp.render_indirect_read_index = md.indirect_write_index;
         prefix_sum[0] = 0; bi.total_update_count = md.alive_count;
-        const uint32_t tiles = (md.alive_count + tile - 1) / tile;
+        const uint32_t tiles = hnb::hnb_tile_count(md.alive_count, tile_word);
         tile_prefix[0] = 0; tile_prefix[1] = tiles; batch_tiles[0] = tiles; ticket[0] = 0;
         emu_update(&b, ctas, 64 * 1024);
         printf("frame %u: updated %u -> alive %u (instance_count %u)\n", f, md.max_update, md.alive_count, draw[1]);
@@ -220,6 +223,26 @@ def main():
         p = subprocess.run([str(exe), str(chunks), str(ctas)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
         races = p.stderr.count("WARNING: ThreadSanitizer: data race")
         print(f"chunks={chunks} ctas={ctas}: exit {p.returncode}, {races} data-race reports")
+        print(p.stdout.strip())
+        if races:
+            print(p.stderr[:6000])
+        rc |= p.returncode or races
+    # the tapered kernel (HNB_TILE_TAPER, experimental): big tiles, then small ones, in one look-back chain
+    import os
+    os.environ["HNB_TILE_TAPER"] = "100"
+    src = recipes.c5_lowered().generate_source()
+    os.environ.pop("HNB_TILE_TAPER")
+    assert "#define HNB_TILE_TAPER 1" in src
+    for old, new in K.SUBSTITUTIONS:
+        assert src.count(old) == 1
+        src = src.replace(old, new)
+    cpp, exe = out / "tsan_c5_taper.cpp", out / "tsan_c5_taper"
+    cpp.write_text(K.PRELUDE + src + K.DRIVER + MAIN)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w", str(cpp), "-o", str(exe)], check=True)
+    for chunks, ctas, w, f in ((4, 2, 3, 2), (2, 2, 5, 1)):
+        p = subprocess.run([str(exe), str(chunks), str(ctas), str(w), str(f)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
+        races = p.stderr.count("WARNING: ThreadSanitizer: data race")
+        print(f"taper: chunks={chunks} ctas={ctas} taper_tiles={w} shift={f}: exit {p.returncode}, {races} data-race reports")
         print(p.stdout.strip())
         if races:
             print(p.stderr[:6000])
