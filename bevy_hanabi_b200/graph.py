@@ -162,6 +162,14 @@ class Value:
     def floats(self):
         return [struct.unpack("<f", struct.pack("<I", w))[0] for w in self.words]
 
+    @staticmethod
+    def splat(scalar, count: int) -> "Value":
+        """VectorValue::splat (graph/mod.rs:572-590): a vector of `count` copies of a scalar value."""
+        v = Value.of(scalar)
+        if v.vt not in (BOOL, FLOAT, INT, UINT) or not 2 <= count <= 4:
+            raise ValueError("splat takes a scalar and a count of 2, 3 or 4")
+        return Value(vt_make(vt_elem(v.vt), count), v.words * count)
+
 
 def U32(x: int) -> Value:
     return Value(UINT, (x & 0xFFFFFFFF,))

@@ -691,3 +691,20 @@ def test_effect_asset_builder_names_of_the_reference():
     assert a.generate().name == "named"
     with pytest.raises(ValueError):
         a.add_modifier("render", G.AccelModifier(zero))
+
+
+def test_value_splat():
+    """graph/mod.rs:2350-2408 `splat`: VectorValue::splat for every scalar type and vector width."""
+    for c in (2, 3, 4):
+        b = G.Value.splat(True, c)
+        assert G.vt_elem(b.vt) == "b" and G.vt_count(b.vt) == c and b == G.Value.of([True] * c)
+        f = G.Value.splat(3.4, c)
+        assert G.vt_elem(f.vt) == "f" and G.vt_count(f.vt) == c and f == G.Value.of([3.4] * c)
+        i = G.Value.splat(G.I32(-46458), c)
+        assert G.vt_elem(i.vt) == "i" and G.vt_count(i.vt) == c and i == G.IVec(*[-46458] * c)
+        u = G.Value.splat(G.U32(46458), c)
+        assert G.vt_elem(u.vt) == "u" and G.vt_count(u.vt) == c and u == G.UVec(*[46458] * c)
+    with pytest.raises(ValueError):
+        G.Value.splat(G.Vec2(1, 2), 2)
+    with pytest.raises(ValueError):
+        G.Value.splat(1.0, 5)
