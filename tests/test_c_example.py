@@ -39,3 +39,22 @@ def test_c_example_runs_on_the_gpu():
     lines = [l for l in p.stdout.splitlines() if l.startswith("frame")]
     alive = [int(l.rsplit(" ", 1)[1]) for l in lines]
     assert max(alive) >= 1000 and min(alive) >= 0
+
+
+def test_host_producers_example_runs_without_a_gpu():
+    """examples/host_producers_c_api.c: node graph, EffectProperties store and the EffectSimulation clock driven from plain C
+    (no context, no device): the new entry points are valid C, link, and produce the tables the runtime consumes."""
+    exe = ROOT / "build" / "host_producers_c_api"
+    (ROOT / "build").mkdir(exist_ok=True)
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "host_producers_c_api.c"), f"-L{ROOT / 'bevy_hanabi_b200'}",
+           "-lhanabi_b200", f"-Wl,-rpath,{ROOT / 'bevy_hanabi_b200'}", "-lm", "-o", str(exe)]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = p.stdout
+    assert "graph lowers to: (particle.position) + ((particle.velocity) * (sim_params.delta_time))" in out
+    assert "update code: particle.position = (particle.position) + ((particle.velocity) * (sim_params.delta_time));" in out
+    assert "properties: 1 stored, changed 1, blob 4 bytes, speed = 7.5" in out
+    assert "type mismatch refused: Cannot assign value of type vec3<f32> to property 'speed' of type f32" in out
+    assert "frame 2: delta_time 0 " in out and "was_paused 1" in out
+    assert "negative speed refused: tried to go back in time" in out
