@@ -111,6 +111,8 @@ template <typename Ptr> HNB_DI u32 hnb_find_effect(Ptr prefix, u32 lo, u32 hi, u
 #define HNB_INIT_ITEMS 4
 #endif
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchParams P) {
+    hnb_pdl_launch_dependents();
+    hnb_pdl_wait();  // the previous frame's update wrote the dead stack and the counters read below
     const BatchInfo bi = *P.batch_info;
     struct Item {
         const Spawner* spawner;
@@ -328,6 +330,12 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
     const u32 warp = tid >> 5u;
+    // Programmatic dependent launch: this grid may have become resident while the bookkeeping kernel (and, behind it,
+    // the previous frame's update) was still running — its launch latency and CTA start skew are hidden. Nothing
+    // those kernels write has been read yet; from here on it is all visible. The next kernel in the stream (the next
+    // frame's bookkeeping) may take SM slots as this grid's CTAs retire.
+    hnb_pdl_launch_dependents();
+    hnb_pdl_wait();
 #if HNB_PROFILE
     if (lane == 0 && P.debug) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&P.debug[8], ~_g); }
 #endif

@@ -13,6 +13,7 @@
 // this per-instance step — and (b) the prefix step also scans the per-instance update TILE counts
 // consumed by the persistent update kernel.
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include "hnb_wgsl.cuh"
@@ -108,10 +109,20 @@ __global__ void k_prefix_sum(StaticTables T) {
 // Fused indirect + prefix-sum: CTA b owns batch b. Requires that the batches tile the spawner table
 // (checked on the host: HNB_ERR_BATCH_COVERAGE), which Batcher::push guarantees in the reference
 // (prefix sums and spawners are allocated in sync, vfx_indirect.wgsl:66).
+//
+// Launched with programmatic stream serialization (see hnb_pdl_wait): the CTA becomes resident during the tail of the
+// previous frame's update kernel and lets this frame's update grid follow it onto the SMs, so that the frame chain
+// update(N) -> bookkeeping(N+1) -> update(N+1) pays no launch latency. `header_words` != NULL: the 64-byte frame header
+// (sim params, epoch, batch count) travels as a kernel parameter and CTA 0 stores it into the device frame block —
+// frames whose tables did not change need no host->device copy at all.
 #define BK_THREADS 256
-__global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T) {
+struct FrameHeaderWords { u32 w[sizeof(FrameHeader) / 4]; };
+__global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, const __grid_constant__ FrameHeaderWords header, u32 write_header) {
     __shared__ u32 s_warp_a[BK_THREADS / 32], s_warp_t[BK_THREADS / 32];
     __shared__ u32 s_carry_a, s_carry_t;
+    hnb_pdl_launch_dependents();
+    hnb_pdl_wait();
+    if (write_header && blockIdx.x == 0 && threadIdx.x < sizeof(FrameHeader) / 4) ((u32*)T.frame)[threadIdx.x] = header.w[threadIdx.x];
     const u32 batch_index = blockIdx.x;
     BatchInfo* bi = &T.batch_infos[batch_index];
     const u32 offset = bi->prefix_sum_offset;
@@ -410,9 +421,21 @@ cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile,
     k_tile_prefix<<<1, BK_THREADS, 0, st>>>(T, batch_index, tile);
     return cudaGetLastError();
 }
-cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, cudaStream_t st) {
+cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, const FrameHeader* header_by_value, bool pdl, cudaStream_t st) {
     if (num_batches == 0) return cudaSuccess;
-    k_bookkeeping<<<num_batches, BK_THREADS, 0, st>>>(T);
+    FrameHeaderWords hw{};
+    if (header_by_value) memcpy(hw.w, header_by_value, sizeof(FrameHeader));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_batches);
+    cfg.blockDim = dim3(BK_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_bookkeeping, T, hw, u32(header_by_value ? 1u : 0u));
+    if (e != cudaSuccess) return e;
     if (T.num_child_infos) k_clear_events<<<blocks_for(num_effects, 64), 64, 0, st>>>(T);
     return cudaGetLastError();
 }

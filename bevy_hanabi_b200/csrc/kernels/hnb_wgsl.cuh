@@ -24,6 +24,25 @@ typedef unsigned long long u64;
 namespace hnb {
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+). A kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream still runs; hnb_pdl_wait() blocks until every predecessor grid
+// has completed and its writes are visible (a no-op for a normally launched kernel), hnb_pdl_launch_dependents() lets
+// the successor's CTAs take whatever SM slots free up from here on. Used on the frame chain
+// update(N) -> bookkeeping(N+1) -> update(N+1): launch latency and the start skew of the persistent grid hide behind
+// the predecessor's tail. (Compiled out on the host: the CPU kernel emulation of the test-suite.)
+// ---------------------------------------------------------------------------------------------
+HNB_DI void hnb_pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+HNB_DI void hnb_pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // Vector types
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct vec2 {

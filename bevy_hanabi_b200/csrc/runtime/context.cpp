@@ -194,6 +194,9 @@ struct hnb_ctx {
     uint32_t* d_sort_hist = nullptr;
     uint32_t sort_rows = 0;
     uint32_t tile_chunks_override = 0;  // HNB_TILE_CHUNKS env: fixed sub-tile count per tile (tuning)
+    bool pdl = true;          // HNB_PDL=0: launch the frame chain without programmatic dependent launch
+    bool plan_dirty = false;  // plan_batch changed a tile-size or range word of the host frame block since the last upload
+    uint64_t frame_copies = 0, frames = 0;  // hnb_simulate calls that needed the host->device copy of the frame block / all calls
     unsigned long long* d_debug = nullptr;  // 16 diagnostic counters (HNB_PROFILE kernels)
 
     hnb::FrameHeader* header() { return reinterpret_cast<hnb::FrameHeader*>(h_arena); }
@@ -343,6 +346,7 @@ void flush_arena(hnb_ctx* c, bool with_ranges) {
     CUDA_CHECK(cudaEventRecord(slot.done, c->stream));
     slot.used = true;
     c->dirty_tables = false;
+    if (bytes >= c->lay.off_prefix_sum) c->plan_dirty = false;
 }
 
 void next_epoch(hnb_ctx* c) {
@@ -480,13 +484,20 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
             small_tile = tile >> shift;
         }
     }
-    c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile_word;
+    if (c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] != tile_word) {
+        c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile_word;
+        c->plan_dirty = true;
+    }
 
     const bool consume = (lp.fx->flags & HNB_EFFECT_CONSUME_GPU_SPAWN_EVENTS) != 0;
     uint32_t init_threads = 0;
     if (consume) {
         if (bl.consume_events >= c->event_buffers.size()) fail(HNB_ERR_INVALID_ARG, "event-driven effect needs a consume_events buffer");
-        init_threads = ceil_div(c->event_buffers[bl.consume_events].capacity, 64) * 64;
+        // One logical init thread per event-buffer ENTRY, not per 64-thread workgroup of the reference's dispatch: the
+        // threads of the last partial workgroup would read past the buffer when a parent over-emits (event_count is
+        // unclamped, lib.rs:976-993), which WGSL's robust buffer access forgives and raw CUDA does not. The init
+        // accounting in the bookkeeping kernel uses the same bound (range = capacity).
+        init_threads = c->event_buffers[bl.consume_events].capacity;
     } else {
         init_threads = ceil_div(lp.total_spawn, 64) * 64;  // dispatch_workgroups(ceil(n/64)), mod.rs:7157-7173
     }
@@ -501,7 +512,12 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
                 r = end > sp[g] ? end - sp[g] : 0;
                 if (consume && r) r |= 0x80000000u;
             }
-            range[g] = r;
+            if (range[g] != r) {
+                range[g] = r;
+                c->plan_dirty = true;
+            }
+            // a non-zero range must reach the device every frame: the bookkeeping kernel zeroes it after use
+            if (r) c->plan_dirty = true;
         }
     }
     ensure_tile_state(c, lp.batch, lp.slab->capacity / small_tile + bi.prefix_sum_count + 1);  // n_big + n_small <= rows / s + 1 per instance
@@ -557,10 +573,23 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     return lp;
 }
 
+// hnb_init / hnb_update start with griddepcontrol.wait, so they may always be launched with programmatic stream
+// serialization: behind a kernel they become resident early (launch latency hidden), behind anything else the attribute
+// has no effect.
 void launch_kernel(hnb_ctx* c, CUfunction f, uint32_t blocks, hnb::BatchParams& P, uint32_t smem_bytes = 0, cudaStream_t st = nullptr) {
     void* args[] = {&P};
-    CUresult r = c->drv.LaunchKernel(f, blocks, 1, 1, 256, 1, 1, smem_bytes, (CUstream)(st ? st : c->stream), args, nullptr);
-    if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuLaunchKernel: " + cu_error_string(c->drv, r));
+    CUlaunchConfig cfg{};
+    cfg.gridDimX = blocks; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+    cfg.blockDimX = 256; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+    cfg.sharedMemBytes = smem_bytes;
+    cfg.hStream = (CUstream)(st ? st : c->stream);
+    CUlaunchAttribute attr{};
+    attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr.value.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    CUresult r = c->drv.LaunchKernelEx(&cfg, f, args, nullptr);
+    if (r != CUDA_SUCCESS) fail(HNB_ERR_CUDA, "cuLaunchKernelEx: " + cu_error_string(c->drv, r));
     c->launches++;
 }
 
@@ -666,6 +695,15 @@ void check_coverage(hnb_ctx* c, const std::vector<LaunchPlan>& plans) {
     if (pos != c->header()->sim.num_effects) fail(HNB_ERR_BATCH_COVERAGE, "batches do not cover sim_params.num_effects instances");
     for (uint32_t b = 0; b < c->B; ++b)
         if (bis[b].spawner_base != bis[b].prefix_sum_offset) fail(HNB_ERR_BATCH_COVERAGE, "spawner_base must equal prefix_sum_offset");
+    // Row indices the kernels dereference without a bounds check (wgpu would clamp them): validated whenever the
+    // caller uploaded new rows.
+    if (c->dirty_tables) {
+        const hnb_spawner* sp = c->h_at<hnb_spawner>(c->lay.off_spawners);
+        for (uint32_t i = 0; i < c->header()->sim.num_effects; ++i) {
+            if (sp[i].effect_metadata_index >= c->md_rows) fail(HNB_ERR_OUT_OF_RANGE, "spawner row " + std::to_string(i) + ": effect_metadata_index outside the metadata table");
+            if (sp[i].draw_indirect_index >= c->draw_rows) fail(HNB_ERR_OUT_OF_RANGE, "spawner row " + std::to_string(i) + ": draw_indirect_index outside the draw-args table");
+        }
+    }
     std::vector<bool> seen(c->B, false);
     for (auto& p : plans) {
         if (seen[p.batch]) fail(HNB_ERR_INVALID_ARG, "batch launched twice");
@@ -718,6 +756,7 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
         if (const char* env = getenv("HNB_TILE_CHUNKS")) c->tile_chunks_override = (uint32_t)atoi(env);
         if (const char* env = getenv("HNB_EPOCH_START")) c->epoch = uint32_t(strtoul(env, nullptr, 0)) & 0x3fffffffu;  // tests: start near the wrap
         if (const char* env = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::max(0, std::min(atoi(env), 31));
+        if (const char* env = getenv("HNB_PDL")) c->pdl = atoi(env) != 0;
         ensure_arena(c.get(), 0, 0);
         CUDA_CHECK(cudaMalloc((void**)&c->d_debug, 16 * 8));
         CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
@@ -1234,7 +1273,14 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         for (uint32_t i = 0; i < n; ++i) plans.push_back(plan_batch(c, batches[i], true));
         check_coverage(c, plans);  // nothing has been enqueued yet: a bad frame is skipped as a whole
         next_epoch(c);
-        flush_arena(c, true);
+        // The frame block reaches the device with ONE copy — or with none: when no table row, tile size or init range
+        // changed since the last upload (a steady-state frame without spawns), the only new bytes are the 64-byte
+        // header (sim params, epoch), and those ride in the bookkeeping kernel's parameter space. The frame is then
+        // a pure kernel chain, which programmatic dependent launch pipelines against the previous frame.
+        const bool copy_block = c->dirty_tables || c->plan_dirty;
+        if (copy_block) flush_arena(c, true);
+        c->frames++;
+        c->frame_copies += copy_block ? 1 : 0;
         // pass "hanabi:init" (mod.rs:7025-7179). Batches write disjoint slab rows and table rows; the only
         // cross-batch access is a child reading its parent's records, so frames with event-driven children keep
         // the reference's serial order.
@@ -1252,7 +1298,7 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             fork.join();
         }
         // passes "hanabi:indirect_dispatch" + "hanabi:update_prefix_sum" (mod.rs:7182-7275), fused
-        CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, c->stream));
+        CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, copy_block ? nullptr : c->header(), c->pdl, c->stream));
         c->launches += 1 + (c->child_rows ? 1 : 0);
         // pass "hanabi:update" (mod.rs:7280-7370): batches are independent (event appends are atomic)
         {

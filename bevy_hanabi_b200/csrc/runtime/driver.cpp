@@ -24,6 +24,7 @@ bool load_driver_api(DriverApi& api, std::string& err) {
     if (!resolve("cuModuleUnload", api.ModuleUnload, err)) return false;
     if (!resolve("cuModuleGetFunction", api.ModuleGetFunction, err)) return false;
     if (!resolve("cuLaunchKernel", api.LaunchKernel, err)) return false;
+    if (!resolve("cuLaunchKernelEx", api.LaunchKernelEx, err)) return false;
     if (!resolve("cuFuncSetAttribute", api.FuncSetAttribute, err)) return false;
     if (!resolve("cuFuncGetAttribute", api.FuncGetAttribute, err)) return false;
     if (!resolve("cuOccupancyMaxActiveBlocksPerMultiprocessor", api.OccupancyMaxActiveBlocksPerMultiprocessor, err)) return false;

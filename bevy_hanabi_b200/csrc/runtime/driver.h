@@ -14,6 +14,7 @@ struct DriverApi {
     decltype(&cuModuleUnload) ModuleUnload = nullptr;
     decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
     decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuLaunchKernelEx) LaunchKernelEx = nullptr;  // launch attributes (programmatic dependent launch)
     decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
     decltype(&cuFuncGetAttribute) FuncGetAttribute = nullptr;
     decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) OccupancyMaxActiveBlocksPerMultiprocessor = nullptr;

@@ -149,7 +149,7 @@ int main(int argc, char** argv) {
         CHECK(hnb_set_sim_params(ctx, &sim));
         CHECK(hnb_upload_spawners(ctx, &row, 1));
         CHECK(hnb_upload_batches(ctx, infos, n_batches, prefix, n_prefix));
-        hnb_batch_launch launch = {effect, slab, 0, totals[0], 0xFFFFFFFFu, 0xFFFFFFFFu, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}};
+        hnb_batch_launch launch = HNB_BATCH_LAUNCH_INIT(effect, slab, 0, totals[0]);
         CHECK(hnb_simulate(ctx, &launch, 1));
         if (f % 20 == 19 || f == frames - 1) {
             hnb_draw_indexed_indirect_args draw;

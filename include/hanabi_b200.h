@@ -353,6 +353,10 @@ typedef struct hnb_batch_launch {
     hnb_event_buffer consume_events; /* event buffer read by init (children), 0xFFFFFFFF if none */
     hnb_event_buffer emit_events[4]; /* event buffers appended by update (parents), 0xFFFFFFFF = unused */
 } hnb_batch_launch;
+/** Initialiser with every optional binding set to "none" (a zero-initialised struct would bind slab / buffer 0). */
+#define HNB_BATCH_LAUNCH_INIT(effect_, slab_, batch_info_index_, total_spawn_count_) \
+    { (effect_), (slab_), (batch_info_index_), (total_spawn_count_), 0xFFFFFFFFu, 0xFFFFFFFFu, \
+      { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu } }
 
 /**
  * Enqueue one simulation frame: init (per batch with spawns) → indirect + prefix-sum (one fused

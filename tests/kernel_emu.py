@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import os
 import subprocess
 from pathlib import Path
 
@@ -224,10 +225,11 @@ def build_emulated_effect(lowered, allow_events: bool = False) -> C.CDLL:
     cpp, so = OUT / f"emu_{tag}.cpp", OUT / f"emu_{tag}.so"
     if not so.exists():
         cpp.write_text(text)
-        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread", "-w", str(cpp), "-o", str(so)]
+        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread", "-w", str(cpp), "-o", str(so) + f".{os.getpid()}.tmp"]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("host build of the kernel templates failed:\n" + proc.stderr[:6000])
+        os.replace(str(so) + f".{os.getpid()}.tmp", so)  # atomic: parallel test workers build the same tag
     lib = C.CDLL(str(so))
     lib.emu_init.argtypes = [C.POINTER(EmuBatch), C.c_uint32]
     lib.emu_update.argtypes = [C.POINTER(EmuBatch), C.c_uint32, C.c_uint32]

@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import hashlib
 import re
+import os
 import subprocess
 from pathlib import Path
 
@@ -25,6 +26,7 @@ EXTRA_PRELUDE = r"""
 #include <map>
 #include <mutex>
 typedef int cudaError_t;
+#define __grid_constant__
 typedef void* cudaStream_t;
 namespace emu {
 struct Launch { pthread_barrier_t grid_bar; unsigned grid, block; };
@@ -102,7 +104,7 @@ using namespace hnb;
 extern "C" void semu_indirect(const StaticTables* T, uint32_t n) { StaticTables t = *T; emu_run([&] { k_indirect(t); }, (n + 63) / 64, 64); }
 extern "C" void semu_clear_events(const StaticTables* T, uint32_t n) { StaticTables t = *T; emu_run([&] { k_clear_events(t); }, (n + 63) / 64, 64); }
 extern "C" void semu_prefix_sum(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_prefix_sum(t); }, (nb + 63) / 64, 64); }
-extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_bookkeeping(t); }, nb, 256, 8); }
+extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_bookkeeping(t, FrameHeaderWords{}, 0u); }, nb, 256, 8); }
 extern "C" void semu_tile_prefix(const StaticTables* T, uint32_t batch, uint32_t tile) { StaticTables t = *T; emu_run([&] { k_tile_prefix(t, batch, tile); }, 1, 256); }
 extern "C" void semu_ribbon_sort_small(const RibbonSortArgs* a) { RibbonSortArgs r = *a; emu_run([&] { k_ribbon_sort_small(r); }, r.instance_count, 1024, 3); }
 extern "C" void semu_ribbon_sort_large(const RibbonSortArgs* a, uint32_t grid) { RibbonSortArgs r = *a; r.scratch_grid = grid; emu_run([&] { k_ribbon_sort_large(r); }, grid, 512); }
@@ -167,10 +169,11 @@ def build() -> C.CDLL:
     cpp, so = OUT / f"static_{tag}.cpp", OUT / f"static_{tag}.so"
     if not so.exists():
         cpp.write_text(text)
-        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", str(cpp), "-o", str(so)]
+        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", str(cpp), "-o", str(so) + f".{os.getpid()}.tmp"]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("host build of the static kernels failed:\n" + proc.stderr[:6000])
+        os.replace(str(so) + f".{os.getpid()}.tmp", so)  # atomic: parallel test workers build the same tag
     lib = C.CDLL(str(so))
     for f in ("semu_sizeof_static_tables", "semu_sizeof_ribbon_args", "semu_sizeof_event_args"):
         getattr(lib, f).restype = C.c_uint32

@@ -1,4 +1,4 @@
-"""Pending GPU tests (not collected: see tests/pending/README.md): BASELINE.json's C2 and C3 at their quoted sizes.
+"""BASELINE.json's C2 and C3 at their quoted sizes (first green on a B200 in round 2, profiles/r2_pending_tests_first_gpu_run.txt).
 
 tests/test_gpu_effects.py runs the same effects at 4096 / 8192 particles; tests/test_gpu_fullsize.py covers C4 and C5 at
 full size through checksums. These two compare EVERY record with the numpy interpreter at the sizes BASELINE.json names

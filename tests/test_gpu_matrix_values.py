@@ -1,4 +1,4 @@
-"""Pending GPU test (not collected: see tests/pending/README.md): matrix literals and properties on the device."""
+"""Matrix literals and properties on the device."""
 import pytest
 
 from tests.helpers import Instance, RefWorld

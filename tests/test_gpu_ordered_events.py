@@ -1,4 +1,4 @@
-"""Pending GPU test (not collected: see tests/pending/README.md)."""
+"""HNB_EFFECT_ORDERED_EVENTS on the device."""
 from collections import Counter  # noqa: F401
 
 import numpy as np
@@ -16,7 +16,7 @@ A = G.Attribute
 
 
 def test_ordered_events_two_children(ctx, orc):
-    """HNB_EFFECT_ORDERED_EVENTS on the device (validated so far only under emulation, see tests/pending/README.md): with
+    """HNB_EFFECT_ORDERED_EVENTS on the device : with
     ordered append the buffers must hold EXACTLY the canonical sequence, overflow included, and the children need no
     re-ordering of the oracle's events. Scenario: one parent, two event channels: channel 0 fed every frame by particles that are alive (EventEmitCondition::Always,
     count 0 or 1 drawn per particle), channel 1 by dying particles (OnDie, 4 events each). Each child consumes its

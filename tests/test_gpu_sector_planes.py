@@ -1,4 +1,4 @@
-"""Pending GPU test (not collected: see tests/pending/README.md): the sector-plane slab layout on the device."""
+"""The sector-plane slab layout on the device."""
 import numpy as np
 import pytest
 

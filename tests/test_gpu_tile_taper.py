@@ -1,4 +1,4 @@
-"""Pending GPU test (not collected: see tests/pending/README.md): the experimental tile taper (HNB_TILE_TAPER) on the device."""
+"""The experimental tile taper (HNB_TILE_TAPER) on the device."""
 import numpy as np
 import pytest
 
