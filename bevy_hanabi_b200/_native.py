@@ -86,6 +86,12 @@ class ChildInfo(C.Structure):
     _fields_ = [("init_indirect_dispatch_index", u32), ("event_count", i32)]
 
 
+class SlabView(C.Structure):
+    _fields_ = [("capacity_rows", u32), ("particle_stride", u32), ("num_planes", u32), ("_pad", u32),
+                ("planes", C.c_void_p * 16), ("plane_offset", u32 * 16), ("plane_width", u32 * 16),
+                ("ping", C.c_void_p), ("pong", C.c_void_p), ("dead", C.c_void_p)]
+
+
 class AttrLayout(C.Structure):
     _fields_ = [("name", C.c_char_p), ("value_type", u32), ("offset", u32)]
 
@@ -161,6 +167,17 @@ SIGNATURES = {
     "hnb_slab_fill_c5": (i32, [vp, u32, u32, u32, u32, f32, f32]),
     "hnb_slab_checksum": (i32, [vp, u32, u32, u32, P(C.c_uint64)]),
     "hnb_slab_checksum_indirect": (i32, [vp, u32, u32, u32, P(C.c_uint64)]),
+    "hnb_slab_fill_c5_ex": (i32, [vp, u32, u32, u32, u32, f32, f32, u32]),
+    "hnb_slab_checksum_ex": (i32, [vp, u32, u32, u32, C.c_uint64, P(C.c_uint64)]),
+    "hnb_slab_device_view": (i32, [vp, u32, P(SlabView)]),
+    "hnb_slab_export_aos_device": (i32, [vp, u32, u32, u32, vp]),
+    "hnb_slab_import_aos_device": (i32, [vp, u32, u32, u32, vp]),
+    "hnb_slab_export_indirect_device": (i32, [vp, u32, u32, u32, vp]),
+    "hnb_slab_import_indirect_device": (i32, [vp, u32, u32, u32, vp]),
+    "hnb_device_alloc": (vp, [vp, C.c_size_t]),
+    "hnb_device_free": (None, [vp, vp]),
+    "hnb_device_download": (i32, [vp, vp, vp, C.c_size_t]),
+    "hnb_device_upload": (i32, [vp, vp, vp, C.c_size_t]),
     "hnb_effect_compile": (i32, [vp, P(EffectDesc), P(u32)]),
     "hnb_effect_destroy": (i32, [vp, u32]),
     "hnb_compile_job_start": (vp, [P(EffectDesc)]),

@@ -12,6 +12,7 @@
 // (vfx_init.wgsl:141,151) — our init kernel assigns ranks instead and defers the counter update to
 // this per-instance step — and (b) the prefix step also scans the per-instance update TILE counts
 // consumed by the persistent update kernel.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <cuda_runtime.h>
@@ -233,48 +234,16 @@ __global__ void k_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 cou
     dead[first + i] = first + i;  // effect_cache.rs:317-319
 }
 
-// AoS rows (stride_words u32 each) <-> planes. Plane p covers words [word_off[p], word_off[p]+words[p]).
-__global__ void k_aos_to_planes(const u32* aos, PlaneSet planes, u32 first, u32 count, u32 stride_words) {
-    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    const u64 total = u64(count) * stride_words;
-    if (i >= total) return;
-    const u32 row = u32(i / stride_words), w = u32(i % stride_words);
-    const u32 p = planes.word_to_plane[w];
-    const u32 lane = w - planes.word_off[p];
-    ((u32*)planes.ptr[p])[u64(first + row) * planes.words[p] + lane] = aos[i];
-}
-__global__ void k_planes_to_aos(u32* aos, PlaneSet planes, u32 first, u32 count, u32 stride_words) {
-    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    const u64 total = u64(count) * stride_words;
-    if (i >= total) return;
-    const u32 row = u32(i / stride_words), w = u32(i % stride_words);
-    const u32 p = planes.word_to_plane[w];
-    const u32 lane = w - planes.word_off[p];
-    aos[i] = ((const u32*)planes.ptr[p])[u64(first + row) * planes.words[p] + lane];
-}
-__global__ void k_indirect_interleave(u32* rows3, const u32* ping, const u32* pong, const u32* dead, u32 first, u32 count) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    rows3[3u * i + 0u] = ping[first + i];
-    rows3[3u * i + 1u] = pong[first + i];
-    rows3[3u * i + 2u] = dead[first + i];
-}
-__global__ void k_indirect_deinterleave(const u32* rows3, u32* ping, u32* pong, u32* dead, u32 first, u32 count) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    ping[first + i] = rows3[3u * i + 0u];
-    pong[first + i] = rows3[3u * i + 1u];
-    dead[first + i] = rows3[3u * i + 2u];
-}
-
 // Synthetic C5 state: counter-based so that the CPU oracle can regenerate any row.
 //   s = pcg_hash(row ^ seed); six successive pcg_hash -> position, velocity in [-1,1); one more -> lifetime
+// `logical_first`: row of the LOGICAL instance stored at slab row `first` (a shard of an instance split by index range
+// over several devices holds the unsharded instance's values under shard-local indices).
 __global__ void k_fill_c5(float4* pos_age, float4* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed,
-                          f32 lifetime_lo, f32 lifetime_hi) {
+                          f32 lifetime_lo, f32 lifetime_hi, u32 logical_first) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const u32 row = first + i;
-    u32 s = pcg_hash(row ^ seed);
+    u32 s = pcg_hash((logical_first + i) ^ seed);
     f32 v[7];
     for (int k = 0; k < 7; ++k) { s = pcg_hash(s); v[k] = to_float01(s); }
     pos_age[row] = make_float4(v[0] * 2.0f - 1.0f, v[1] * 2.0f - 1.0f, v[2] * 2.0f - 1.0f, 0.0f);
@@ -285,10 +254,10 @@ __global__ void k_fill_c5(float4* pos_age, float4* vel_life, u32* ping, u32* pon
 }
 
 // Order-independent checksum: sum over rows of a 64-bit mix of the row's AoS words and row index.
-__global__ void k_checksum(PlaneSet planes, u32 first, u32 count, u32 stride_words, u64* out) {
+__global__ void k_checksum(PlaneSet planes, u32 first, u32 count, u32 stride_words, u64 index_base, u64* out) {
     u64 acc = 0;
     for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += u64(gridDim.x) * blockDim.x) {
-        u64 h = 0xcbf29ce484222325ull ^ u64(i);
+        u64 h = 0xcbf29ce484222325ull ^ (index_base + u64(i));
         for (u32 w = 0; w < stride_words; ++w) {
             const u32 p = planes.word_to_plane[w];
             const u32 lane = w - planes.word_off[p];
@@ -458,38 +427,18 @@ cudaError_t launch_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 co
     k_slab_reset<<<blocks_for(count, 256), 256, 0, st>>>(ping, pong, dead, first, count);
     return cudaGetLastError();
 }
-cudaError_t launch_aos_to_planes(const u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st) {
+cudaError_t launch_fill_c5(void* pos_age, void* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed, f32 lo, f32 hi, u32 logical_first, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
-    k_aos_to_planes<<<blocks_for(u64(count) * stride_words, 256), 256, 0, st>>>(aos, planes, first, count, stride_words);
-    return cudaGetLastError();
-}
-cudaError_t launch_planes_to_aos(u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st) {
-    if (count == 0) return cudaSuccess;
-    k_planes_to_aos<<<blocks_for(u64(count) * stride_words, 256), 256, 0, st>>>(aos, planes, first, count, stride_words);
-    return cudaGetLastError();
-}
-cudaError_t launch_indirect_interleave(u32* rows3, const u32* ping, const u32* pong, const u32* dead, u32 first, u32 count, cudaStream_t st) {
-    if (count == 0) return cudaSuccess;
-    k_indirect_interleave<<<blocks_for(count, 256), 256, 0, st>>>(rows3, ping, pong, dead, first, count);
-    return cudaGetLastError();
-}
-cudaError_t launch_indirect_deinterleave(const u32* rows3, u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st) {
-    if (count == 0) return cudaSuccess;
-    k_indirect_deinterleave<<<blocks_for(count, 256), 256, 0, st>>>(rows3, ping, pong, dead, first, count);
-    return cudaGetLastError();
-}
-cudaError_t launch_fill_c5(void* pos_age, void* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed, f32 lo, f32 hi, cudaStream_t st) {
-    if (count == 0) return cudaSuccess;
-    k_fill_c5<<<blocks_for(count, 256), 256, 0, st>>>((float4*)pos_age, (float4*)vel_life, ping, pong, first, count, seed, lo, hi);
+    k_fill_c5<<<blocks_for(count, 256), 256, 0, st>>>((float4*)pos_age, (float4*)vel_life, ping, pong, first, count, seed, lo, hi, logical_first);
     return cudaGetLastError();
 }
 cudaError_t launch_measure_sm_clock(u64* out2, u64 window_ns, cudaStream_t st) {
     k_measure_sm_clock<<<1, 1, 0, st>>>(out2, window_ns);
     return cudaGetLastError();
 }
-cudaError_t launch_checksum(const PlaneSet& planes, u32 first, u32 count, u32 stride_words, u64* out, cudaStream_t st) {
+cudaError_t launch_checksum(const PlaneSet& planes, u32 first, u32 count, u32 stride_words, u64 index_base, u64* out, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
-    k_checksum<<<148 * 4, 256, 0, st>>>(planes, first, count, stride_words, out);
+    k_checksum<<<148 * 4, 256, 0, st>>>(planes, first, count, stride_words, index_base, out);
     return cudaGetLastError();
 }
 

@@ -926,25 +926,119 @@ int32_t hnb_slab_download_indirect(hnb_ctx* c, hnb_slab h, uint32_t first, uint3
     });
 }
 
+// ---- device-resident interop (§8 f-2): the consumer of the hot path is the render pass, which binds the particle
+// buffer as AoS records and the indirect buffer as interleaved rows ON THE DEVICE (vfx_render.wgsl:228-231,
+// mod.rs:139-146). These run asynchronously on the context stream; no host copy is involved.
+int32_t hnb_slab_export_aos_device(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, void* d_dst) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count && !d_dst) fail(HNB_ERR_INVALID_ARG, "d_dst is NULL");
+        if ((uintptr_t)d_dst & 3u) fail(HNB_ERR_INVALID_ARG, "d_dst must be 4-byte aligned (16-byte aligned for full speed)");
+        CUDA_CHECK(hnb::launch_planes_to_aos((uint32_t*)d_dst, plane_set(s), first, count, s.stride / 4, c->stream));
+        c->launches += count ? 1 : 0;
+    });
+}
+int32_t hnb_slab_import_aos_device(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, const void* d_src) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count && !d_src) fail(HNB_ERR_INVALID_ARG, "d_src is NULL");
+        if ((uintptr_t)d_src & 3u) fail(HNB_ERR_INVALID_ARG, "d_src must be 4-byte aligned (16-byte aligned for full speed)");
+        CUDA_CHECK(hnb::launch_aos_to_planes((const uint32_t*)d_src, plane_set(s), first, count, s.stride / 4, c->stream));
+        c->launches += count ? 1 : 0;
+    });
+}
+int32_t hnb_slab_export_indirect_device(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, hnb_indirect_index* d_dst) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count && !d_dst) fail(HNB_ERR_INVALID_ARG, "d_dst is NULL");
+        CUDA_CHECK(hnb::launch_indirect_interleave((uint32_t*)d_dst, s.ping, s.pong, s.dead, first, count, c->stream));
+        c->launches += count ? 1 : 0;
+    });
+}
+int32_t hnb_slab_import_indirect_device(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, const hnb_indirect_index* d_src) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, count);
+        if (count && !d_src) fail(HNB_ERR_INVALID_ARG, "d_src is NULL");
+        CUDA_CHECK(hnb::launch_indirect_deinterleave((const uint32_t*)d_src, s.ping, s.pong, s.dead, first, count, c->stream));
+        c->launches += count ? 1 : 0;
+    });
+}
+int32_t hnb_slab_device_view(hnb_ctx* c, hnb_slab h, hnb_slab_view* out) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        if (!out) fail(HNB_ERR_INVALID_ARG, "out is NULL");
+        memset(out, 0, sizeof(*out));
+        out->capacity_rows = s.capacity;
+        out->particle_stride = s.stride;
+        out->num_planes = (uint32_t)s.planes.size();
+        for (size_t p = 0; p < s.planes.size(); ++p) {
+            out->planes[p] = s.d_planes[p];
+            out->plane_offset[p] = s.planes[p].offset;
+            out->plane_width[p] = s.planes[p].width;
+        }
+        out->ping = s.ping;
+        out->pong = s.pong;
+        out->dead = s.dead;
+    });
+}
+void* hnb_device_alloc(hnb_ctx* c, size_t bytes) {
+    void* p = nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&p, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void hnb_device_free(hnb_ctx* c, void* p) {
+    if (!p) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(p);
+}
+int32_t hnb_device_download(hnb_ctx* c, void* host_dst, const void* d_src, size_t bytes) {
+    return guarded([&] {
+        CUDA_CHECK(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t hnb_device_upload(hnb_ctx* c, void* d_dst, const void* host_src, size_t bytes) {
+    return guarded([&] {
+        CUDA_CHECK(cudaMemcpyAsync(d_dst, host_src, bytes, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
 int32_t hnb_slab_fill_c5(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint32_t seed, float lo, float hi) {
+    return hnb_slab_fill_c5_ex(c, h, first, count, seed, lo, hi, first);
+}
+
+int32_t hnb_slab_fill_c5_ex(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint32_t seed, float lo, float hi, uint32_t logical_first) {
     return guarded([&] {
         Slab& s = get_slab(c, h);
         check_rows(s, first, count);
         if (s.stride != 32) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 needs the 32-byte {position,age,velocity,lifetime} layout");
         if (s.sector_planes) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 writes the default plane layout; spawn through the init pass or use hnb_slab_upload_aos");
-        CUDA_CHECK(hnb::launch_fill_c5(s.d_planes[0], s.d_planes[1], s.ping, s.pong, first, count, seed, lo, hi, c->stream));
+        CUDA_CHECK(hnb::launch_fill_c5(s.d_planes[0], s.d_planes[1], s.ping, s.pong, first, count, seed, lo, hi, logical_first, c->stream));
         c->launches++;
     });
 }
 
 int32_t hnb_slab_checksum(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint64_t* out) {
+    return hnb_slab_checksum_ex(c, h, first, count, 0, out);
+}
+
+int32_t hnb_slab_checksum_ex(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t count, uint64_t index_base, uint64_t* out) {
     return guarded([&] {
         Slab& s = get_slab(c, h);
         check_rows(s, first, count);
         unsigned long long* d = nullptr;
         CUDA_CHECK(cudaMalloc((void**)&d, 8));
         CUDA_CHECK(cudaMemsetAsync(d, 0, 8, c->stream));
-        CUDA_CHECK(hnb::launch_checksum(plane_set(s), first, count, s.stride / 4, d, c->stream));
+        CUDA_CHECK(hnb::launch_checksum(plane_set(s), first, count, s.stride / 4, index_base, d, c->stream));
         c->launches++;
         CUDA_CHECK(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -968,7 +1062,7 @@ int32_t hnb_slab_checksum_indirect(hnb_ctx* c, hnb_slab h, uint32_t first, uint3
         unsigned long long* d = nullptr;
         CUDA_CHECK(cudaMalloc((void**)&d, 8));
         CUDA_CHECK(cudaMemsetAsync(d, 0, 8, c->stream));
-        CUDA_CHECK(hnb::launch_checksum(ps, first, count, 3, d, c->stream));
+        CUDA_CHECK(hnb::launch_checksum(ps, first, count, 3, 0, d, c->stream));
         c->launches++;
         CUDA_CHECK(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));

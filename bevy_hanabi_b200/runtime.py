@@ -255,13 +255,51 @@ class Context:
         check(lib.hnb_slab_download_indirect(self._h, slab, first, count, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def slab_fill_c5(self, slab: int, first: int, count: int, seed: int, lifetime_lo: float, lifetime_hi: float) -> None:
-        check(lib.hnb_slab_fill_c5(self._h, slab, first, count, seed, lifetime_lo, lifetime_hi))
+    def slab_fill_c5(self, slab: int, first: int, count: int, seed: int, lifetime_lo: float, lifetime_hi: float,
+                     logical_first: int | None = None) -> None:
+        """`logical_first`: the slab rows hold logical rows [logical_first, +count) of an instance sharded over devices."""
+        check(lib.hnb_slab_fill_c5_ex(self._h, slab, first, count, seed, lifetime_lo, lifetime_hi, first if logical_first is None else logical_first))
 
-    def slab_checksum(self, slab: int, first: int, count: int) -> int:
+    def slab_checksum(self, slab: int, first: int, count: int, index_base: int = 0) -> int:
         out = C.c_uint64(0)
-        check(lib.hnb_slab_checksum(self._h, slab, first, count, C.byref(out)))
+        check(lib.hnb_slab_checksum_ex(self._h, slab, first, count, index_base, C.byref(out)))
         return out.value
+
+    # -- device-resident interop (the renderer's view of the state, §8 f-2)
+    def slab_device_view(self, slab: int) -> "N.SlabView":
+        out = N.SlabView()
+        check(lib.hnb_slab_device_view(self._h, slab, C.byref(out)))
+        return out
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = lib.hnb_device_alloc(self._h, nbytes)
+        if not p:
+            raise MemoryError(f"hnb_device_alloc({nbytes}) failed")
+        return p
+
+    def device_free(self, ptr: int) -> None:
+        lib.hnb_device_free(self._h, ptr)
+
+    def device_download(self, ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes // 4, dtype=np.uint32)
+        check(lib.hnb_device_download(self._h, out.ctypes.data_as(C.c_void_p), ptr, nbytes))
+        return out
+
+    def device_upload(self, ptr: int, data: np.ndarray) -> None:
+        a = np.ascontiguousarray(data)
+        check(lib.hnb_device_upload(self._h, ptr, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def slab_export_aos_device(self, slab: int, first: int, count: int, d_dst: int) -> None:
+        check(lib.hnb_slab_export_aos_device(self._h, slab, first, count, d_dst))
+
+    def slab_import_aos_device(self, slab: int, first: int, count: int, d_src: int) -> None:
+        check(lib.hnb_slab_import_aos_device(self._h, slab, first, count, d_src))
+
+    def slab_export_indirect_device(self, slab: int, first: int, count: int, d_dst: int) -> None:
+        check(lib.hnb_slab_export_indirect_device(self._h, slab, first, count, d_dst))
+
+    def slab_import_indirect_device(self, slab: int, first: int, count: int, d_src: int) -> None:
+        check(lib.hnb_slab_import_indirect_device(self._h, slab, first, count, d_src))
 
     def slab_checksum_indirect(self, slab: int, first: int, count: int) -> int:
         out = C.c_uint64(0)

@@ -202,15 +202,50 @@ HNB_API int32_t hnb_slab_download_indirect(hnb_ctx* ctx, hnb_slab slab, uint32_t
  */
 HNB_API int32_t hnb_slab_fill_c5(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
                                  uint32_t seed, float lifetime_lo, float lifetime_hi);
+/** The same fill for a SHARD of a logical instance split by index range over several devices: slab rows
+ *  [first,first+count) receive the values of logical rows [logical_first, logical_first+count) — what a single-GPU slab
+ *  holding the whole instance would have there — under shard-local particle indices. */
+HNB_API int32_t hnb_slab_fill_c5_ex(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
+                                    uint32_t seed, float lifetime_lo, float lifetime_hi, uint32_t logical_first);
 /** 64-bit FNV-style checksum of the AoS bytes of rows [first,first+count), computed on device
  *  (order-independent sum of per-row hashes), for whole-slab comparisons at sizes the host
  *  cannot download cheaply. */
 HNB_API int32_t hnb_slab_checksum(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
                                   uint64_t* out);
 
+/** The same with row i hashed as logical row `index_base + i`: the checksums of the shards of a logical instance then
+ *  add up (mod 2^64) to the checksum of the unsharded instance. */
+HNB_API int32_t hnb_slab_checksum_ex(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count, uint64_t index_base,
+                                     uint64_t* out);
 /** Same checksum over the interleaved {ping,pong,dead} rows of the slab's indirection columns. */
 HNB_API int32_t hnb_slab_checksum_indirect(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
                                            uint64_t* out);
+
+/* Device-resident interop. The only consumer of the simulated state is the render pass, which binds
+ * the particle buffer as AoS `Particle` records and the indirect buffer as interleaved rows on the DEVICE
+ * (vfx_render.wgsl:228-231 reads particle_buffer[indirect_buffer[i].particle_index[render_pong]], mod.rs:139-146).
+ * A renderer sharing the CUDA device (Vulkan/D3D12 external memory, or a CUDA rasteriser) either reads the SoA columns in
+ * place (hnb_slab_device_view) or asks for the reference layouts in its own device buffer; both are asynchronous on the
+ * context stream and involve no host copy. `d_*` pointers are DEVICE pointers. */
+typedef struct hnb_slab_view {
+    uint32_t capacity_rows, particle_stride, num_planes, _pad;
+    void* planes[16];          /* column p holds bytes [plane_offset[p], +plane_width[p]) of every record, capacity_rows elements */
+    uint32_t plane_offset[16];
+    uint32_t plane_width[16];  /* 16, 8 or 4 bytes (32 with HNB_SLAB_SECTOR_PLANES: two 16-byte pieces per element) */
+    uint32_t *ping, *pong, *dead; /* the three u32 columns of IndirectEntry */
+} hnb_slab_view;
+HNB_API int32_t hnb_slab_device_view(hnb_ctx* ctx, hnb_slab slab, hnb_slab_view* out);
+/** Rows [first,first+count) as AoS records into `d_dst` (count * particle_stride bytes). */
+HNB_API int32_t hnb_slab_export_aos_device(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count, void* d_dst);
+HNB_API int32_t hnb_slab_import_aos_device(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count, const void* d_src);
+/** Rows [first,first+count) of the indirection columns as interleaved {ping,pong,dead} rows (12 bytes each). */
+HNB_API int32_t hnb_slab_export_indirect_device(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count, hnb_indirect_index* d_dst);
+HNB_API int32_t hnb_slab_import_indirect_device(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count, const hnb_indirect_index* d_src);
+/** Plain device memory on the context's GPU for callers without their own CUDA allocator (tests, examples). */
+HNB_API void* hnb_device_alloc(hnb_ctx* ctx, size_t bytes);
+HNB_API void hnb_device_free(hnb_ctx* ctx, void* d_ptr);
+HNB_API int32_t hnb_device_download(hnb_ctx* ctx, void* host_dst, const void* d_src, size_t bytes);
+HNB_API int32_t hnb_device_upload(hnb_ctx* ctx, void* d_dst, const void* host_src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------ */
 /* 4. Compiled effects ≙ pipeline specialisation (reference mod.rs:1758,1866;            */

@@ -96,6 +96,14 @@ def load() -> C.CDLL:
     lib.orc_update_c5_parallel.argtypes = [P(SimParams), P(u32), vp, vp, P(Spawner), P(EffectMetadata), P(f32), vp, C.c_int]
     lib.orc_checksum.restype = C.c_uint64
     lib.orc_checksum.argtypes = [vp, u32, u32, u32]
+    lib.orc_fill_c5_ex.restype = None
+    lib.orc_fill_c5_ex.argtypes = [vp, vp, u32, u32, u32, f32, f32, u32]
+    lib.orc_indirect_reset.restype = None
+    lib.orc_indirect_reset.argtypes = [vp, u32, u32]
+    lib.orc_checksum_ex.restype = C.c_uint64
+    lib.orc_checksum_ex.argtypes = [vp, u32, u32, u32, C.c_uint64]
+    lib.orc_set_threads.restype = None
+    lib.orc_set_threads.argtypes = [C.c_int]
     lib.orc_max_threads.restype = C.c_int
     lib.orc_max_threads.argtypes = []
     return lib

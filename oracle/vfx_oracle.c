@@ -394,12 +394,15 @@ static void body_init_const(uint32_t* particle, orc_thread* t) {
 ORC_API orc_init_body orc_body_init_const(void) { return body_init_const; }
 
 /* ---- synthetic C5 state, same counter-based generator as hnb_slab_fill_c5 ---------------------- */
-ORC_API void orc_fill_c5(float* particles_aos /* 8 floats per row */, orc_indirect_entry* indirect, uint32_t first,
-                         uint32_t count, uint32_t seed, float lifetime_lo, float lifetime_hi) {
+/* `logical_first`: row of the LOGICAL instance that slab row `first` holds. A shard of an instance split by index range
+ * over several devices stores logical rows [logical_first, logical_first + count) at its own rows
+ * [first, first + count): same particle values as the unsharded instance, shard-local indices. */
+ORC_API void orc_fill_c5_ex(float* particles_aos /* 8 floats per row */, orc_indirect_entry* indirect, uint32_t first,
+                            uint32_t count, uint32_t seed, float lifetime_lo, float lifetime_hi, uint32_t logical_first) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)count; ++i) {
         uint32_t row = first + (uint32_t)i;
-        uint32_t s = orc_pcg_hash(row ^ seed);
+        uint32_t s = orc_pcg_hash((logical_first + (uint32_t)i) ^ seed);
         float v[7];
         for (int k = 0; k < 7; ++k) {
             s = orc_pcg_hash(s);
@@ -413,6 +416,23 @@ ORC_API void orc_fill_c5(float* particles_aos /* 8 floats per row */, orc_indire
             indirect[row].particle_index[0] = (uint32_t)i;
             indirect[row].particle_index[1] = (uint32_t)i;
         }
+    }
+}
+
+ORC_API void orc_fill_c5(float* particles_aos, orc_indirect_entry* indirect, uint32_t first, uint32_t count, uint32_t seed,
+                         float lifetime_lo, float lifetime_hi) {
+    orc_fill_c5_ex(particles_aos, indirect, first, count, seed, lifetime_lo, lifetime_hi, first);
+}
+
+/* ParticleSlab::new's initial indirect rows (effect_cache.rs:309-322): ping = pong = 0, dead[i] = i. In parallel so that
+ * the pages are first touched by the threads that will update them (the CPU baseline of bench.py). */
+ORC_API void orc_indirect_reset(orc_indirect_entry* indirect, uint32_t first, uint32_t count) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)count; ++i) {
+        uint32_t row = first + (uint32_t)i;
+        indirect[row].particle_index[0] = 0u;
+        indirect[row].particle_index[1] = 0u;
+        indirect[row].dead_index = row;
     }
 }
 
@@ -484,17 +504,31 @@ ORC_API uint32_t orc_update_c5_parallel(const orc_sim_params* sim_params, uint32
 
 /* Order-independent checksum of `count` rows of `stride_words` u32 each: same function as the device-side
  * hnb_slab_checksum (sum over rows of a 64-bit mix of the row's words and its index). */
-ORC_API uint64_t orc_checksum(const uint32_t* words, uint32_t first, uint32_t count, uint32_t stride_words) {
+ORC_API uint64_t orc_checksum_ex(const uint32_t* words, uint32_t first, uint32_t count, uint32_t stride_words, uint64_t index_base) {
     uint64_t acc = 0;
 #pragma omp parallel for schedule(static) reduction(+ : acc)
     for (int64_t i = 0; i < (int64_t)count; ++i) {
-        uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)i;
+        uint64_t h = 0xcbf29ce484222325ull ^ (index_base + (uint64_t)i);
         const uint32_t* row = words + (size_t)(first + (uint32_t)i) * stride_words;
         for (uint32_t w = 0; w < stride_words; ++w) h = (h ^ (uint64_t)row[w]) * 0x100000001b3ull;
         h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
         acc += h;
     }
     return acc;
+}
+
+ORC_API uint64_t orc_checksum(const uint32_t* words, uint32_t first, uint32_t count, uint32_t stride_words) {
+    return orc_checksum_ex(words, first, count, stride_words, 0);
+}
+
+/* Thread count of the `parallel for` loops above (fill, reset, checksum); the update takes its own count. A launcher may
+ * have exported OMP_NUM_THREADS=1 (torchrun does): the benchmark's CPU arm decides from the CPUs it may actually use. */
+ORC_API void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 ORC_API int orc_max_threads(void) {

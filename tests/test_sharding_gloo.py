@@ -77,3 +77,24 @@ def _worker(rank, world, port, total):
 
 def test_two_process_gloo():
     mp.spawn(_worker, args=(2, _free_port(), 64 << 20), nprocs=2, join=True)
+
+
+def test_oracle_shard_fill_and_checksum_compose(orc):
+    """The oracle side of hnb_slab_fill_c5_ex / hnb_slab_checksum_ex: shards hold the unsharded values, checksums add up."""
+    import numpy as np
+    from oracle import c_oracle as O
+    P, seed = 9000, 31
+    ref = np.zeros((P, 8), dtype=np.float32)
+    orc.orc_fill_c5(O.ptr(ref), None, 0, P, seed, 0.2, 0.9)
+    whole = orc.orc_checksum(O.ptr(ref), 0, P, 8)
+    for world in (2, 3, 8):
+        acc = 0
+        for r in range(world):
+            first, end = shard_range(P, r, world)
+            shard = np.zeros((end - first, 8), dtype=np.float32)
+            ind = np.zeros((end - first, 3), dtype=np.uint32)
+            orc.orc_fill_c5_ex(O.ptr(shard), O.ptr(ind), 0, end - first, seed, 0.2, 0.9, first)
+            np.testing.assert_array_equal(shard, ref[first:end])
+            np.testing.assert_array_equal(ind[:, 0], np.arange(end - first, dtype=np.uint32))
+            acc = (acc + orc.orc_checksum_ex(O.ptr(shard), 0, end - first, 8, first)) % 2**64
+        assert acc == whole

@@ -294,7 +294,82 @@ def taper():
     os.environ.pop("HNB_TILE_TAPER", None)
 
 
-SCENARIOS = {"churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math, "taper": taper}
+def frame_chain():
+    """Whole frames (bookkeeping + update, state resident, no table changes) back to back, with and without programmatic
+    dependent launch: what one step costs beyond its update kernel, at the shard sizes of the strong-scaling runs."""
+    import os
+    for mi in (1, 2, 4, 8, 16, 64):
+        P = mi << 20
+        for pdl in ("0", "1"):
+            os.environ["HNB_PDL"] = pdl
+            ctx = hb.Context(0, stream.cuda_stream)
+            slab = ctx.slab_create(P, 32)
+            ctx.slab_fill_c5(slab, 0, P, 42, 1e9, 1e9)
+            single_instance(ctx, P, 32, alive=P)
+            la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered()), slab, 0, 0)]
+            for _ in range(10):
+                ctx.simulate(la)
+            fr = min(frame_ms(ctx, la, 200) for _ in range(3))
+            k = timed_update(ctx, la, 50)
+            report(f"C5 {mi:2d}Mi frame chain, HNB_PDL={pdl}", fr, 72 * P, f"isolated update kernel {k:.4f} ms; frame - kernel = {1e3 * (fr - k):+.1f} us")
+            ctx.close()
+    os.environ.pop("HNB_PDL", None)
+
+
+def chunks_sweep():
+    """Tile size (HNB_TILE_CHUNKS sub-tiles of 128 rows) and CTAs per SM under the pipelined frame chain."""
+    import os
+    for mi in (2, 4, 8, 16, 32):
+        P = mi << 20
+        for defines in ("", "HNB_MIN_BLOCKS=4"):
+            for chunks in ("1", "2", "4"):
+                os.environ["HNB_TILE_CHUNKS"] = chunks
+                if defines:
+                    os.environ["HNB_DEFINES"] = defines
+                else:
+                    os.environ.pop("HNB_DEFINES", None)
+                ctx = hb.Context(0, stream.cuda_stream)
+                slab = ctx.slab_create(P, 32)
+                ctx.slab_fill_c5(slab, 0, P, 42, 1e9, 1e9)
+                single_instance(ctx, P, 32, alive=P)
+                la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered()), slab, 0, 0)]
+                for _ in range(10):
+                    ctx.simulate(la)
+                fr = min(frame_ms(ctx, la, 200) for _ in range(3))
+                report(f"C5 {mi:2d}Mi frame chain, chunks={chunks} {defines}", fr, 72 * P)
+                ctx.close()
+    os.environ.pop("HNB_TILE_CHUNKS", None)
+    os.environ.pop("HNB_DEFINES", None)
+
+
+def interop():
+    """Device-resident export of the reference layouts (what a renderer binds): SoA planes -> AoS records and
+    {ping,pong,dead} columns -> interleaved rows, device to device; bytes = read + written."""
+    for stride, P in ((32, 64 << 20), (48, 32 << 20), (20, 32 << 20)):
+        ctx = hb.Context(0, stream.cuda_stream)
+        slab = ctx.slab_create(P, stride)
+        buf = ctx.device_alloc(P * stride)
+        ibuf = ctx.device_alloc(P * 12)
+        for name, fn, nbytes in (("export AoS", lambda: ctx.slab_export_aos_device(slab, 0, P, buf), 2 * P * stride),
+                                 ("import AoS", lambda: ctx.slab_import_aos_device(slab, 0, P, buf), 2 * P * stride),
+                                 ("export indirect rows", lambda: ctx.slab_export_indirect_device(slab, 0, P, ibuf), 2 * P * 12),
+                                 ("import indirect rows", lambda: ctx.slab_import_indirect_device(slab, 0, P, ibuf), 2 * P * 12)):
+            for _ in range(3):
+                fn()
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(10):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            report(f"interop {name}, stride {stride}, {P >> 20} Mi rows", e0.elapsed_time(e1) / 10, nbytes)
+        ctx.device_free(buf)
+        ctx.device_free(ibuf)
+        ctx.close()
+
+
+SCENARIOS = {"chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math, "taper": taper}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
