@@ -151,21 +151,76 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's multi-threaded C5 update (oracle/vfx_oracle.c::orc_update_c5_parallel)
 # ---------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """(logical CPUs this process may run on, physical cores among them, how it was decided). Launchers export
+    OMP_NUM_THREADS=1 (torchrun does) — that says nothing about the machine, so it is ignored: the affinity mask, the
+    cgroup CPU quota and the sibling lists of /sys decide."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    how = f"{len(cpus)} logical CPUs in the affinity mask"
+    cores = set()
+    for c in cpus:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+            pkg = open(f"/sys/devices/system/cpu/cpu{c}/topology/physical_package_id").read().strip()
+            cores.add((pkg, sib))
+        except OSError:
+            cores.add(("?", str(c)))
+    n_cores = len(cores)
+    quota = None
+    try:  # cgroup v2: "max 100000" or "1600000 100000"
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = max(1, int(q) // int(period))
+    except Exception:
+        try:  # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = max(1, q // period)
+        except Exception:
+            pass
+    if quota is not None and quota < n_cores:
+        how += f", {n_cores} physical cores, cgroup quota {quota} CPUs"
+        n_cores = quota
+    else:
+        how += f", {n_cores} physical cores"
+    return len(cpus), max(1, n_cores), how
+
+
+def cpu_workload_particles():
+    """The 64 Mi-particle C5 instance itself when the host has the memory for it (2.9 GiB of buffers), else 8 Mi."""
+    need = TOTAL_PARTICLES * (32 + 12 + 1)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    if avail is None or avail > 3 * need:
+        return TOTAL_PARTICLES, "the full 64 Mi-particle instance"
+    return 8 * 1024 * 1024, f"an 8 Mi-particle instance (host has {avail >> 20} MiB available, the 64 Mi one needs {need >> 20} MiB)"
+
+
 class CpuC5:
-    def __init__(self, particles: int):
+    """One C5 instance on the host, stepped with the oracle's OpenMP port of the reference's passes."""
+
+    def __init__(self, particles: int, threads: int):
         import numpy as np
+        # one thread per physical core, pinned, neighbours first (must be in the environment before libgomp starts)
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
         from oracle import c_oracle as O
         self.np, self.O = np, O
         self.orc = O.load()
         self.n = particles
-        try:
-            usable = len(os.sched_getaffinity(0))
-        except AttributeError:
-            usable = os.cpu_count() or 1
-        self.threads = max(1, min(self.orc.orc_max_threads(), usable))
+        self.threads = threads
+        self.orc.orc_set_threads(threads)  # for the fill / reset loops; the update takes its own count
         self.particles = np.empty((particles, 8), dtype=np.float32)
-        self.indirect = np.zeros((particles, 3), dtype=np.uint32)
-        self.indirect[:, 2] = np.arange(particles, dtype=np.uint32)
+        self.indirect = np.empty((particles, 3), dtype=np.uint32)
+        # first touch by the threads that will own the rows (static schedule, same partition as the update)
+        self.orc.orc_indirect_reset(O.ptr(self.indirect), 0, particles)
         self.orc.orc_fill_c5(O.ptr(self.particles), O.ptr(self.indirect), 0, particles, 42, 1e9, 1e9)
         self.flags = np.zeros(particles, dtype=np.uint8)
         self.sim = O.SimParams(DT, 0, DT, 0, DT, 0, 1)
@@ -182,57 +237,62 @@ class CpuC5:
         self.bi[0].prefix_sum_count = 1
         self.dispatch = np.zeros(3, dtype=np.uint32)
         self.k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
+        self.frames = 0
 
-    def calibrate(self):
-        """Pick the OpenMP thread count that is actually fastest on this host: "all logical CPUs" can be far from it
-        (hyper-threads, or a container CPU quota below the affinity mask makes spinning OpenMP barriers collapse).
-        Times two frames for max, max/2, ... max/16 threads (and the cgroup CPU quota) and keeps the best."""
-        best_t, best_threads = None, self.threads
-        top = self.threads
-        candidates = {max(1, top >> k) for k in range(5)}  # max, max/2, ..., max/16
-        try:  # cgroup v2 CPU quota, e.g. "1600000 100000" = 16 CPUs worth of time
-            quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-            if quota != "max":
-                candidates.add(max(1, min(top, int(quota) // int(period))))
-        except Exception:
-            pass
-        for threads in sorted(candidates, reverse=True):
-            self.threads = threads
-            self.step()
-            t0 = time.perf_counter()
-            self.step()
-            self.step()
-            el = time.perf_counter() - t0
-            if best_t is None or el < best_t:
-                best_t, best_threads = el, threads
-        self.threads = best_threads
-        return best_threads
-
-    def step(self):
+    def step(self, threads=None):
         """One full frame: indirect -> prefix sum -> update (all of vfx_*.wgsl's work for this config)."""
         o, P, u32 = self.orc, C.POINTER, C.c_uint32
         o.orc_indirect(C.byref(self.sim), self.md, self.draw.ctypes.data_as(P(u32)), self.sp, self.prefix.ctypes.data_as(P(u32)), None, 0)
         o.orc_prefix_sum(self.bi, 1, self.prefix.ctypes.data_as(P(u32)), self.dispatch.ctypes.data_as(P(u32)))
         alive = o.orc_update_c5_parallel(C.byref(self.sim), self.draw.ctypes.data_as(P(u32)), self.O.ptr(self.particles),
-                                         self.O.ptr(self.indirect), self.sp, self.md, self.k, self.O.ptr(self.flags), self.threads)
+                                         self.O.ptr(self.indirect), self.sp, self.md, self.k, self.O.ptr(self.flags),
+                                         self.threads if threads is None else threads)
+        if alive != self.n:
+            raise RuntimeError(f"CPU arm: {alive} of {self.n} particles alive")
+        self.frames += 1
         return alive
 
+    def checksum(self):
+        return int(self.orc.orc_checksum(self.O.ptr(self.particles), 0, self.n, 8))
 
-def cpu_baseline(seconds: float, sample: int = 8 * 1024 * 1024):
-    arm = CpuC5(sample)
-    arm.calibrate()  # includes the warm-up
-    t0 = time.perf_counter()
-    steps = 0
-    while True:
-        arm.step()
-        steps += 1
-        el = time.perf_counter() - t0
-        if el >= seconds or steps >= 200:
-            break
-    return {"value": sample * steps / el, "unit": UNIT, "cores": arm.threads, "kind": "port",
-            "sample": f"{steps} full frames (indirect+prefix-sum+update) of a {sample}-particle C5 instance, {el:.1f} s wall, "
-                      f"oracle/vfx_oracle.c OpenMP x{arm.threads} (fastest of max, max/2 ... max/16 threads)",
-            "gbps": BYTES_PER_PARTICLE_STEP * sample * steps / el / 1e9}
+    def timed_steps(self, steps, threads=None):
+        out = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.step(threads)
+            out.append(time.perf_counter() - t0)
+        return out
+
+
+def measure_cpu_arm(steps: int, warmup: int, budget_s: float):
+    """The CPU arm of both the `cpu_baseline` block and `--impl reference`: same workload, same threads, same timing, so
+    that the two agree on the same box. Returns (value over the timed steps, per-step seconds, description dict)."""
+    n, what = cpu_workload_particles()
+    logical, cores, how = usable_cpus()
+    arm = CpuC5(n, cores)
+    w = arm.timed_steps(max(1, warmup))
+    est = min(w)
+    steps = max(1, min(steps, int(budget_s / max(est, 1e-6))))  # exactly the K asked for unless that would take minutes
+    ts = arm.timed_steps(steps)
+    total = sum(ts)
+    med5 = statistics.median((ts + arm.timed_steps(max(0, 5 - steps)))[:5])  # BASELINE.md §3: median of five timed steps
+    # BASELINE.md §3 also asks for the single-thread figure: one warm step, two timed
+    one = arm.timed_steps(3, threads=1)[1:]
+    desc = {
+        "cores": cores, "kind": "port", "particles_per_step": n, "steps": steps,
+        "sample": f"{steps} full frames (indirect + prefix-sum + update) of {what}, {total:.1f} s wall, oracle/vfx_oracle.c, "
+                  f"OpenMP x{cores} (one thread per physical core, OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}; {how}; "
+                  f"OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')} from the launcher ignored); the Rust/wgpu "
+                  "reference cannot be built in this image (no Rust toolchain, no Vulkan ICD)",
+        "median_of_5_value": n / med5, "single_thread_value": n / statistics.median(one),
+        "gbps": BYTES_PER_PARTICLE_STEP * n * steps / total / 1e9,
+    }
+    return n * steps / total, ts, desc, arm
+
+
+def cpu_baseline(seconds: float):
+    value, _, desc, arm = measure_cpu_arm(20, 2, seconds)
+    return {"value": value, "unit": UNIT, **desc}, arm
 
 
 def run_reference(args):
@@ -241,26 +301,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8 * 1024 * 1024
-    arm = CpuC5(sample)
-    arm.calibrate()  # fastest thread count on this host; also warms the pages up
-    for _ in range(max(1, min(args.warmup, 2))):
-        arm.step()
-    steps = max(1, min(args.steps, 40))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        arm.step()
-    el = time.perf_counter() - t0
-    value = sample * steps / el
+    value, ts, desc, _ = measure_cpu_arm(args.steps, min(args.warmup, 2), 60.0)
+    steps = desc["steps"]
+    n = desc["particles_per_step"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "warmup": args.warmup, "ms_per_step": sum(ts) / steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5 synthetic 64M-particle SoA buffer, Accel+LinearDrag update (bounded CPU sample)",
-                   "particles_per_step": sample, "dt": DT},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": "port",
-                         "sample": f"one full frame (indirect+prefix-sum+update) of an {sample}-particle C5 instance per step, {steps} steps, OpenMP x{arm.threads} "
-                                   "(fastest of max, max/2 ... max/16 threads; oracle port: the Rust/wgpu reference cannot be built in this image)"},
+        "config": {"workload": "C5 synthetic 64M-particle SoA buffer, Accel+LinearDrag update, sharded by index range",
+                   "particles_total": n, "particles_per_step": n, "dt": DT,
+                   "note": "CPU arm: one host runs the whole instance whatever --gpus says"},
+        "cpu_baseline": {"value": value, "unit": UNIT, **desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -305,9 +356,10 @@ def run_b200(args):
     slab = ctx.slab_create(per_rank, recipes.C5_STRIDE)
     # the C5 effect authored through the Module/Modifier/EffectAsset API and lowered to CUDA C by the library
     effect = ctx.effect_compile(recipes.c5_asset(per_rank).generate())
-    # shard `rank` owns rows [rank*per_rank, (rank+1)*per_rank) of the logical 64M instance: same
-    # counter-based state as a 1-GPU run would hold for those rows (seed mixes the global row)
-    ctx.slab_fill_c5(slab, 0, per_rank, 42 + rank, 1e9, 1e9)
+    # shard `rank` owns logical rows [first_row, end_row) of the 64M instance under shard-local indices: the same
+    # counter-based values a 1-GPU run holds for those rows (one seed for the whole instance, hashed with the LOGICAL row)
+    logical_first = first_row if args.scaling == "strong" else rank * per_rank
+    ctx.slab_fill_c5(slab, 0, per_rank, 42, 1e9, 1e9, logical_first=logical_first)
     md = R.initial_metadata(per_rank, 0, 8)
     md.alive_count = per_rank
     md.max_spawn = 0
@@ -420,9 +472,17 @@ def run_b200(args):
     e2e_value = total * args.steps / (ms_e2e * 1e-3)
     h2d = 64 + 24 + 4 + 4 + 128 + 12  # frame header + batch info + tile size (+pad) + spawner row + range/spawn-prefix/prefix words
 
-    # -- correctness guard inside the bench: the state must have advanced (age = steps*dt) and nothing died
+    # -- correctness guard inside the bench: nothing died, and the checksum of the whole logical instance (each shard
+    # hashes its rows under their LOGICAL index; the sum over the shards is independent of how many GPUs hold it)
     mdr = ctx.read_metadata(0)
     assert mdr.alive_count == per_rank and mdr.max_update == per_rank, "bench state corrupted"
+    frames_run = ctx.frames_simulated
+    shard_sum = ctx.slab_checksum(slab, 0, per_rank, index_base=logical_first)
+    state_sum = shard_sum
+    if world > 1:
+        t = torch.tensor([shard_sum - (1 << 64) if shard_sum >= (1 << 63) else shard_sum], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)  # wraps mod 2^64
+        state_sum = int(t.item()) % (1 << 64)
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -440,7 +500,10 @@ def run_b200(args):
                        "particles_total": total, "particles_per_gpu": per_rank, "dt": DT, "steps_per_sec": args.steps / (ms * 1e-3),
                        "ms_per_step_by_rank": value_per_rank_ms,
                        "l2": "inputs larger than L2 (per-GPU working set %.0f MB per step)" % (per_rank * 72 / 1e6),
-                       "parallelism": f"index-range shards x{n_gpus}, no collective"},
+                       "parallelism": f"index-range shards x{n_gpus}, no collective",
+                       "state_checksum": {"frames": int(frames_run), "sum_over_shards": f"0x{state_sum:016x}",
+                                          "note": "order-independent 64-bit checksum of all particle records after `frames` frames, rows hashed "
+                                                  "under their logical index: equal for every --gpus N at equal `frames`"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,
                     "ms_per_step": ms_e2e / args.steps, "frames_in_flight": FRAMES_IN_FLIGHT,
                     "note": "host per-frame tables (spawner row, batch info, prefix sums, sim params) copied in, "
@@ -463,7 +526,32 @@ def run_b200(args):
             except Exception:
                 pass
         if not args.no_cpu_baseline and n_gpus == 1:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            cb, arm = cpu_baseline(args.cpu_seconds)
+            line["cpu_baseline"] = cb
+            # parity inside the bench: replay as many frames as the CPU arm ran on a fresh slab of the same instance and
+            # compare the whole-state checksums (C5 is IEEE-exact: bit-for-bit)
+            n_cpu, frames_cpu = cb["particles_per_step"], arm.frames
+            c2 = hb.Context(local_rank, stream.cuda_stream)
+            s2 = c2.slab_create(n_cpu, recipes.C5_STRIDE)
+            e2 = c2.effect_compile(recipes.c5_asset(n_cpu).generate())
+            c2.slab_fill_c5(s2, 0, n_cpu, 42, 1e9, 1e9)
+            md2 = R.initial_metadata(n_cpu, 0, 8)
+            md2.alive_count, md2.max_spawn = n_cpu, 0
+            c2.metadata_insert(0, md2)
+            c2.draw_args_insert(0)
+            c2.upload_spawners_raw(spawners, 1)
+            c2.upload_batches_raw(batches, 1, prefix, 1)
+            c2.set_sim_params(DT, 0.0, 1)
+            l2 = (N.BatchLaunch * 1)(N.BatchLaunch.make(e2, s2, 0, 0))
+            for _ in range(frames_cpu):
+                c2.simulate_raw(l2, 1)
+            gpu_sum = c2.slab_checksum(s2, 0, n_cpu)
+            cpu_sum = arm.checksum()
+            c2.close()
+            line["parity_check"] = {"particles": n_cpu, "frames": frames_cpu, "gpu_checksum": f"0x{gpu_sum:016x}",
+                                    "cpu_oracle_checksum": f"0x{cpu_sum:016x}", "match": gpu_sum == cpu_sum}
+            if gpu_sum != cpu_sum:
+                raise SystemExit("bench.py: GPU state differs from the CPU oracle's after the same number of frames")
         print(json.dumps(line), flush=True)
     for ptr in pinned:
         N.lib.hnb_host_free(ptr)

@@ -156,6 +156,7 @@ SIGNATURES = {
     "hnb_sync": (i32, [vp]),
     "hnb_ctx_stream": (C.c_size_t, [vp]),
     "hnb_ctx_launch_count": (C.c_uint64, [vp]),
+    "hnb_ctx_frame_count": (None, [vp, P(C.c_uint64), P(C.c_uint64)]),
     "hnb_slab_create": (i32, [vp, u32, u32, P(u32)]),
     "hnb_slab_create_ex": (i32, [vp, u32, u32, u32, P(u32)]),
     "hnb_slab_destroy": (i32, [vp, u32]),
@@ -214,6 +215,7 @@ SIGNATURES = {
     "hnb_host_alloc": (vp, [C.c_size_t]),
     "hnb_host_free": (None, [vp]),
     "hnb_ctx_read_debug": (i32, [vp, P(C.c_uint64), i32]),
+    "hnb_ctx_read_debug_ring": (i32, [vp, P(C.c_uint64), i32]),
     "hnb_ctx_measure_sm_mhz": (i32, [vp, u32, P(C.c_double)]),
     "hnb_ctx_enable_kernel_timing": (i32, [vp, i32]),
     "hnb_ctx_kernel_time_ms": (i32, [vp, P(C.c_double), P(C.c_uint64)]),

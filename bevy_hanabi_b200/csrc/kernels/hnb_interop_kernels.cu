@@ -38,12 +38,15 @@ __global__ void __launch_bounds__(TR_THREADS) k_transpose(u32* __restrict__ aos,
     }
     for (u32 p = 0; p < num_planes; ++p) {
         const u32 w = planes.words[p], off = planes.word_off[p];
+        const bool aligned16 = ((stride_words | off) & 3u) == 0u;
         for (u32 r = threadIdx.x; r < rows; r += TR_THREADS) {
             u32* t = tr_tile + r * stride_words + off;
             const u64 grow = u64(first) + row0 + r;
             if (w == 4u) {
                 uint4* g = (uint4*)planes.ptr[p] + grow;
-                if (TO_AOS) { const uint4 v = *g; t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w; }
+                if (aligned16) {  // record stride and piece offset multiples of 16 bytes: one 128-bit shared-memory access
+                    if (TO_AOS) *(uint4*)t = *g; else *g = *(const uint4*)t;
+                } else if (TO_AOS) { const uint4 v = *g; t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w; }
                 else *g = make_uint4(t[0], t[1], t[2], t[3]);
             } else if (w == 8u) {  // sector planes: two 16-byte pieces per element
                 uint4* g = (uint4*)planes.ptr[p] + 2ull * grow;
@@ -92,8 +95,9 @@ __global__ void __launch_bounds__(TR_THREADS) k_indirect_rows(u32* __restrict__ 
     }
 }
 
-// rows per CTA of the record transposes: as many as fit 48 KB of shared memory, at most 256
-static inline u32 transpose_rows(u32 stride_words) { return std::max(1u, std::min(256u, (48u * 1024u) / (stride_words * 4u))); }
+// rows per CTA of the record transposes: as many as fit 48 KB of shared memory, at most 1024
+// (1024 rows of 32 bytes: every thread moves four records per plane, enough loads in flight to cover the two barriers)
+static inline u32 transpose_rows(u32 stride_words) { return std::max(1u, std::min(1024u, (48u * 1024u) / (stride_words * 4u))); }
 static inline u32 count_planes(const PlaneSet& planes, u32 stride_words) {
     u32 n = 0, covered = 0;
     while (n < HNB_MAX_PLANES && covered < stride_words && planes.words[n]) covered += planes.words[n++];

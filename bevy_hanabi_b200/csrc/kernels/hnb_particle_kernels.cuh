@@ -335,9 +335,21 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // those kernels write has been read yet; from here on it is all visible. The next kernel in the stream (the next
     // frame's bookkeeping) may take SM slots as this grid's CTAs retire.
     hnb_pdl_launch_dependents();
+#if HNB_PROFILE
+    // per-frame timeline ring (diagnostics, tools/diag_frame_chain.py): 4 words per frame at debug[16 + 4 * (epoch & 63)]:
+    // ~(earliest CTA residency), ~(earliest start after the dependency wait), ~(earliest end of a first sub-tile), latest warp end
+    unsigned long long prof_resident;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_resident));
+#endif
     hnb_pdl_wait();
 #if HNB_PROFILE
     if (lane == 0 && P.debug) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&P.debug[8], ~_g); }
+    unsigned long long* const prof_ring = P.debug ? P.debug + 16 + 4 * (P.frame->epoch & 63u) : nullptr;
+    if (lane == 0 && prof_ring) {
+        unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g));
+        atomicMax(&prof_ring[0], ~prof_resident);
+        atomicMax(&prof_ring[1], ~_g);
+    }
 #endif
 
     const BatchInfo bi = *P.batch_info;
@@ -531,6 +543,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                 if (lane == 0) survivors[j * HNB_TILE_K + k] = ballot;
                 tile_alive += __popc(ballot);
             }
+#if HNB_PROFILE
+            if (prof_first && j == 0u && lane == 0 && prof_ring) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&prof_ring[2], ~_g); }
+#endif
         }
         // Publish this tile's survivor count right away: the first tile of an instance knows its prefix (0),
         // the others publish an AGGREGATE that successors can sum over while this tile's own prefix is
@@ -611,6 +626,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         atomicMax(&P.debug[6], (unsigned long long)(clock64() - prof_start));  // longest-lived warp (cycles)
     }
     HNB_PROF_TIME(11, false) HNB_PROF_TIME(13, true)
+    if (lane == 0 && prof_ring) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&prof_ring[3], _g); }
 #endif
 }
 

@@ -116,6 +116,7 @@ struct EventBuffer {
 };
 
 // Pinned staging slot of the per-frame upload (see flush_arena).
+constexpr size_t kDebugWords = 16 + 4 * 64;
 constexpr int kStageSlots = 32;  // frames the host may queue ahead of the GPU before blocking
 struct StageSlot {
     char* h = nullptr;
@@ -197,7 +198,7 @@ struct hnb_ctx {
     bool pdl = true;          // HNB_PDL=0: launch the frame chain without programmatic dependent launch
     bool plan_dirty = false;  // plan_batch changed a tile-size or range word of the host frame block since the last upload
     uint64_t frame_copies = 0, frames = 0;  // hnb_simulate calls that needed the host->device copy of the frame block / all calls
-    unsigned long long* d_debug = nullptr;  // 16 diagnostic counters (HNB_PROFILE kernels)
+    unsigned long long* d_debug = nullptr;  // 16 diagnostic counters + a 64-frame timeline ring of 4 words (HNB_PROFILE kernels)
 
     hnb::FrameHeader* header() { return reinterpret_cast<hnb::FrameHeader*>(h_arena); }
     template <typename T> T* h_at(size_t off) { return reinterpret_cast<T*>(h_arena + off); }
@@ -758,8 +759,8 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
         if (const char* env = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::max(0, std::min(atoi(env), 31));
         if (const char* env = getenv("HNB_PDL")) c->pdl = atoi(env) != 0;
         ensure_arena(c.get(), 0, 0);
-        CUDA_CHECK(cudaMalloc((void**)&c->d_debug, 16 * 8));
-        CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
+        CUDA_CHECK(cudaMalloc((void**)&c->d_debug, kDebugWords * 8));
+        CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, kDebugWords * 8, c->stream));
         *out = c.release();
     });
 }
@@ -803,6 +804,10 @@ int32_t hnb_sync(hnb_ctx* c) {
 }
 uintptr_t hnb_ctx_stream(hnb_ctx* c) { return (uintptr_t)c->stream; }
 uint64_t hnb_ctx_launch_count(hnb_ctx* c) { return c->launches; }
+void hnb_ctx_frame_count(hnb_ctx* c, uint64_t* frames, uint64_t* frame_block_copies) {
+    if (frames) *frames = c->frames;
+    if (frame_block_copies) *frame_block_copies = c->frame_copies;
+}
 
 // ---- slabs ----------------------------------------------------------------------------------
 int32_t hnb_slab_create(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, hnb_slab* out) { return hnb_slab_create_ex(c, capacity_rows, stride, 0u, out); }
@@ -1586,6 +1591,14 @@ int32_t hnb_ctx_read_debug(hnb_ctx* c, uint64_t* out16, int32_t clear) {
     return guarded([&] {
         CUDA_CHECK(cudaMemcpyAsync(out16, c->d_debug, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
         if (clear) CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, 16 * 8, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_ctx_read_debug_ring(hnb_ctx* c, uint64_t* out256, int32_t clear) {
+    return guarded([&] {
+        CUDA_CHECK(cudaMemcpyAsync(out256, c->d_debug + 16, 256 * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (clear) CUDA_CHECK(cudaMemsetAsync(c->d_debug + 16, 0, 256 * 8, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     });
 }

@@ -203,9 +203,26 @@ class Context:
     def launch_count(self) -> int:
         return lib.hnb_ctx_launch_count(self._h)
 
+    @property
+    def frames_simulated(self) -> int:
+        f, c = C.c_uint64(0), C.c_uint64(0)
+        lib.hnb_ctx_frame_count(self._h, C.byref(f), C.byref(c))
+        return f.value
+
+    @property
+    def frame_block_copies(self) -> int:
+        f, c = C.c_uint64(0), C.c_uint64(0)
+        lib.hnb_ctx_frame_count(self._h, C.byref(f), C.byref(c))
+        return c.value
+
     def read_debug(self, clear: bool = True) -> list[int]:
         out = (C.c_uint64 * 16)()
         check(lib.hnb_ctx_read_debug(self._h, out, int(clear)))
+        return list(out)
+
+    def read_debug_ring(self, clear: bool = True) -> list[int]:
+        out = (C.c_uint64 * 256)()
+        check(lib.hnb_ctx_read_debug_ring(self._h, out, int(clear)))
         return list(out)
 
     def measure_sm_mhz(self, window_us: int = 50) -> float:

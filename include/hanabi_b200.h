@@ -158,6 +158,9 @@ HNB_API int32_t hnb_sync(hnb_ctx* ctx);
 HNB_API uintptr_t hnb_ctx_stream(hnb_ctx* ctx);
 /** Number of kernels launched by this context since creation (for bench `gpu_launches`). */
 HNB_API uint64_t hnb_ctx_launch_count(hnb_ctx* ctx);
+/** hnb_simulate() calls so far, and how many of them had to copy the frame block host->device (the others carried the
+ *  64-byte frame header in kernel parameter space: no table row, tile size or init range had changed). */
+HNB_API void hnb_ctx_frame_count(hnb_ctx* ctx, uint64_t* frames, uint64_t* frame_block_copies);
 
 /* ------------------------------------------------------------------------------------ */
 /* 3. Particle slabs ≙ ParticleSlab::new (reference src/render/effect_cache.rs:246-356)  */
@@ -436,6 +439,9 @@ HNB_API void hnb_host_free(void* p);
 /** Read (and optionally clear) the 16 diagnostic counters written by kernels compiled with HNB_PROFILE=1
  *  (per-phase cycle totals of hnb_update; see hnb_particle_kernels.cuh). */
 HNB_API int32_t hnb_ctx_read_debug(hnb_ctx* ctx, uint64_t* out16, int32_t clear);
+/** The HNB_PROFILE kernels' per-frame timeline ring: 64 frames x {~earliest CTA residency, ~earliest start after the
+ *  dependency wait, ~earliest end of a first sub-tile, latest warp end} in %globaltimer ns, indexed by epoch & 63. */
+HNB_API int32_t hnb_ctx_read_debug_ring(hnb_ctx* ctx, uint64_t* out256, int32_t clear);
 HNB_API int32_t hnb_ctx_measure_sm_mhz(hnb_ctx* ctx, uint32_t window_us, double* mhz);
 HNB_API int32_t hnb_ctx_enable_kernel_timing(hnb_ctx* ctx, int32_t enabled);
 HNB_API int32_t hnb_ctx_kernel_time_ms(hnb_ctx* ctx, double* update_ms_total, uint64_t* update_launches);
