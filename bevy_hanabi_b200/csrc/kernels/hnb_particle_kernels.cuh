@@ -60,15 +60,6 @@ namespace hnb {
 #ifndef HNB_PROFILE
 #define HNB_PROFILE 0  // 1: accumulate per-phase cycle counters into BatchParams::debug (diagnostics)
 #endif
-#ifndef HNB_TILE_TAPER
-#define HNB_TILE_TAPER 0  // 1: honour the taper fields of the tile size word (hnb_tile_word): the tail rows of an instance
-                          // are processed in smaller tiles. Set by the host together with the word (HNB_TILE_TAPER env).
-#endif
-#if HNB_TILE_TAPER
-#define HNB_PT_BUFFER(pt) ((pt).buffer & 1u)  // PendingTile::buffer = stash buffer | chunks of the tile << 1
-#else
-#define HNB_PT_BUFFER(pt) ((pt).buffer)
-#endif
 #ifndef HNB_LOOKBACK_SLEEP_NS
 #define HNB_LOOKBACK_SLEEP_NS 0  // back-off between polls of an unpublished predecessor (0 = spin)
 #endif
@@ -212,9 +203,6 @@ struct PendingTile {
 HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const u32* survivors, const u32 (*pidx_stash)[32],
                              u32 chunks, u32 epoch, u32 lane, long long& prof_polls) {
     u64* const states = P.tile_state;
-#if HNB_TILE_TAPER
-    chunks = pt.buffer >> 1u;  // sub-tiles of THIS tile (big or small)
-#endif
     const u32 tile = pt.tile, row0 = pt.row0, tile_alive = pt.tile_alive, max_update = pt.max_update;
     const u32 base_particle = pt.base_particle, inst_first_tile = pt.inst_first_tile;
     EffectMetadata* const md = &P.metadata[pt.metadata_index];
@@ -372,17 +360,8 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     u64* const states = P.tile_state;
     // rows per tile = 32 lanes * K rows per lane * chunks; the chunk count is chosen per launch by the
     // host (and used by the bookkeeping kernel for the tile prefix), so it is a run-time value here
-#if HNB_TILE_TAPER
-    const u32 tile_word = P.tile_rows;
-    const u32 tile_rows = hnb_tile_rows_big(tile_word);
-    const u32 small_rows = tile_rows >> hnb_tile_shift(tile_word);
-    const u32 big_chunks = tile_rows / (32u * HNB_TILE_K), small_chunks = small_rows / (32u * HNB_TILE_K);
-    u32 inst_big_tiles = 0u;  // big tiles of the cached instance; the tiles after them are small
-    u32 chunks = big_chunks;
-#else
-    const u32 tile_rows = P.tile_rows;
+    const u32 tile_rows = hnb_tile_rows(P.tile_rows);
     const u32 chunks = tile_rows / (32u * HNB_TILE_K);
-#endif
     PendingTile& pending = sh_pending[warp];
     u32 cur = 0u;  // buffer the tile being streamed uses
 
@@ -463,21 +442,8 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
 #if HNB_EMIT_EVENTS
             hnb_ctx.base_child_index = md->base_child_index;
 #endif
-#if HNB_TILE_TAPER
-            {
-                u32 n_small;
-                inst_big_tiles = hnb_tile_split(max_update, tile_word, &n_small);
-            }
-#endif
         }
-#if HNB_TILE_TAPER
-        const u32 tile_in_inst = tile - inst_first_tile;
-        const bool big = tile_in_inst < inst_big_tiles;
-        const u32 row0 = big ? tile_in_inst * tile_rows : inst_big_tiles * tile_rows + (tile_in_inst - inst_big_tiles) * small_rows;
-        chunks = big ? big_chunks : small_chunks;
-#else
         const u32 row0 = (tile - inst_first_tile) * tile_rows;
-#endif
         u32* const survivors = sh_survivors[warp][cur];
         u32(*const pidx_stash)[32] = sh_pidx[warp][cur];
 
@@ -570,7 +536,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         __syncwarp();
         if (pending.valid) {
             const PendingTile pt = pending;
-            hnb_compact_tile(P, pt, sh_survivors[warp][HNB_PT_BUFFER(pt)], sh_pidx[warp][HNB_PT_BUFFER(pt)], chunks, epoch, lane, prof_polls);
+            hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
         }
         __syncwarp();
         if (lane == 0) {
@@ -578,11 +544,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             pending.base_particle = base_particle; pending.max_update = max_update; pending.write_index = write_index;
             pending.render_index = render_index; pending.inst_first_tile = inst_first_tile; pending.inst_end_tile = inst_end_tile;
             pending.metadata_index = metadata_index;
-#if HNB_TILE_TAPER
-            pending.buffer = cur | (chunks << 1u);
-#else
             pending.buffer = cur;
-#endif
         }
         cur ^= 1u;
         __syncwarp();
@@ -593,11 +555,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             pt.valid = 1u; pt.tile = tile; pt.row0 = row0; pt.tile_alive = tile_alive; pt.base_particle = base_particle;
             pt.max_update = max_update; pt.write_index = write_index; pt.render_index = render_index;
             pt.inst_first_tile = inst_first_tile; pt.inst_end_tile = inst_end_tile; pt.metadata_index = metadata_index;
-#if HNB_TILE_TAPER
-            pt.buffer = cur | (chunks << 1u);
-#else
             pt.buffer = cur;
-#endif
             hnb_compact_tile(P, pt, survivors, pidx_stash, chunks, epoch, lane, prof_polls);
             __syncwarp();
         }
@@ -612,7 +570,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     __syncwarp();
     if (pending.valid) {
         const PendingTile pt = pending;
-        hnb_compact_tile(P, pt, sh_survivors[warp][HNB_PT_BUFFER(pt)], sh_pidx[warp][HNB_PT_BUFFER(pt)], chunks, epoch, lane, prof_polls);
+        hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
     }
 #endif
 #if HNB_PROFILE

@@ -49,38 +49,20 @@ struct ChildInfo {  // GpuChildInfo, event.rs:204
 };
 
 // ---- update tile size word (BatchParams::tile_rows, StaticTables::batch_tile_size) -----------------------------
-//   [15:0]  S  rows of a (big) tile, a multiple of 32*K
-//   [19:16] f  taper shift: small tiles have s = S >> f rows
-//   [31:20] w  taper length in big tiles: the last min(rows, w*S) rows of an INSTANCE are cut into small tiles
-// w == 0 (the default) is the plain layout: ceil(rows / S) tiles of S rows. With a taper the instance has
-// n_big = (rows - min(rows, w*S)) / S big tiles followed by ceil((rows - n_big*S) / s) small ones, so that the tail of
-// a launch (one tile time) shrinks by 2^f. The bookkeeping kernels and hnb_update share this rule.
+//   [15:0]  S  rows of a tile, a multiple of 32*K
+//   [31]    slot order (HNB_EFFECT_SLOT_ORDER): tiles cut the instance's SLOTS [0, capacity), not its alive-list rows
+// An instance with `rows` rows (alive particles, or slots in slot order) has ceil(rows / S) tiles; the bookkeeping
+// kernels and hnb_update share this rule.
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 #define HNB_HD __host__ __device__ __forceinline__
 #else
 #define HNB_HD inline
 #endif
-HNB_HD u32 hnb_tile_word(u32 rows_big, u32 shift, u32 taper_tiles) { return rows_big | (shift << 16) | (taper_tiles << 20); }
-HNB_HD u32 hnb_tile_rows_big(u32 word) { return word & 0xffffu; }
-HNB_HD u32 hnb_tile_shift(u32 word) { return (word >> 16) & 15u; }
-HNB_HD u32 hnb_tile_taper(u32 word) { return word >> 20; }
-// number of big tiles of an instance with `rows` rows; *n_small = number of small tiles that follow
-HNB_HD u32 hnb_tile_split(u32 rows, u32 word, u32* n_small) {
-    const u32 S = hnb_tile_rows_big(word), w = hnb_tile_taper(word);
-    if (w == 0u) {
-        *n_small = 0u;
-        return (rows + S - 1u) / S;
-    }
-    const u32 taper_rows = w * S;  // <= 4095 * 65535
-    const u32 n_big = (rows - (rows < taper_rows ? rows : taper_rows)) / S;
-    const u32 s = S >> hnb_tile_shift(word);
-    *n_small = (rows - n_big * S + s - 1u) / s;
-    return n_big;
-}
+#define HNB_TILE_SLOT_ORDER 0x80000000u
+HNB_HD u32 hnb_tile_rows(u32 word) { return word & 0xffffu; }
 HNB_HD u32 hnb_tile_count(u32 rows, u32 word) {
-    u32 n_small;
-    const u32 n_big = hnb_tile_split(rows, word, &n_small);
-    return n_big + n_small;
+    const u32 S = hnb_tile_rows(word);
+    return (rows + S - 1u) / S;
 }
 
 #define HNB_DRAW_INDEXED_INDIRECT_STRIDE 5u  // vfx_common.wgsl:146
@@ -130,7 +112,7 @@ struct BatchParams {
     u32 emit_events_capacity[HNB_MAX_EVENT_BINDINGS];
     u32 init_thread_count;           // ceil64(total_spawn_count): logical init threads of this launch
     u32 properties_stride;           // bytes
-    u32 tile_rows;                   // tile size word of this launch (see hnb_tile_word): rows per tile (multiple of 32*K, <= 32*K*HNB_MAX_CHUNKS) + taper
+    u32 tile_rows;                   // tile size word of this launch (see hnb_tile_rows): rows per tile (multiple of 32*K, <= 32*K*HNB_MAX_CHUNKS) + flags
     u32 _pad0;
     unsigned long long* debug;       // 16 counters, written only by kernels compiled with HNB_PROFILE=1
     u32* event_counts[HNB_MAX_EVENT_BINDINGS];  // HNB_EFFECT_ORDERED_EVENTS: events requested by update row r on channel b (else NULL)

@@ -103,7 +103,6 @@ struct Effect {
     uint64_t hash = 0;
     KernelModule* km = nullptr;
     uint32_t tile_k = 4, flags = 0, particle_stride = 0, parent_stride = 0, rows_per_lane = 16, update_smem = 0;
-    hnb_rt::TileTaper taper;  // the module was generated with HNB_TILE_TAPER when percent != 0
     int update_blocks_per_sm = 1;
     uint32_t props_size = 0, props_stride = 0, props_rows = 0;
     char* d_props = nullptr;
@@ -473,18 +472,8 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     }
     chunks = std::max(1u, std::min(chunks, lp.fx->rows_per_lane / lp.fx->tile_k));
     const uint32_t tile = sub_tile * chunks;
-    // Tile size word shared with the bookkeeping kernels (hnb_tile_word). Experimental taper: the last `percent` % of a
-    // wave of big tiles of every instance in tiles of tile >> shift rows (never below one sub-tile).
-    uint32_t tile_word = tile, small_tile = tile;
-    if (lp.fx->taper.percent && chunks > 1) {
-        uint32_t shift = 0;
-        while ((chunks >> (shift + 1)) >= 1 && shift < lp.fx->taper.shift && ((chunks >> (shift + 1)) << (shift + 1)) == chunks) ++shift;
-        const uint32_t taper_tiles = (uint32_t)std::min<uint64_t>(4095, std::max<uint64_t>(1, uint64_t(total_warps) * lp.fx->taper.percent / 100));
-        if (shift) {
-            tile_word = hnb::hnb_tile_word(tile, shift, taper_tiles);
-            small_tile = tile >> shift;
-        }
-    }
+    // Tile size word shared with the bookkeeping kernels (hnb_tile_rows + flags)
+    const uint32_t tile_word = tile, small_tile = tile;
     if (c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] != tile_word) {
         c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile_word;
         c->plan_dirty = true;
@@ -1107,7 +1096,6 @@ struct EffectBlueprint {
     uint64_t hash = 0;
     bool fast_math = false;
     uint32_t tile_k = 4, rows_per_lane = 16, update_smem = 0, flags = 0, particle_stride = 0, parent_stride = 0, props_size = 0;
-    hnb_rt::TileTaper taper;
 };
 static EffectBlueprint make_blueprint(const hnb_effect_desc& desc) {
     EffectBlueprint bp;
@@ -1117,7 +1105,6 @@ static EffectBlueprint make_blueprint(const hnb_effect_desc& desc) {
     bp.fast_math = (desc.flags & HNB_EFFECT_FAST_MATH) != 0;  // the flag is part of the source (hash)
     bp.tile_k = choose_tile_k(desc);
     bp.rows_per_lane = rows_per_lane();
-    bp.taper = tile_taper();  // same environment read as generate_effect_source above
     bp.update_smem = update_smem_bytes(desc);
     bp.flags = desc.flags;
     bp.particle_stride = desc.particle_stride;
@@ -1134,7 +1121,6 @@ static hnb_effect install_effect(hnb_ctx* c, const EffectBlueprint& bp, const st
     fx.km = get_module(c, bp.source, fx.name, fx.hash, bp.fast_math, precompiled_cubin);
     fx.tile_k = bp.tile_k;
     fx.rows_per_lane = bp.rows_per_lane;
-    fx.taper = bp.taper;
     fx.update_smem = bp.update_smem;
     {
         CUresult r = c->drv.FuncSetAttribute(fx.km->update, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)fx.update_smem);

@@ -214,21 +214,6 @@ uint32_t rows_per_lane() {
     return 16;
 }
 
-TileTaper tile_taper() {
-    // HNB_TILE_TAPER="<percent>[:<shift>]" (experimental, off by default): the last <percent> % of one wave of big tiles
-    // of every instance is cut into tiles 2^<shift> times smaller (default shift: down to one sub-tile). See
-    // hnb_tile_word in hnb_tables.cuh and DESIGN.md §10-3.
-    TileTaper t;
-    if (const char* e = getenv("HNB_TILE_TAPER")) {
-        const int pct = atoi(e);
-        if (pct > 0) {
-            t.percent = (uint32_t)std::min(pct, 10000);
-            if (const char* colon = strchr(e, ':')) t.shift = (uint32_t)std::max(0, std::min(atoi(colon + 1), 15));
-        }
-    }
-    return t;
-}
-
 uint32_t update_smem_bytes(const hnb_effect_desc& d) {
     // must mirror the carve-up at the top of hnb_update (hnb_particle_kernels.cuh)
     const uint32_t R = rows_per_lane(), warps = 8;
@@ -274,7 +259,6 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
             pos = end + 1;
         }
     }
-    if (tile_taper().percent) o << "#define HNB_TILE_TAPER 1\n";
     o << "#define HNB_NUM_PLANES " << planes.size() << "\n";
     o << "#define HNB_TILE_K " << choose_tile_k(d) << "\n";
     o << "#define HNB_ROWS_PER_LANE " << rows_per_lane() << "\n";

@@ -35,14 +35,6 @@ std::vector<Plane> physical_planes(uint32_t stride_bytes, bool sector_planes);
 // logical init threads (vfx_init.wgsl invocations) per CUDA thread of hnb_init == HNB_INIT_ITEMS of the generated kernels
 constexpr uint32_t kInitItems = 4;
 uint32_t rows_per_lane();  // == HNB_ROWS_PER_LANE of the generated kernels: tile_rows <= 32 * rows_per_lane()
-// Experimental tile taper (HNB_TILE_TAPER env, off by default): `percent` of one wave of big tiles at the tail of every
-// instance is processed in tiles `shift` halvings smaller (shift 15 = down to one sub-tile). When percent != 0 the
-// generated source carries `#define HNB_TILE_TAPER 1` (so it is part of the source hash) and the launch plan encodes
-// the taper into the tile size word.
-struct TileTaper {
-    uint32_t percent = 0, shift = 15;
-};
-TileTaper tile_taper();
 uint32_t choose_tile_k(const hnb_effect_desc& d);
 // Dynamic shared memory of hnb_update for this effect (tile-prefix table + per-warp double-buffered stash +
 // pending-tile records + Properties staging).

@@ -244,22 +244,17 @@ def build_emulated_effect(lowered, allow_events: bool = False) -> C.CDLL:
 
 def tile_count(rows, word: int):
     """hnb_tile_count (hnb_tables.cuh) restated: tiles of an instance with `rows` rows under a tile size word."""
-    S, f, w = word & 0xFFFF, (word >> 16) & 15, word >> 20
+    S = word & 0xFFFF
     rows = np.asarray(rows, dtype=np.int64)
-    if w == 0:
-        return (rows + S - 1) // S
-    n_big = (rows - np.minimum(rows, w * S)) // S
-    s = S >> f
-    return n_big + (rows - n_big * S + s - 1) // s
+    return (rows + S - 1) // S
 
 
 class EmuWorld:
     """One batch (all instances of `ref`) simulated by the emulated kernels, starting from `ref`'s current state."""
 
-    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None, static_lib=None, taper=None):
+    def __init__(self, ref, lowered, chunks: int = 1, update_ctas: int = 2, property_blobs=None, static_lib=None):
         """`static_lib` (tests/static_emu.build()): run the real bookkeeping and ribbon-sort kernels too instead of their
-        restatements. `taper` = (taper length in big tiles, shift): tile size word with a taper (needs a source generated
-        under HNB_TILE_TAPER, i.e. `#define HNB_TILE_TAPER 1`)."""
+        restatements."""
         self.ref, self.lib = ref, build_emulated_effect(lowered)
         self.static_lib = static_lib
         self.ribbons = bool(lowered.flags & (1 << 5))  # HNB_EFFECT_RIBBONS
@@ -271,10 +266,6 @@ class EmuWorld:
         assert chunks * k <= self.lib.emu_rows_per_lane()
         self.tile = 32 * k * chunks
         self.tile_word, small = self.tile, self.tile
-        if taper:
-            w, f = taper
-            assert chunks % (1 << f) == 0 and "#define HNB_TILE_TAPER 1" in lowered.generate_source()
-            self.tile_word, small = self.tile | (f << 16) | (w << 20), self.tile >> f
         self.update_ctas = update_ctas
         u32 = np.uint32
         self.planes = [np.zeros(rows * 8, dtype=u32) for _ in range(16)]          # room for 32-byte-wide (sector) columns

@@ -708,20 +708,3 @@ def test_value_splat():
         G.Value.splat(G.Vec2(1, 2), 2)
     with pytest.raises(ValueError):
         G.Value.splat(1.0, 5)
-
-
-def test_tile_taper_is_opt_in_and_part_of_the_source(monkeypatch):
-    """HNB_TILE_TAPER (experimental): without it the generated translation unit does not define HNB_TILE_TAPER (the taper code
-    of hnb_update is compiled out and the tile size word stays a plain row count); with it the define is part of the source,
-    hence of the source hash that keys the module cache, and the tapered kernel still compiles for sm_100a without spills."""
-    monkeypatch.delenv("HNB_TILE_TAPER", raising=False)
-    fx = _c5_asset().generate()
-    plain = fx.generate_source()
-    assert "#define HNB_TILE_TAPER 1" not in plain and "#define HNB_TILE_TAPER 0" in plain   # only the template's default
-    monkeypatch.setenv("HNB_TILE_TAPER", "0")
-    assert fx.generate_source() == plain
-    monkeypatch.setenv("HNB_TILE_TAPER", "100:1")
-    tapered = fx.generate_source()
-    assert "#define HNB_TILE_TAPER 1" in tapered and tapered != plain
-    size, log = R.nvrtc_check(tapered)
-    assert size > 0 and " 0 bytes spill stores" in log

@@ -647,63 +647,8 @@ def test_c3_force_field_at_its_baseline_size(orc):
     assert ref.metadata[0].alive_count == n - 4096 + 500
 
 
-# ---- tile taper (HNB_TILE_TAPER, experimental): the tail rows of every instance go through smaller tiles ------------
-@pytest.mark.timeout(600)
-@pytest.mark.parametrize("chunks,taper,ctas,static", [(4, (2, 2), 2, False), (4, (3, 1), 3, True), (2, (1, 1), 2, True), (4, (40, 2), 1, False)])
-def test_tile_taper_single_instance(orc, monkeypatch, chunks, taper, ctas, static):
-    """Big tiles then small tiles inside one look-back chain (the chain, the dead-stack ranks and the last-tile totals do not
-    care about tile sizes), with the restated and with the real bookkeeping kernel computing the tile prefix; a taper longer
-    than the instance means small tiles only. Same bit-exact bar as the untapered kernel."""
-    from tests import static_emu
-    monkeypatch.setenv("HNB_TILE_TAPER", "100")
-    rng = np.random.default_rng(chunks * 100 + ctas)
-    ref = _c5_world(rng, [Instance(0, 5000, alive=4700, seed=42)])
-    emu = EmuWorld(ref, recipes.c5_lowered(), chunks=chunks, update_ctas=ctas, taper=taper, static_lib=static_emu.build() if static else None)
-    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
-    for step in range(5):
-        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
-        emu.frame_step(orc, ref.sim, [0], [42])
-        _assert_same(ref, emu.pull(), f"taper {taper} step {step}")
-        # the launch really used both tile sizes (unless the taper swallows the instance)
-        S, (w, f) = emu.tile, taper
-        alive_in = int(ref.metadata[0].max_update)
-        assert int(emu.batch_tiles[0]) == int(tile_count(alive_in, emu.tile_word))
-        if w * S < alive_in:
-            assert (alive_in + S - 1) // S < int(emu.batch_tiles[0]) < (alive_in + (S >> f) - 1) // (S >> f) + 1
-    assert 0 < ref.metadata[0].alive_count < 4700
-
-
-@pytest.mark.timeout(600)
-def test_tile_taper_many_instances_with_spawns(orc, monkeypatch):
-    """Every instance of a batch gets its own taper: instances smaller than the taper, around tile multiples, empty ones;
-    spawns into recycled slots between the updates (init kernel + real bookkeeping + tapered update)."""
-    from tests import static_emu
-    monkeypatch.setenv("HNB_TILE_TAPER", "100:1")
-    rng = np.random.default_rng(77)
-    caps = [40, 512, 513, 1700, 1, 1024, 90, 3000, 256]
-    alive = [40, 512, 400, 1650, 0, 1024, 0, 2900, 255]
-    insts, off = [], 0
-    for c, a in zip(caps, alive):
-        insts.append(Instance(off, c, alive=a, seed=off + 5))
-        off += c
-    ref = _c5_world(rng, insts)
-    emu = EmuWorld(ref, recipes.c5_lowered(), chunks=4, update_ctas=3, taper=(2, 1), static_lib=static_emu.build())
-    k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
-    seeds = [i.seed for i in insts]
-    for step in range(5):
-        ref.oracle_frame(orc, orc.orc_body_update_c5(), k)
-        emu.frame_step(orc, ref.sim, [0] * len(insts), seeds)
-        _assert_same(ref, emu.pull(), f"step {step}")
-
-
 def test_tile_word_rule():
-    """hnb_tile_split as restated by tile_count: plain layout when the taper is off, exact row coverage with it."""
+    """hnb_tile_count as restated by tile_count: ceil(rows / S) tiles, whatever flags the word carries."""
     for rows in (0, 1, 127, 128, 129, 511, 512, 513, 4700, 65536, 1 << 20):
         assert int(tile_count(rows, 512)) == (rows + 511) // 512
-        for w, f in ((1, 1), (2, 2), (7, 2), (4095, 1)):
-            word = 512 | (f << 16) | (w << 20)
-            S, s = 512, 512 >> f
-            n = int(tile_count(rows, word))
-            n_big = (rows - min(rows, w * S)) // S
-            assert n_big * S <= rows and (n - n_big - 1) * s < rows - n_big * S <= (n - n_big) * s or rows == n_big * S == 0 and n == 0
-            assert n <= rows // s + 1
+        assert int(tile_count(rows, 512 | 0x80000000)) == (rows + 511) // 512

@@ -5,7 +5,6 @@ size through whole-state checksums (tests/test_gpu_fullsize.py); this is the exh
 
     python tools/emu_c5_fullsize.py [particles] [instances]     # instances > 1: BASELINE's C4 topology (equal slices of one
                                                                 # slab in ONE batch, each filled to a random level)
-    HNB_TILE_TAPER=100 python tools/emu_c5_fullsize.py 8388608   # the same through the tapered kernel: one B200 wave of big
                                                                 # tiles (3552) at the tail of every instance in 128-row tiles
 """
 import ctypes as C
@@ -34,8 +33,7 @@ for s in range(0,n,blk):   # rows beyond an instance's alive count are never rea
     m=min(blk,n-s)
     p[s:s+m,0:3]=rng.uniform(-1,1,(m,3)); p[s:s+m,4:7]=rng.uniform(-1,1,(m,3)); p[s:s+m,7]=rng.uniform(0.02,0.15,m); p[s:s+m,3]=0
 print("world built", f"{time.time()-t:.0f} s", flush=True)
-taper=(3552*int(os.environ["HNB_TILE_TAPER"].split(":")[0])//100, 2) if os.environ.get("HNB_TILE_TAPER") else None   # as plan_batch encodes it on a B200
-emu=EmuWorld(ref, recipes.c5_lowered(), chunks=4, update_ctas=3, taper=taper)
+emu=EmuWorld(ref, recipes.c5_lowered(), chunks=4, update_ctas=3)
 print("emu built", f"{time.time()-t:.0f} s", flush=True)
 k=(C.c_float*4)(0.0,-9.8,0.0,0.5)
 for step in range(2):

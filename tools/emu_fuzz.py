@@ -2,7 +2,6 @@
 grids for a time budget; stops at the first mismatch with the oracle and prints the seed.
 
     python tools/emu_fuzz.py [seconds] [first_seed] [sector]     # "sector": half of the worlds on HNB_SLAB_SECTOR_PLANES slabs
-    python tools/emu_fuzz.py [seconds] [first_seed] taper        # kernels generated under HNB_TILE_TAPER, random taper per world
 """
 import os
 import sys
@@ -24,7 +23,7 @@ from tests.test_gpu_scene import _drifting_sparks, _growing_dust  # noqa: E402
 from tests.test_kernel_emu_cpu import _assert_same  # noqa: E402
 
 
-def one(seed, orc, slib, sector_mix=False, taper_mix=False):
+def one(seed, orc, slib, sector_mix=False):
     rng = np.random.default_rng(seed)
     kind = int(rng.integers(0, 4))
     asset = [_drifting_sparks, _firework_trails, _growing_dust, _ribbon_asset][kind](1)
@@ -46,11 +45,7 @@ def one(seed, orc, slib, sector_mix=False, taper_mix=False):
     k = {32: 4, 48: 2}.get(size, 1)
     if chunks * k > 16:
         chunks = 1
-    taper = None
-    if taper_mix and chunks > 1:
-        h = int(pcg_hash(np.array([seed ^ 0x7A9E], dtype=np.uint32))[0])   # independent of `rng`: same worlds as without the option
-        taper = (1 + h % 5, 1 + (h >> 8) % (2 if chunks == 4 else 1))
-    emu = EmuWorld(ref, fx, chunks=chunks, update_ctas=ctas, static_lib=slib, taper=taper)
+    emu = EmuWorld(ref, fx, chunks=chunks, update_ctas=ctas, static_lib=slib)
     frames = int(rng.integers(3, 9))
     for f in range(frames):
         ref.sim.time = np.float32(f) * ref.sim.delta_time
@@ -60,7 +55,7 @@ def one(seed, orc, slib, sector_mix=False, taper_mix=False):
         ref.set_spawns(spawns, seeds)
         eo.frame(ref, orc)
         emu.frame_step(orc, ref.sim, spawns, seeds)
-        _assert_same(ref, emu.pull(), f"seed {seed} kind {kind} caps {caps} chunks {chunks} ctas {ctas} sector {sector} taper {taper} frame {f}")
+        _assert_same(ref, emu.pull(), f"seed {seed} kind {kind} caps {caps} chunks {chunks} ctas {ctas} sector {sector} frame {f}")
     return kind
 
 
@@ -68,19 +63,15 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     sector_mix = len(sys.argv) > 3 and sys.argv[3] == "sector"
-    taper_mix = len(sys.argv) > 3 and sys.argv[3] == "taper"
-    if taper_mix:
-        os.environ["HNB_TILE_TAPER"] = "100"   # generated sources carry #define HNB_TILE_TAPER 1
     orc, slib = c_oracle.load(), static_emu.build()
     t0, n, kinds = time.time(), 0, [0, 0, 0, 0]
     while time.time() - t0 < budget:
-        kinds[one(seed, orc, slib, sector_mix, taper_mix)] += 1
+        kinds[one(seed, orc, slib, sector_mix)] += 1
         seed += 1
         n += 1
         if n % 25 == 0:
             print(f"{n} worlds ok ({time.time() - t0:.0f} s), next seed {seed}, per effect {kinds}", flush=True)
-    print(f"done: {n} random worlds bit-exact against the oracle, seeds up to {seed - 1}, per effect {kinds}" + (", half of them on sector-plane slabs" if sector_mix else "")
-          + (", kernels generated under HNB_TILE_TAPER with a random taper wherever the tile has more than one sub-tile" if taper_mix else ""))
+    print(f"done: {n} random worlds bit-exact against the oracle, seeds up to {seed - 1}, per effect {kinds}" + (", half of them on sector-plane slabs" if sector_mix else ""))
 
 
 if __name__ == "__main__":

@@ -22,9 +22,7 @@ MAIN = r"""
 int main(int argc, char** argv) {
     const uint32_t rows = 6000, chunks = argc > 1 ? atoi(argv[1]) : 2, ctas = argc > 2 ? atoi(argv[2]) : 2, frames = 4;
     const uint32_t tile = 32u * HNB_TILE_K * chunks;
-    // argv[3], argv[4]: taper length (big tiles) and shift of the tile size word (kernel generated under HNB_TILE_TAPER)
-    const uint32_t taper_tiles = argc > 4 ? atoi(argv[3]) : 0, shift = argc > 4 ? atoi(argv[4]) : 0;
-    const uint32_t tile_word = hnb::hnb_tile_word(tile, shift, taper_tiles), small = tile >> shift;
+    const uint32_t tile_word = tile, small = tile;
     std::vector<float4> plane0(rows), plane1(rows);
     std::vector<uint32_t> ping(rows), pong(rows), dead(rows), tile_prefix(2), prefix_sum(1), spawn_prefix(1), batch_tiles(1), ticket(1), draw(5);
     std::vector<unsigned long long> states(rows / small + 4);
@@ -223,26 +221,6 @@ def main():
         p = subprocess.run([str(exe), str(chunks), str(ctas)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
         races = p.stderr.count("WARNING: ThreadSanitizer: data race")
         print(f"chunks={chunks} ctas={ctas}: exit {p.returncode}, {races} data-race reports")
-        print(p.stdout.strip())
-        if races:
-            print(p.stderr[:6000])
-        rc |= p.returncode or races
-    # the tapered kernel (HNB_TILE_TAPER, experimental): big tiles, then small ones, in one look-back chain
-    import os
-    os.environ["HNB_TILE_TAPER"] = "100"
-    src = recipes.c5_lowered().generate_source()
-    os.environ.pop("HNB_TILE_TAPER")
-    assert "#define HNB_TILE_TAPER 1" in src
-    for old, new in K.SUBSTITUTIONS:
-        assert src.count(old) == 1
-        src = src.replace(old, new)
-    cpp, exe = out / "tsan_c5_taper.cpp", out / "tsan_c5_taper"
-    cpp.write_text(K.PRELUDE + src + K.DRIVER + MAIN)
-    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-w", str(cpp), "-o", str(exe)], check=True)
-    for chunks, ctas, w, f in ((4, 2, 3, 2), (2, 2, 5, 1)):
-        p = subprocess.run([str(exe), str(chunks), str(ctas), str(w), str(f)], capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
-        races = p.stderr.count("WARNING: ThreadSanitizer: data race")
-        print(f"taper: chunks={chunks} ctas={ctas} taper_tiles={w} shift={f}: exit {p.returncode}, {races} data-race reports")
         print(p.stdout.strip())
         if races:
             print(p.stderr[:6000])

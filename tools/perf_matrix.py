@@ -269,31 +269,6 @@ def fresh_sector():
     _burst("C5 recipe on SECTOR planes, 32Mi burst", asset, 64 << 20, 32 << 20, sector_planes=True)
 
 
-def taper():
-    """HNB_TILE_TAPER (experimental): C5 update at the shard sizes of the strong-scaling runs (64 Mi / N) and smaller, with the
-    taper off and with several lengths / small-tile sizes. The variable is read when the effect source is generated and
-    when a launch is planned, so every setting gets its own context and effect."""
-    import os
-    for mi in (1, 2, 4, 8, 16, 32, 64):
-        P = mi << 20
-        for setting in (None, "100", "50", "200", "100:1", "25"):
-            if setting is None:
-                os.environ.pop("HNB_TILE_TAPER", None)
-            else:
-                os.environ["HNB_TILE_TAPER"] = setting
-            ctx = hb.Context(0, stream.cuda_stream)
-            slab = ctx.slab_create(P, 32)
-            ctx.slab_fill_c5(slab, 0, P, 42, 1e9, 1e9)
-            single_instance(ctx, P, 32, alive=P)
-            la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered()), slab, 0, 0)]
-            for _ in range(5):
-                ctx.simulate(la)
-            ms = timed_update(ctx, la, 50)
-            report(f"C5 {mi:2d}Mi update, HNB_TILE_TAPER={setting or 'off'}", ms, 72 * P)
-            ctx.close()
-    os.environ.pop("HNB_TILE_TAPER", None)
-
-
 def frame_chain():
     """Whole frames (bookkeeping + update, state resident, no table changes) back to back, with and without programmatic
     dependent launch: what one step costs beyond its update kernel, at the shard sizes of the strong-scaling runs."""
@@ -369,7 +344,7 @@ def interop():
         ctx.close()
 
 
-SCENARIOS = {"chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math, "taper": taper}
+SCENARIOS = {"chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
