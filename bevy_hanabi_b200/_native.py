@@ -132,6 +132,7 @@ EFFECT_RIBBONS = 1 << 5
 EFFECT_FAST_MATH = 1 << 6
 EFFECT_ORDERED_EVENTS = 1 << 7
 EFFECT_SECTOR_PLANES = 1 << 8
+EFFECT_SLOT_ORDER = 1 << 9
 SLAB_SECTOR_PLANES = 1 << 0
 
 
@@ -161,6 +162,7 @@ SIGNATURES = {
     "hnb_slab_create_ex": (i32, [vp, u32, u32, u32, P(u32)]),
     "hnb_slab_destroy": (i32, [vp, u32]),
     "hnb_slab_reset_rows": (i32, [vp, u32, u32, u32]),
+    "hnb_slab_rebuild_alive_bits": (i32, [vp, u32, u32, u32, u32, u32]),
     "hnb_slab_upload_aos": (i32, [vp, u32, u32, u32, vp]),
     "hnb_slab_download_aos": (i32, [vp, u32, u32, u32, vp]),
     "hnb_slab_upload_indirect": (i32, [vp, u32, u32, u32, vp]),

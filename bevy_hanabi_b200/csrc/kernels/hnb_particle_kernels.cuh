@@ -64,10 +64,29 @@ namespace hnb {
 #define HNB_LOOKBACK_SLEEP_NS 0  // back-off between polls of an unpublished predecessor (0 = spin)
 #endif
 
-// --- tile state word of the decoupled look-back: [63:34] epoch | [33:32] flag | [31:0] value ---
+#ifndef HNB_SLOT_ORDER
+#define HNB_SLOT_ORDER 0  // 1 (HNB_EFFECT_SLOT_ORDER): the update pass walks the instance's SLOTS in ascending order, guided by
+                          // the slab's alive bitmap, instead of walking the alive list. See "slot order" below.
+#endif
+
+// --- tile state word of the decoupled look-back ---
+//   default:    [63:34] epoch | [33:32] flag | [31:0] survivors
+//   slot order: [63:62] flag | [61:56] epoch & 63 | [55:28] survivors | [27:0] valid rows   (two running counts: the dead
+//               stack position of a dead row needs the number of ALIVE-BEFORE-THE-PASS rows in front of it, which in
+//               alive-list order is simply the row number; instances are limited to 2^28 slots)
 #define HNB_FLAG_AGGREGATE 1ull
 #define HNB_FLAG_PREFIX 2ull
+#if HNB_SLOT_ORDER
+HNB_DI u64 hnb_pack_state(u32 epoch, u64 flag, u32 survivors, u32 valid) {
+    return (flag << 62) | (u64(epoch & 63u) << 56) | (u64(survivors) << 28) | u64(valid);
+}
+HNB_DI u32 hnb_state_flag(u64 s, u32 epoch) { return ((u32(s >> 56) & 63u) == (epoch & 63u)) ? u32(s >> 62) : 0u; }
+HNB_DI u64 hnb_state_value(u64 s) { return s & 0x00ffffffffffffffull; }
+#else
 HNB_DI u64 hnb_pack_state(u32 epoch, u64 flag, u32 value) { return (u64(epoch) << 34) | (flag << 32) | u64(value); }
+HNB_DI u32 hnb_state_flag(u64 s, u32 epoch) { return (u32(s >> 34) == epoch) ? (u32(s >> 32) & 3u) : 0u; }
+HNB_DI u64 hnb_state_value(u64 s) { return s & 0xffffffffull; }
+#endif
 HNB_DI void hnb_st_state(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 HNB_DI u64 hnb_ld_state(const u64* p) {
     u64 v;
@@ -180,6 +199,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
 
         // Append to the alive list (:191-192) and write the particle back (:195)
         P.slab.particle_index[md->indirect_write_index][base_particle + it.alive_index] = particle_index;
+#if HNB_SLOT_ORDER
+        atomicOr(&P.slab.alive_bits[(base_particle + particle_index) >> 5u], 1u << ((base_particle + particle_index) & 31u));
+#endif
         RawParticle raw;
         hnb_raw_zero(raw);
         hnb_pack<true>(particle, raw);  // init also stores PREV/NEXT (vfx_init.wgsl:175-181)
@@ -196,11 +218,12 @@ struct PendingTile {
     u32 valid, tile, row0, tile_alive;
     u32 base_particle, max_update, write_index, render_index;
     u32 inst_first_tile, inst_end_tile, metadata_index, buffer;
-};
+    u32 tile_valid, _pad[3];  // slot order: rows of the tile that were alive before the pass
+};  // 64 bytes (mirrored by update_smem_bytes on the host)
 
 // Compaction of one tile: exclusive prefix of survivors over the previous tiles of the instance
 // (decoupled look-back), then survivors -> write list, dead -> dead stack (vfx_update.wgsl:148-166).
-HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const u32* survivors, const u32 (*pidx_stash)[32],
+HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const u32* survivors, const u32* valids, const u32 (*pidx_stash)[32],
                              u32 chunks, u32 epoch, u32 lane, long long& prof_polls) {
     u64* const states = P.tile_state;
     const u32 tile = pt.tile, row0 = pt.row0, tile_alive = pt.tile_alive, max_update = pt.max_update;
@@ -210,6 +233,12 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
     (void)prof_polls;
 
     u32 alive_before = 0u;
+#if HNB_SLOT_ORDER
+    u32 valid_before = 0u;
+    u64 sum_before = 0ull;  // both counts, packed like the state word's value
+#else
+    (void)valids;
+#endif
 #if HNB_RELAXED_ORDER
     // Reference-style order (vfx_update.wgsl:164) with one warp-aggregated atomic per tile.
     if (lane == 0) alive_before = atomicAdd(&P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * pt.render_index + 1u], tile_alive);
@@ -225,13 +254,17 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
 #pragma unroll
             for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
                 const u32 back = 32u * g + lane;
+#if HNB_SLOT_ORDER
+                s[g] = (pos >= inst_first_tile + back) ? hnb_ld_state(&states[pos - back]) : hnb_pack_state(epoch, HNB_FLAG_PREFIX, 0u, 0u);
+#else
                 s[g] = (pos >= inst_first_tile + back) ? hnb_ld_state(&states[pos - back]) : hnb_pack_state(epoch, HNB_FLAG_PREFIX, 0u);
+#endif
             }
             bool done = false, stalled = false;
 #pragma unroll
             for (int g = 0; g < HNB_LOOKBACK_GROUPS; ++g) {
                 if (!done && !stalled) {
-                    const u32 flag = (u32(s[g] >> 34) == epoch) ? (u32(s[g] >> 32) & 3u) : 0u;
+                    const u32 flag = hnb_state_flag(s[g], epoch);
                     const u32 ready_mask = __ballot_sync(0xffffffffu, flag != 0u);
                     const u32 prefix_mask = __ballot_sync(0xffffffffu, flag == u32(HNB_FLAG_PREFIX));
                     const u32 first_p = prefix_mask ? (u32)(__ffs(prefix_mask) - 1) : 32u;
@@ -239,10 +272,17 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
                     if ((ready_mask & need) != need) {
                         stalled = true;  // a needed predecessor has not published yet: poll again from here
                     } else {
+#if HNB_SLOT_ORDER
+                        u64 contrib = lane <= first_p ? hnb_state_value(s[g]) : 0ull;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                        sum_before += contrib;
+#else
                         u32 contrib = lane <= first_p ? u32(s[g]) : 0u;
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
                         alive_before += contrib;
+#endif
                         if (prefix_mask) done = true; else pos -= 32u;
                     }
                 }
@@ -257,12 +297,49 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
 #endif
             }
         }
+#if HNB_SLOT_ORDER
+        alive_before = u32(sum_before >> 28) & 0x0fffffffu;
+        valid_before = u32(sum_before) & 0x0fffffffu;
+        if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, alive_before + tile_alive, valid_before + pt.tile_valid));
+#else
         if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, HNB_FLAG_PREFIX, alive_before + tile_alive));
+#endif
     }
 #endif
 
     // survivors into the write list, the dead onto the dead stack, indices from the shared-memory stash
     u32 alive_rank_base = alive_before;
+#if HNB_SLOT_ORDER
+    // slot order: a row IS its slot; rows that were alive before the pass are the set bits of `valids`
+    (void)pidx_stash;
+    u32 valid_rank_base = valid_before;
+#pragma unroll 4
+    for (u32 jk = 0; jk < chunks * HNB_TILE_K; ++jk) {
+        const u32 row = row0 + jk * 32u + lane;
+        const u32 ballot = survivors[jk], vmask = valids[jk];
+        if ((vmask >> lane) & 1u) {
+            const u32 alive_rank = alive_rank_base + __popc(ballot & hnb_lanemask_lt());
+            if ((ballot >> lane) & 1u) {
+                write_col[alive_rank] = row;
+            } else {
+                // serial-order value of atomicSub(alive_count,1)-1 when the threads run in ascending slot order
+                const u32 dead_rank = valid_rank_base + __popc(vmask & hnb_lanemask_lt()) - alive_rank;
+                P.slab.dead_index[base_particle + (max_update - 1u - dead_rank)] = base_particle + row;
+            }
+        }
+        alive_rank_base += __popc(ballot);
+        valid_rank_base += __popc(vmask);
+    }
+    if (lane == 0 && tile + 1u == pt.inst_end_tile) {
+        const u32 alive_total = alive_before + tile_alive;
+        const u32 dead_total = max_update - alive_total;
+        P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * pt.render_index + 1u] = alive_total;
+        md->alive_count = md->alive_count - dead_total;
+        md->max_spawn = md->max_spawn + dead_total;
+        // the bitmap and the counters must describe the same population (debug word 15 counts instances where they do not)
+        if (valid_before + pt.tile_valid != max_update && P.debug) atomicAdd(&P.debug[15], 1ull);
+    }
+#else
 #pragma unroll 4
     for (u32 jk = 0; jk < chunks * HNB_TILE_K; ++jk) {
         const u32 row = row0 + jk * 32u + lane;
@@ -298,11 +375,12 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
         md->max_spawn = md->max_spawn + dead_total;
     }
 #endif
+#endif  // HNB_SLOT_ORDER
 }
 
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_update(const BatchParams P) {
     // Dynamic shared memory (size = hnb_update_smem_bytes, computed identically on the host):
-    //   tile-prefix table | per warp, double-buffered: alive-list entries [2][R][32] and survivor ballots [2][R] |
+    //   tile-prefix table | per warp, double-buffered: alive-list entries [2][R][32], survivor ballots [2][R], valid masks [2][R] |
     //   per warp: PendingTile | per warp: Properties staging slot
     extern __shared__ __align__(16) unsigned char hnb_smem[];
     u32* const sh_tile_prefix = (u32*)hnb_smem;
@@ -310,10 +388,11 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     typedef u32 SurvBuf[HNB_ROWS_PER_LANE];
     PidxBuf(*const sh_pidx)[2] = (PidxBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES);
     SurvBuf(*const sh_survivors)[2] = (SurvBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES + sizeof(PidxBuf) * 2 * HNB_WARPS);
-    PendingTile* const sh_pending = (PendingTile*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * 2 * HNB_WARPS);
+    SurvBuf(*const sh_valids)[2] = (SurvBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * 2 * HNB_WARPS);  // slot order
+    PendingTile* const sh_pending = (PendingTile*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + 2 * sizeof(SurvBuf)) * 2 * HNB_WARPS);
 #if HNB_HAS_PROPERTIES
     typedef unsigned char PropsBuf[(sizeof(Properties) + 15) / 16 * 16];
-    PropsBuf* const sh_props = (PropsBuf*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * 2 * HNB_WARPS + sizeof(PendingTile) * HNB_WARPS);
+    PropsBuf* const sh_props = (PropsBuf*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + 2 * sizeof(SurvBuf)) * 2 * HNB_WARPS + sizeof(PendingTile) * HNB_WARPS);
 #endif
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
@@ -371,6 +450,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     Spawner* spawner = nullptr;
     u32 metadata_index = 0u;
     u32 base_particle = 0u, spawner_seed = 0u, max_update = 0u, write_index = 0u, render_index = 0u;
+#if HNB_SLOT_ORDER
+    u32 inst_capacity = 0u;  // slots of the cached instance
+#endif
     const u32* __restrict__ read_col = nullptr;
 
     Ctx hnb_ctx;
@@ -423,6 +505,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             metadata_index = spawner->effect_metadata_index;
             const EffectMetadata* md = &P.metadata[metadata_index];
             max_update = md->max_update;  // :119
+#if HNB_SLOT_ORDER
+            inst_capacity = md->capacity;
+#endif
             write_index = md->indirect_write_index;
             render_index = md->indirect_render_index;
             read_col = P.slab.particle_index[1u - write_index] + base_particle;
@@ -450,18 +535,45 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         // ---- pass 1: stream the tile's rows in `chunks` sub-tiles of 32*K rows:
         //      alive-list entry -> particle record -> simulate -> write back; remember who survived.
         u32 tile_alive = 0u;
+#if HNB_SLOT_ORDER
+        // Slot order: row r of the tile IS slot row0 + r of the instance; the slab's alive bitmap says which slots hold a
+        // particle. Instances start on multiples of 32 slab rows (checked on the host), so word row0/32 + jk of the
+        // bitmap belongs to this warp alone: lane jk loads it now and stores the survivors' ballot back after the pass —
+        // 4 bytes per 32 slots instead of 4 bytes per particle of alive-list reads, and every record access of a warp
+        // falls into one contiguous span of each plane, however the population was recycled.
+        u32* const valids = sh_valids[warp][cur];
+        u32* const tile_bits = P.slab.alive_bits + ((base_particle + row0) >> 5u);
+        const bool owns_word = lane < chunks * HNB_TILE_K && row0 + lane * 32u < inst_capacity;
+        u32 my_bits = owns_word ? tile_bits[lane] : 0u;
+        if (owns_word && inst_capacity - (row0 + lane * 32u) < 32u) my_bits &= (1u << (inst_capacity - (row0 + lane * 32u))) - 1u;
+        u32 my_new_bits = 0u, tile_valid = 0u;
+        (void)read_col;
+#else
         u32 pidx_next[HNB_TILE_K];
 #pragma unroll
         for (int k = 0; k < HNB_TILE_K; ++k) {
             const u32 row = row0 + k * 32u + lane;
             pidx_next[k] = row < max_update ? read_col[row] : 0u;
         }
+#endif
 #pragma unroll 1
         for (u32 j = 0; j < chunks; ++j) {
             u32 pidx[HNB_TILE_K];
             bool valid[HNB_TILE_K];
             RawParticle raw[HNB_TILE_K];
             // gather the particle records (all loads in flight before any use)
+#if HNB_SLOT_ORDER
+#pragma unroll
+            for (int k = 0; k < HNB_TILE_K; ++k) {
+                const u32 vmask = __shfl_sync(0xffffffffu, my_bits, int(j * HNB_TILE_K + k));
+                pidx[k] = row0 + (j * HNB_TILE_K + k) * 32u + lane;
+                valid[k] = (vmask >> lane) & 1u;
+                if (lane == 0) valids[j * HNB_TILE_K + k] = vmask;
+                tile_valid += __popc(vmask);
+                if (valid[k]) hnb_load_raw(raw[k], P.slab, base_particle + pidx[k]);
+                else hnb_raw_zero(raw[k]);
+            }
+#else
 #pragma unroll
             for (int k = 0; k < HNB_TILE_K; ++k) {
                 const u32 row = row0 + (j * HNB_TILE_K + k) * 32u + lane;
@@ -479,6 +591,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                     pidx_next[k] = row < max_update ? read_col[row] : 0u;
                 }
             }
+#endif
             // simulate + write back (WRITEBACK_CODE: every attribute except PREV/NEXT, lib.rs:1270-1281)
 #pragma unroll
             for (int k = 0; k < HNB_TILE_K; ++k) {
@@ -508,6 +621,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                 const u32 ballot = __ballot_sync(0xffffffffu, alive);
                 if (lane == 0) survivors[j * HNB_TILE_K + k] = ballot;
                 tile_alive += __popc(ballot);
+#if HNB_SLOT_ORDER
+                if (lane == j * HNB_TILE_K + k) my_new_bits = ballot;
+#endif
             }
 #if HNB_PROFILE
             if (prof_first && j == 0u && lane == 0 && prof_ring) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&prof_ring[2], ~_g); }
@@ -516,7 +632,10 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         // Publish this tile's survivor count right away: the first tile of an instance knows its prefix (0),
         // the others publish an AGGREGATE that successors can sum over while this tile's own prefix is
         // still unknown.
-#if !HNB_RELAXED_ORDER
+#if HNB_SLOT_ORDER
+        if (owns_word) tile_bits[lane] = my_new_bits;  // the survivors are the next frame's population of these slots
+        if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, tile == inst_first_tile ? HNB_FLAG_PREFIX : HNB_FLAG_AGGREGATE, tile_alive, tile_valid));
+#elif !HNB_RELAXED_ORDER
         if (lane == 0) hnb_st_state(&states[tile], hnb_pack_state(epoch, tile == inst_first_tile ? HNB_FLAG_PREFIX : HNB_FLAG_AGGREGATE, tile_alive));
 #endif
         HNB_PROF_MARK(prof_pass1)
@@ -536,7 +655,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         __syncwarp();
         if (pending.valid) {
             const PendingTile pt = pending;
-            hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
+            hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_valids[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
         }
         __syncwarp();
         if (lane == 0) {
@@ -545,6 +664,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             pending.render_index = render_index; pending.inst_first_tile = inst_first_tile; pending.inst_end_tile = inst_end_tile;
             pending.metadata_index = metadata_index;
             pending.buffer = cur;
+#if HNB_SLOT_ORDER
+            pending.tile_valid = tile_valid;
+#endif
         }
         cur ^= 1u;
         __syncwarp();
@@ -556,7 +678,12 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             pt.max_update = max_update; pt.write_index = write_index; pt.render_index = render_index;
             pt.inst_first_tile = inst_first_tile; pt.inst_end_tile = inst_end_tile; pt.metadata_index = metadata_index;
             pt.buffer = cur;
-            hnb_compact_tile(P, pt, survivors, pidx_stash, chunks, epoch, lane, prof_polls);
+#if HNB_SLOT_ORDER
+            pt.tile_valid = tile_valid;
+            hnb_compact_tile(P, pt, survivors, valids, pidx_stash, chunks, epoch, lane, prof_polls);
+#else
+            hnb_compact_tile(P, pt, survivors, nullptr, pidx_stash, chunks, epoch, lane, prof_polls);
+#endif
             __syncwarp();
         }
 #endif
@@ -570,7 +697,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     __syncwarp();
     if (pending.valid) {
         const PendingTile pt = pending;
-        hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
+        hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_valids[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
     }
 #endif
 #if HNB_PROFILE

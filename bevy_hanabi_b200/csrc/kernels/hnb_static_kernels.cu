@@ -26,7 +26,7 @@ namespace hnb {
 // ---------------------------------------------------------------------------------------------
 // Per-instance step shared by k_indirect and k_bookkeeping.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 indirect_one_effect(const StaticTables& T, u32 global_effect_index) {
+__device__ __forceinline__ u32 indirect_one_effect(const StaticTables& T, u32 global_effect_index, u32* capacity_out = nullptr) {
     Spawner* spawner = &T.spawners[global_effect_index];
     const u32 effect_metadata_index = spawner->effect_metadata_index;
     EffectMetadata* md = &T.metadata[effect_metadata_index];
@@ -55,6 +55,7 @@ __device__ __forceinline__ u32 indirect_one_effect(const StaticTables& T, u32 gl
     const u32 dri_base = HNB_DRAW_INDEXED_INDIRECT_STRIDE * spawner->draw_indirect_index;
     T.draw_args[dri_base + 1u] = 0u;
     const u32 capacity = md->capacity;
+    if (capacity_out) *capacity_out = capacity;
     const u32 dead_count = capacity - alive_count;
     T.prefix_sum[global_effect_index] = alive_count;
     md->max_update = alive_count;
@@ -97,7 +98,9 @@ __global__ void k_prefix_sum(StaticTables T) {
         T.prefix_sum[i] = sum;
         T.tile_prefix[i] = tiles;
         sum += count;
-        tiles += hnb_tile_count(count, tile);
+        // slot order: the update pass walks the instance's slots, not its alive rows
+        const u32 rows = (tile & HNB_TILE_SLOT_ORDER) ? T.metadata[T.spawners[bi->spawner_base + (i - offset)].effect_metadata_index].capacity : count;
+        tiles += hnb_tile_count(rows, tile);
     }
     bi->total_update_count = sum;
     T.dispatch_args[batch_index * 3u + 0u] = (sum + 63u) >> 6u;
@@ -136,8 +139,9 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
         const u32 i = chunk + tid;
         u32 a = 0u, t = 0u;
         if (i < count) {
-            a = indirect_one_effect(T, offset + i);
-            t = hnb_tile_count(a, tile);
+            u32 capacity;
+            a = indirect_one_effect(T, offset + i, &capacity);
+            t = hnb_tile_count((tile & HNB_TILE_SLOT_ORDER) ? capacity : a, tile);
         }
         // block-wide exclusive scan of (a, t)
         u32 ia = a, it = t;
@@ -186,7 +190,8 @@ __global__ void __launch_bounds__(BK_THREADS) k_tile_prefix(StaticTables T, u32 
         u32 t = 0u;
         if (i < count) {
             const Spawner* sp = &T.spawners[bi->spawner_base + i];
-            t = hnb_tile_count(T.metadata[sp->effect_metadata_index].max_update, tile);
+            const EffectMetadata* md = &T.metadata[sp->effect_metadata_index];
+            t = hnb_tile_count((tile & HNB_TILE_SLOT_ORDER) ? md->capacity : md->max_update, tile);
         }
         u32 it = t;
 #pragma unroll
@@ -232,6 +237,29 @@ __global__ void k_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 cou
     ping[first + i] = 0u;
     pong[first + i] = 0u;
     dead[first + i] = first + i;  // effect_cache.rs:317-319
+}
+
+// Alive bitmap of a slab (one bit per row, HNB_EFFECT_SLOT_ORDER): set or clear the bits of rows [first, first+count).
+// One thread per 32-row word; words only partly inside the range are updated atomically.
+__global__ void k_bits_range(u32* bits, u32 first, u32 count, u32 set) {
+    const u32 w0 = first >> 5u;
+    const u32 w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 end = u64(first) + count;
+    if (u64(w) * 32u >= end) return;
+    const u64 lo = u64(w) * 32u > first ? u64(w) * 32u : u64(first);
+    const u64 hi = u64(w) * 32u + 32u < end ? u64(w) * 32u + 32u : end;
+    const u32 n = u32(hi - lo), sh = u32(lo - u64(w) * 32u);
+    const u32 mask = (n == 32u ? 0xffffffffu : ((1u << n) - 1u)) << sh;
+    if (mask == 0xffffffffu) bits[w] = set ? 0xffffffffu : 0u;
+    else if (set) atomicOr(&bits[w], mask);
+    else atomicAnd(&bits[w], ~mask);
+}
+// ... and the bits of the rows an alive list names: list[i] (instance-local) + base, i < alive_count
+__global__ void k_bits_from_list(u32* bits, const u32* list, u32 base, u32 alive_count) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= alive_count) return;
+    const u32 row = base + list[i];
+    atomicOr(&bits[row >> 5u], 1u << (row & 31u));
 }
 
 // Synthetic C5 state: counter-based so that the CPU oracle can regenerate any row.
@@ -425,6 +453,17 @@ cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, 
 cudaError_t launch_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
     k_slab_reset<<<blocks_for(count, 256), 256, 0, st>>>(ping, pong, dead, first, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_bits_range(u32* bits, u32 first, u32 count, bool set, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    const u32 words = u32(((u64(first) + count + 31u) >> 5u) - (first >> 5u));
+    k_bits_range<<<blocks_for(words, 256), 256, 0, st>>>(bits, first, count, set ? 1u : 0u);
+    return cudaGetLastError();
+}
+cudaError_t launch_bits_from_list(u32* bits, const u32* list, u32 base, u32 alive_count, cudaStream_t st) {
+    if (alive_count == 0) return cudaSuccess;
+    k_bits_from_list<<<blocks_for(alive_count, 256), 256, 0, st>>>(bits, list, base, alive_count);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_c5(void* pos_age, void* vel_life, u32* ping, u32* pong, u32 first, u32 count, u32 seed, f32 lo, f32 hi, u32 logical_first, cudaStream_t st) {

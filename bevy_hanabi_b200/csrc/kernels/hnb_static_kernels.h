@@ -79,6 +79,9 @@ cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_b
 cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
                                       u32 dst_stride, u32 count, cudaStream_t st);
 cudaError_t launch_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st);
+// alive bitmap of a slab (HNB_EFFECT_SLOT_ORDER): set / clear the bits of a row range; set the bits an alive list names
+cudaError_t launch_bits_range(u32* bits, u32 first, u32 count, bool set, cudaStream_t st);
+cudaError_t launch_bits_from_list(u32* bits, const u32* list, u32 base, u32 alive_count, cudaStream_t st);
 cudaError_t launch_aos_to_planes(const u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st);
 cudaError_t launch_planes_to_aos(u32* aos, const PlaneSet& planes, u32 first, u32 count, u32 stride_words, cudaStream_t st);
 cudaError_t launch_indirect_interleave(u32* rows3, const u32* ping, const u32* pong, const u32* dead, u32 first, u32 count, cudaStream_t st);

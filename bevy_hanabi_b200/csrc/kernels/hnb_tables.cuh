@@ -86,6 +86,7 @@ struct SlabView {
     void* planes[HNB_MAX_PLANES];
     u32* particle_index[2];  // ping / pong alive lists (instance-local particle indices)
     u32* dead_index;         // dead stack (slab-global rows)
+    u32* alive_bits;         // one bit per slab row: the row holds a particle (kept current by HNB_EFFECT_SLOT_ORDER effects)
     u32 capacity_rows;
     u32 _pad;
 };

@@ -86,6 +86,7 @@ struct Slab {
     std::vector<Plane> planes;   // physical columns
     void* d_planes[HNB_RT_MAX_PLANES] = {};
     uint32_t *ping = nullptr, *pong = nullptr, *dead = nullptr;
+    uint32_t* alive_bits = nullptr;  // one bit per row (HNB_EFFECT_SLOT_ORDER effects keep it current)
     // HNB_EFFECT_ORDERED_EVENTS scratch, allocated on first use: per channel the per-row event counts and their block sums
     uint32_t* event_counts[HNB_MAX_EVENT_BINDINGS] = {};
     uint32_t* event_block_sums[HNB_MAX_EVENT_BINDINGS] = {};
@@ -172,6 +173,8 @@ struct hnb_ctx {
     uint32_t *d_tile_prefix = nullptr, *d_dispatch_args = nullptr, *d_batch_tiles = nullptr, *d_tickets = nullptr;
     std::vector<unsigned long long*> d_tile_state;  // per batch
     std::vector<uint32_t> tile_state_cap;
+    std::vector<uint64_t> tile_state_sig;  // what the batch's states were last written for (see plan_batch, slot order)
+    uint64_t md_generation = 1;            // bumped by hnb_metadata_insert
 
     std::vector<Slab> slabs;
     std::vector<Effect> effects;
@@ -300,6 +303,7 @@ void ensure_scratch(hnb_ctx* c) {
         c->scratch_B = cap;
         c->d_tile_state.resize(cap, nullptr);
         c->tile_state_cap.resize(cap, 0);
+        c->tile_state_sig.resize(cap, 0);
     }
 }
 
@@ -388,6 +392,7 @@ hnb::SlabView slab_view(const Slab& s) {
     v.particle_index[0] = s.ping;
     v.particle_index[1] = s.pong;
     v.dead_index = s.dead;
+    v.alive_bits = s.alive_bits;
     v.capacity_rows = s.capacity;
     return v;
 }
@@ -441,6 +446,7 @@ void ensure_tile_state(hnb_ctx* c, uint32_t batch, uint32_t tiles) {
     CUDA_CHECK(cudaMalloc((void**)&c->d_tile_state[batch], size_t(cap) * 8));
     CUDA_CHECK(cudaMemsetAsync(c->d_tile_state[batch], 0, size_t(cap) * 8, c->stream));
     c->tile_state_cap[batch] = cap;
+    c->tile_state_sig[batch] = 0;
 }
 
 // Build the kernel parameters of one batch and write its per-instance init thread ranges and tile
@@ -473,7 +479,14 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     chunks = std::max(1u, std::min(chunks, lp.fx->rows_per_lane / lp.fx->tile_k));
     const uint32_t tile = sub_tile * chunks;
     // Tile size word shared with the bookkeeping kernels (hnb_tile_rows + flags)
-    const uint32_t tile_word = tile, small_tile = tile;
+    const bool slot_order = (lp.fx->flags & HNB_EFFECT_SLOT_ORDER) != 0;
+    const uint32_t tile_word = tile | (slot_order ? HNB_TILE_SLOT_ORDER : 0u), small_tile = tile;
+    if (slot_order) {
+        // bitmap words must belong to one instance (and one warp) each
+        const hnb_spawner* sp = c->h_at<hnb_spawner>(c->lay.off_spawners);
+        for (uint32_t i = 0; i < bi.prefix_sum_count; ++i)
+            if (sp[bi.spawner_base + i].slab_offset & 31u) fail(HNB_ERR_LAYOUT, "HNB_EFFECT_SLOT_ORDER needs every instance to start on a multiple of 32 slab rows");
+    }
     if (c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] != tile_word) {
         c->h_at<uint32_t>(c->lay.off_tile_size)[lp.batch] = tile_word;
         c->plan_dirty = true;
@@ -510,7 +523,22 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
             if (r) c->plan_dirty = true;
         }
     }
-    ensure_tile_state(c, lp.batch, lp.slab->capacity / small_tile + bi.prefix_sum_count + 1);  // n_big + n_small <= rows / s + 1 per instance
+    ensure_tile_state(c, lp.batch, lp.slab->capacity / small_tile + bi.prefix_sum_count + 1);  // ceil(rows_i / tile) summed over the instances
+    if (slot_order || c->tile_state_sig[lp.batch]) {
+        // Slot-order state words carry only 6 bits of epoch: enough while every tile of the batch is rewritten every
+        // frame (its tile count depends on capacities only), not across a change of what the batch slot is used for.
+        uint64_t sig = 0;
+        if (slot_order) {
+            sig = 0xcbf29ce484222325ull;
+            for (uint64_t v : {uint64_t(bl.effect), uint64_t(bl.slab), uint64_t(tile_word), uint64_t(bi.prefix_sum_count), uint64_t(bi.spawner_base), c->md_generation})
+                sig = (sig ^ v) * 0x100000001b3ull;
+            sig |= 1;
+        }
+        if (sig != c->tile_state_sig[lp.batch]) {
+            CUDA_CHECK(cudaMemsetAsync(c->d_tile_state[lp.batch], 0, size_t(c->tile_state_cap[lp.batch]) * 8, c->stream));
+            c->tile_state_sig[lp.batch] = sig;
+        }
+    }
 
     hnb::BatchParams& P = lp.params;
     P.frame = c->d_at<hnb::FrameHeader>(0);
@@ -761,7 +789,7 @@ void hnb_ctx_destroy(hnb_ctx* c) {
     for (auto& s : c->slabs) {
         if (!s.live) continue;
         for (auto p : s.d_planes) if (p) cudaFree(p);
-        cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead);
+        cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead); cudaFree(s.alive_bits);
         for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) { cudaFree(s.event_counts[i]); cudaFree(s.event_block_sums[i]); }
     }
     for (auto& e : c->effects) if (e.d_props) cudaFree(e.d_props);
@@ -819,6 +847,8 @@ int32_t hnb_slab_create_ex(hnb_ctx* c, uint32_t capacity_rows, uint32_t stride, 
         CUDA_CHECK(cudaMalloc((void**)&s.ping, size_t(capacity_rows) * 4));
         CUDA_CHECK(cudaMalloc((void**)&s.pong, size_t(capacity_rows) * 4));
         CUDA_CHECK(cudaMalloc((void**)&s.dead, size_t(capacity_rows) * 4));
+        CUDA_CHECK(cudaMalloc((void**)&s.alive_bits, (size_t(capacity_rows) / 32 + 2) * 4));
+        CUDA_CHECK(cudaMemsetAsync(s.alive_bits, 0, (size_t(capacity_rows) / 32 + 2) * 4, c->stream));
         CUDA_CHECK(hnb::launch_slab_reset(s.ping, s.pong, s.dead, 0, capacity_rows, c->stream));
         c->launches++;
         s.live = true;
@@ -832,7 +862,8 @@ int32_t hnb_slab_destroy(hnb_ctx* c, hnb_slab h) {
         Slab& s = get_slab(c, h);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         for (auto& p : s.d_planes) if (p) { cudaFree(p); p = nullptr; }
-        cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead);
+        cudaFree(s.ping); cudaFree(s.pong); cudaFree(s.dead); cudaFree(s.alive_bits);
+        s.alive_bits = nullptr;
         for (int i = 0; i < HNB_MAX_EVENT_BINDINGS; ++i) {
             cudaFree(s.event_counts[i]); cudaFree(s.event_block_sums[i]);
             s.event_counts[i] = s.event_block_sums[i] = nullptr;
@@ -846,7 +877,19 @@ int32_t hnb_slab_reset_rows(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t cou
         Slab& s = get_slab(c, h);
         check_rows(s, first, count);
         CUDA_CHECK(hnb::launch_slab_reset(s.ping, s.pong, s.dead, first, count, c->stream));
-        c->launches++;
+        CUDA_CHECK(hnb::launch_bits_range(s.alive_bits, first, count, false, c->stream));
+        c->launches += 2;
+    });
+}
+
+int32_t hnb_slab_rebuild_alive_bits(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t rows, uint32_t column, uint32_t alive_count) {
+    return guarded([&] {
+        Slab& s = get_slab(c, h);
+        check_rows(s, first, rows);
+        if (column > 1 || alive_count > rows) fail(HNB_ERR_INVALID_ARG, "bad alive-list column or count");
+        CUDA_CHECK(hnb::launch_bits_range(s.alive_bits, first, rows, false, c->stream));
+        CUDA_CHECK(hnb::launch_bits_from_list(s.alive_bits, (column ? s.pong : s.ping) + first, first, alive_count, c->stream));
+        c->launches += rows ? 1 + (alive_count ? 1 : 0) : 0;
     });
 }
 
@@ -1017,7 +1060,8 @@ int32_t hnb_slab_fill_c5_ex(hnb_ctx* c, hnb_slab h, uint32_t first, uint32_t cou
         if (s.stride != 32) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 needs the 32-byte {position,age,velocity,lifetime} layout");
         if (s.sector_planes) fail(HNB_ERR_LAYOUT, "hnb_slab_fill_c5 writes the default plane layout; spawn through the init pass or use hnb_slab_upload_aos");
         CUDA_CHECK(hnb::launch_fill_c5(s.d_planes[0], s.d_planes[1], s.ping, s.pong, first, count, seed, lo, hi, logical_first, c->stream));
-        c->launches++;
+        CUDA_CHECK(hnb::launch_bits_range(s.alive_bits, first, count, true, c->stream));
+        c->launches += 2;
     });
 }
 
@@ -1271,6 +1315,7 @@ int32_t hnb_upload_batches(hnb_ctx* c, const hnb_batch_info* rows, uint32_t nb, 
 int32_t hnb_metadata_insert(hnb_ctx* c, uint32_t row, const hnb_effect_metadata* md) {
     return guarded([&] {
         if (!md) fail(HNB_ERR_INVALID_ARG, "md is NULL");
+        c->md_generation++;
         grow_device(c->d_metadata, c->md_rows, row + 1, c->stream);
         CUDA_CHECK(cudaMemcpyAsync(c->d_metadata + row, md, sizeof(*md), cudaMemcpyHostToDevice, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -218,8 +218,8 @@ uint32_t update_smem_bytes(const hnb_effect_desc& d) {
     // must mirror the carve-up at the top of hnb_update (hnb_particle_kernels.cuh)
     const uint32_t R = rows_per_lane(), warps = 8;
     uint32_t bytes = (2047 + 1) * 4;
-    bytes += (R * 32 * 4 + R * 4) * 2 * warps;
-    bytes += 48 * warps;
+    bytes += (R * 32 * 4 + 2 * R * 4) * 2 * warps;  // alive-list entries, survivor ballots, valid masks
+    bytes += 64 * warps;                            // PendingTile
     if (d.properties_size) bytes += ((d.properties_size + 15) / 16 * 16) * warps;
     return bytes;
 }
@@ -240,6 +240,8 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
     const bool consume = (d.flags & HNB_EFFECT_CONSUME_GPU_SPAWN_EVENTS) != 0;
     const bool emit = (d.flags & HNB_EFFECT_EMIT_GPU_SPAWN_EVENTS) != 0;
     if (read_parent && (!d.parent_attrs || d.n_parent_attrs == 0)) throw std::invalid_argument("READ_PARENT_PARTICLE without parent layout");
+    if ((d.flags & HNB_EFFECT_SLOT_ORDER) && (d.flags & (HNB_EFFECT_RELAXED_ORDER | HNB_EFFECT_ORDERED_EVENTS | HNB_EFFECT_SECTOR_PLANES)))
+        throw std::invalid_argument("HNB_EFFECT_SLOT_ORDER cannot be combined with RELAXED_ORDER, ORDERED_EVENTS or SECTOR_PLANES");
 
     std::ostringstream o;
     o << "// ---- generated by hanabi_b200 for effect '" << nz(d.name) << "' ----\n";
@@ -268,6 +270,7 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
     o << "#define HNB_EMIT_EVENTS " << (emit ? 1 : 0) << "\n";
     o << "#define HNB_READ_PARENT " << (read_parent ? 1 : 0) << "\n";
     o << "#define HNB_RELAXED_ORDER " << ((d.flags & HNB_EFFECT_RELAXED_ORDER) ? 1 : 0) << "\n";
+    o << "#define HNB_SLOT_ORDER " << ((d.flags & HNB_EFFECT_SLOT_ORDER) ? 1 : 0) << "\n";
     o << "#define HNB_ORDERED_EVENTS " << ((emit && (d.flags & HNB_EFFECT_ORDERED_EVENTS)) ? 1 : 0) << "\n";
     o << "#define HNB_FAST_MATH " << ((d.flags & HNB_EFFECT_FAST_MATH) ? 1 : 0) << "\n";  // compiled with contraction + approximate div/sqrt
     o << "#ifndef HNB_LOAD_PLANE\n"

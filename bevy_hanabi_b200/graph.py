@@ -788,7 +788,7 @@ class EffectAsset:
         return blob.raw[:size.value]
 
     def generate(self, parent: Optional["EffectAsset"] = None, num_event_bindings: int = 0, relaxed_order: bool = False,
-                 fast_math: bool = False, ordered_events: bool = False, sector_planes: bool = False) -> LoweredEffect:
+                 fast_math: bool = False, ordered_events: bool = False, sector_planes: bool = False, slot_order: bool = False) -> LoweredEffect:
         """EffectShaderSources::generate: lower to the Level-1 effect description."""
         g = C.c_void_p()
         check(lib.hnb_asset_generate(self._native(), parent._native() if parent else None, num_event_bindings, C.byref(g)))
@@ -805,7 +805,8 @@ class EffectAsset:
                 age_code=s(d.age_code), reap_code=s(d.reap_code), update_code=s(d.update_code), update_extra=s(d.update_extra),
                 properties_struct=s(d.properties_struct), properties_size=d.properties_size,
                 flags=d.flags | (N.EFFECT_RELAXED_ORDER if relaxed_order else 0) | (N.EFFECT_FAST_MATH if fast_math else 0)
-                | (N.EFFECT_ORDERED_EVENTS if ordered_events else 0) | (N.EFFECT_SECTOR_PLANES if sector_planes else 0),
+                | (N.EFFECT_ORDERED_EVENTS if ordered_events else 0) | (N.EFFECT_SECTOR_PLANES if sector_planes else 0)
+                | (N.EFFECT_SLOT_ORDER if slot_order else 0),
                 parent_attrs=[AttrField(s(d.parent_attrs[i].name), d.parent_attrs[i].value_type, d.parent_attrs[i].offset) for i in range(d.n_parent_attrs)],
                 parent_particle_stride=d.parent_particle_stride, num_event_bindings=d.num_event_bindings)
         finally:

@@ -18,7 +18,7 @@ C5_ATTRS = [
 ]
 
 
-def c5_lowered(relaxed_order: bool = False) -> LoweredEffect:
+def c5_lowered(relaxed_order: bool = False, slot_order: bool = False) -> LoweredEffect:
     """Config C5: attrs {POSITION, VELOCITY, AGE, LIFETIME}; update [Accel((0,-9.8,0)), LinearDrag(0.5)];
     MotionIntegration::PostUpdate. Statement order as in SURVEY.md Appendix E."""
     return LoweredEffect(
@@ -39,7 +39,7 @@ def c5_lowered(relaxed_order: bool = False) -> LoweredEffect:
             "    particle.velocity += (vec3<f32>(0.f,-9.8f,0.f)) * sim_params.delta_time;"
             "particle.velocity *= max(0.f, (1.f) - ((0.5f) * (sim_params.delta_time)));\n"
             "particle.position += particle.velocity * sim_params.delta_time;\n"),
-        flags=N.EFFECT_RELAXED_ORDER if relaxed_order else 0,
+        flags=(N.EFFECT_RELAXED_ORDER if relaxed_order else 0) | (N.EFFECT_SLOT_ORDER if slot_order else 0),
     )
 
 

@@ -253,6 +253,9 @@ class Context:
     def slab_reset_rows(self, slab: int, first: int, count: int) -> None:
         check(lib.hnb_slab_reset_rows(self._h, slab, first, count))
 
+    def slab_rebuild_alive_bits(self, slab: int, first: int, rows: int, column: int, alive_count: int) -> None:
+        check(lib.hnb_slab_rebuild_alive_bits(self._h, slab, first, rows, column, alive_count))
+
     def slab_upload_aos(self, slab: int, first: int, particles: np.ndarray) -> None:
         a = np.ascontiguousarray(particles)
         count = a.shape[0]

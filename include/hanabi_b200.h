@@ -186,6 +186,11 @@ HNB_API int32_t hnb_slab_create_ex(hnb_ctx* ctx, uint32_t capacity_rows, uint32_
 HNB_API int32_t hnb_slab_destroy(hnb_ctx* ctx, hnb_slab slab);
 /** Re-initialise dead[i]=i, ping=pong=0 for rows [first,first+count). */
 HNB_API int32_t hnb_slab_reset_rows(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count);
+/** Rebuild the slab's alive bitmap (HNB_EFFECT_SLOT_ORDER) for the instance occupying rows [first,first+rows) from its
+ *  alive list: the first `alive_count` entries of indirection column `column` (0 = ping, 1 = pong). Needed only after state
+ *  was brought in from outside (hnb_slab_upload_* / import); the init and update passes keep the bitmap current. */
+HNB_API int32_t hnb_slab_rebuild_alive_bits(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t rows, uint32_t column,
+                                            uint32_t alive_count);
 /** Upload/download particles in the reference AoS layout (rows [first,first+count)). */
 HNB_API int32_t hnb_slab_upload_aos(hnb_ctx* ctx, hnb_slab slab, uint32_t first, uint32_t count,
                                     const void* particles_aos);
@@ -294,7 +299,16 @@ enum {
                                                   reference's order is scheduling-dependent, lib.rs:976-993). The batch must
                                                   hold one instance (parents of GPU-event children never merge). Costs
                                                   12 B of traffic per updated particle and channel. */
-    HNB_EFFECT_SECTOR_PLANES = 1u << 8         /* the effect addresses slabs created with HNB_SLAB_SECTOR_PLANES (must match) */
+    HNB_EFFECT_SECTOR_PLANES = 1u << 8,        /* the effect addresses slabs created with HNB_SLAB_SECTOR_PLANES (must match) */
+    HNB_EFFECT_SLOT_ORDER = 1u << 9            /* the update pass visits the instance's particles in ascending SLOT order (guided
+                                                  by an alive bitmap of the slab) instead of alive-list order: the result is what
+                                                  the reference computes when its alive list happens to be sorted by particle
+                                                  index — same sets, same counts, lists in ascending-slot serial order — and
+                                                  every warp touches one contiguous span of each column however long the effect
+                                                  has been recycling slots (an alive list that has become a permutation of the
+                                                  slab costs 4-8x in DRAM sectors otherwise, for the reference's AoS layout as
+                                                  well). Needs instances on 32-row boundaries and < 2^28 slots; not combinable
+                                                  with RELAXED_ORDER, ORDERED_EVENTS, SECTOR_PLANES. */
 };
 
 /**

@@ -669,6 +669,10 @@ class EffectOracle:
             W = md.indirect_write_index
             R = 1 - W
             pidx = world.indirect[base:base + n, R].copy()
+            if getattr(world, "slot_order", False):
+                # HNB_EFFECT_SLOT_ORDER: the threads visit the particles in ascending particle index — the reference's update
+                # (vfx_update.wgsl:106-167) when its alive list happens to be sorted; the list itself is left as it is
+                pidx = np.sort(pidx)
             rows = base + pidx.astype(np.int64)
             rec = world.particles[rows].copy()
             P = self.unpack(rec)

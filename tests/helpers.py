@@ -29,6 +29,9 @@ class RefWorld:
                  dt: float = 1.0 / 60.0):
         self.slab_rows = slab_rows
         self.stride_words = stride_words
+        # HNB_EFFECT_SLOT_ORDER: the update pass visits each instance's particles in ascending particle index — the reference's
+        # update when its alive list happens to be sorted. The oracle then reads the list through a sorted copy.
+        self.slot_order = False
         self.instances = list(instances)
         n = len(self.instances)
         self.particles = np.zeros((slab_rows, stride_words), dtype=np.uint32)
@@ -118,7 +121,31 @@ class RefWorld:
         orc.orc_prefix_sum(self.batch_infos, len(self.batches), self.prefix.ctypes.data_as(C.POINTER(C.c_uint32)),
                            self.dispatch.ctypes.data_as(C.POINTER(C.c_uint32)))
 
+    def sorted_read_lists(self, b: int = 0):
+        """Slot order: sort (in place) the alive list every instance of batch `b` is about to be updated through; returns what
+        is needed to put the unsorted entries back afterwards (the device never reorders the list it reads)."""
+        saved = []
+        for i in self.batches[b]:
+            md, sp = self.metadata[i], self.spawners[i]
+            col, base, n = 1 - md.indirect_write_index, sp.slab_offset, md.max_update
+            saved.append((col, base, n, self.indirect[base:base + n, col].copy()))
+            self.indirect[base:base + n, col] = np.sort(self.indirect[base:base + n, col])
+        return saved
+
+    def restore_read_lists(self, saved):
+        for col, base, n, rows in saved:
+            self.indirect[base:base + n, col] = rows
+
     def oracle_update(self, orc, body, user, b: int = 0):
+        if self.slot_order:
+            saved = self.sorted_read_lists(b)
+            try:
+                self.slot_order = False
+                self.oracle_update(orc, body, user, b)
+            finally:
+                self.slot_order = True
+                self.restore_read_lists(saved)
+            return
         threads = int(self.dispatch[3 * b]) * 64  # indirect dispatch: x workgroups of 64 threads
         orc.orc_update(C.byref(self.sim), self.draw.ctypes.data_as(C.POINTER(C.c_uint32)), O.ptr(self.particles),
                        self.stride_words, O.ptr(self.indirect), self.spawners,
@@ -190,6 +217,9 @@ class GpuWorld:
             ctx.upload_properties(self.effect, i, blob)
         ctx.slab_upload_aos(self.slab, 0, ref.particles)
         ctx.slab_upload_indirect(self.slab, 0, ref.indirect)
+        if getattr(lowered_effect, "flags", 0) & N.EFFECT_SLOT_ORDER:  # state came from outside: derive the alive bitmap from the lists
+            for i, inst in enumerate(ref.instances):
+                ctx.slab_rebuild_alive_bits(self.slab, inst.slab_offset, inst.capacity, ref.metadata[i].indirect_write_index, ref.metadata[i].alive_count)
         for i in range(len(ref.instances)):
             md = N.EffectMetadata.from_buffer_copy(bytes(ref.metadata[i]))
             ctx.metadata_insert(i, md)

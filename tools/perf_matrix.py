@@ -212,7 +212,7 @@ def many_batches():
         ctx.close()
 
 
-def churn(sector_planes: bool = False):
+def churn(sector_planes: bool = False, slot_order: bool = False):
     """Steady-state churn: constant spawn rate into recycled slots until the alive list is a random-looking permutation
     of the slab (survivors keep their relative order, new particles land in whatever slots died). The gathers then touch
     scattered 16-byte plane elements (half-used 32-byte sectors): the honest number for long-running effects, unlike the
@@ -221,7 +221,7 @@ def churn(sector_planes: bool = False):
     P = 16 << 20
     ctx = hb.Context(0, stream.cuda_stream)
     asset = _drifting_sparks(P)          # lifetimes U(0.2, 0.9) s
-    fx = asset.generate(sector_planes=sector_planes)
+    fx = asset.generate(sector_planes=sector_planes, slot_order=slot_order)
     stride = fx.particle_stride
     slab = ctx.slab_create(P, stride, sector_planes=sector_planes)
     effect = ctx.effect_compile(fx)
@@ -246,8 +246,47 @@ def churn(sector_planes: bool = False):
     ms, k = ctx.kernel_time_ms()
     ctx.enable_kernel_timing(False)
     alive2 = ctx.read_metadata(0).alive_count
-    report(f"churn steady state{' (sector planes)' if sector_planes else ''}: {alive2 >> 10} Ki of {P >> 10} Ki alive, stride {stride}", ms / k, (8 + 2 * stride) * alive2,
+    report(f"churn steady state{' (sector planes)' if sector_planes else ''}{' (SLOT ORDER)' if slot_order else ''}: {alive2 >> 10} Ki of {P >> 10} Ki alive, stride {stride}", ms / k, (8 + 2 * stride) * alive2,
            f"median |slot jump| between consecutive alive-list entries {np.median(jumps):.0f} (1 = identity order)")
+    ctx.close()
+
+
+def churn_slot():
+    """The same with HNB_EFFECT_SLOT_ORDER: the update walks the slots, not the (permuted) alive list."""
+    churn(slot_order=True)
+
+
+def c5_slot():
+    """C5 in slot order, nobody dies: the headline workload without the alive-list read (68 B instead of 72 B per particle;
+    reported against the same 72 B so that the rows compare)."""
+    for mi in (8, 64):
+        P = mi << 20
+        ctx = hb.Context(0, stream.cuda_stream)
+        slab = ctx.slab_create(P, 32)
+        ctx.slab_fill_c5(slab, 0, P, 42, 1e9, 1e9)
+        single_instance(ctx, P, 32, alive=P)
+        la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered(slot_order=True)), slab, 0, 0)]
+        for _ in range(10):
+            ctx.simulate(la)
+        fr = min(frame_ms(ctx, la, 100) for _ in range(3))
+        k = timed_update(ctx, la, 30)
+        assert ctx.read_metadata(0).alive_count == P
+        report(f"C5 {mi:2d}Mi SLOT ORDER frame chain", fr, 72 * P, f"isolated update kernel {k:.4f} ms = {68 * P / k / 1e6:.0f} GB/s of its own 68 B per particle")
+        ctx.close()
+    # dying: the population thins out but every access stays inside contiguous spans
+    P = 64 << 20
+    ctx = hb.Context(0, stream.cuda_stream)
+    slab = ctx.slab_create(P, 32)
+    ctx.slab_fill_c5(slab, 0, P, 42, 0.0, 0.5)
+    single_instance(ctx, P, 32, alive=P)
+    la = [N.BatchLaunch.make(ctx.effect_compile(recipes.c5_lowered(slot_order=True)), slab, 0, 0)]
+    alive = P
+    for step in range(12):
+        ms = timed_update(ctx, la, 1)
+        after = ctx.read_metadata(0).alive_count
+        if step in (0, 1, 5, 11):
+            report(f"C5 64Mi SLOT ORDER dying, step {step}: {alive >> 10} Ki -> {after >> 10} Ki", ms, 72 * alive, f"{100 * (alive - after) / max(alive, 1):.1f} % died")
+        alive = after
     ctx.close()
 
 
@@ -344,7 +383,7 @@ def interop():
         ctx.close()
 
 
-SCENARIOS = {"chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
+SCENARIOS = {"churn_slot": churn_slot, "c5_slot": c5_slot, "chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
