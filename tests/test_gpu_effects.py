@@ -121,8 +121,9 @@ def test_c2_relaxed_order_same_sets(ctx, orc):
     _run(ctx, orc, asset, ref, 24, lambda f: [700 if f % 12 == 0 else 0], relaxed=True, check_every=3)
 
 
-def _force_field(capacity):
-    """BASELINE config C3 (examples/force_field.rs:126-203 scaled): sphere spawn, two ConformToSphere, two kills."""
+def _force_field(capacity, aabb_half=(3., 2., 3.), kill_center=(-2., 1., 0.), kill_r2=0.36):
+    """BASELINE config C3 (examples/force_field.rs:126-203 scaled): sphere spawn, two ConformToSphere, two kills.
+    (The kill volumes are parameters so that a test can make them bite within a few frames.)"""
     w = G.ExprWriter()
     attractor = w.add_property("attraction_accel", 20.0)
     repulsor = w.add_property("repulsor_position", G.Vec3(0.2, 0.6, 0.))
@@ -133,8 +134,8 @@ def _force_field(capacity):
          .init(G.SetAttributeModifier(A.LIFETIME, w.lit(10.)))
          .update(G.ConformToSphereModifier(w.prop(repulsor), w.lit(0.2), w.lit(0.4), w.lit(-10.), w.lit(-2.), w.lit(0.1), w.lit(2.)))
          .update(G.ConformToSphereModifier(w.lit(G.Vec3(0.6, -0.2, 0.)), w.lit(0.3), w.lit(30.), w.prop(attractor), w.lit(5.)))
-         .update(G.KillAabbModifier(w.lit(G.Vec3(0, 0, 0)), w.lit(G.Vec3(3., 2., 3.))))
-         .update(G.KillSphereModifier(w.lit(G.Vec3(-2., 1., 0.)), w.lit(0.36), True)))
+         .update(G.KillAabbModifier(w.lit(G.Vec3(0, 0, 0)), w.lit(G.Vec3(*aabb_half))))
+         .update(G.KillSphereModifier(w.lit(G.Vec3(*kill_center)), w.lit(kill_r2), True)))
     return m
 
 

@@ -116,22 +116,23 @@ def test_spawning_into_recycled_slots(ctx, orc, caps):
     _no_bitmap_mismatch(ctx)
 
 
-def test_same_population_as_alive_list_order(ctx, orc):
+def test_same_population_as_alive_list_order(ctx, orc, native):
     """Slot order changes the ORDER of the lists, never who lives: for an effect whose per-particle results do not depend on
     the order (no per-thread counters), both modes hold the same particle records and the same alive SET after every frame
     once spawning stops (while spawning, the dead stack order decides which slot a new particle gets)."""
     rng = np.random.default_rng(11)
     worlds = []
-    for slot in (False, True):
+    ctx2 = native.Context(0)  # one context per world: both use metadata / draw / spawner row 0 of their context
+    for slot, c in ((False, ctx), (True, ctx2)):
         ref = RefWorld(6016, 8, [Instance(0, 6016, alive=6000, seed=5)])
         _fill(ref, np.random.default_rng(11), 0.02, 0.5)
-        worlds.append((ref, GpuWorld(ctx, ref, recipes.c5_lowered(slot_order=slot))))
+        worlds.append((ref, GpuWorld(c, ref, recipes.c5_lowered(slot_order=slot))))
     # scramble the alive list of both worlds identically (a permutation, as after long churn)
     perm = rng.permutation(6000).astype(np.uint32)
     for ref, gpu in worlds:
         ref.indirect[:6000, 0] = perm
         ref.indirect[:6000, 1] = perm
-        ctx.slab_upload_indirect(gpu.slab, 0, ref.indirect)
+        gpu.ctx.slab_upload_indirect(gpu.slab, 0, ref.indirect)
     for step in range(12):
         states = []
         for ref, gpu in worlds:
@@ -142,3 +143,4 @@ def test_same_population_as_alive_list_order(ctx, orc):
         np.testing.assert_array_equal(states[0][0], states[1][0])
         assert states[0][1] == states[1][1]
         np.testing.assert_array_equal(states[0][2], states[1][2])
+    ctx2.close()
