@@ -6,6 +6,7 @@
 // simulate() (src/render/mod.rs:6942-7613) — flattened into plain device arrays, one CUDA stream,
 // and one host->device copy per frame.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: a no-op unless a tool (nsys, ncu --nvtx) injects itself
 
 #include <algorithm>
 #include <atomic>
@@ -144,9 +145,15 @@ struct ArenaLayout {
 
 }  // namespace
 
+namespace {
+struct LaunchPlan;
+}
+
 struct hnb_ctx {
     int device = 0;
     int sm_count = 148;
+    std::vector<uint8_t> init_pending;   // per batch: a stand-alone hnb_pass_init whose accounting hnb_pass_indirect has not applied yet
+    std::vector<LaunchPlan> frame_plans;  // hnb_simulate's per-frame launch plans (kept to avoid a heap allocation per frame)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     DriverApi drv;
@@ -697,6 +704,15 @@ void launch_ribbon_sort(hnb_ctx* c, const LaunchPlan& lp) {
     CUDA_CHECK(hnb::launch_ribbon_sort(a, any_large, uint32_t(c->sm_count), c->stream, &launched));
     c->launches += launched;
 }
+
+// NVTX ranges named like the reference's compute passes (mod.rs:7029 "hanabi:init", :7186 "hanabi:indirect_dispatch",
+// :7283 "hanabi:update"), so that an nsys timeline of this backend lines up with a wgpu capture of the reference.
+struct PassRange {
+    explicit PassRange(const char* name) { nvtxRangePushA(name); }
+    ~PassRange() { nvtxRangePop(); }
+    PassRange(const PassRange&) = delete;
+    PassRange& operator=(const PassRange&) = delete;
+};
 
 void check_coverage(hnb_ctx* c, const std::vector<LaunchPlan>& plans) {
     // the fused bookkeeping kernel visits instances batch by batch: the launched batches must tile
@@ -1398,7 +1414,8 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         CUDA_CHECK(cudaSetDevice(c->device));
         if (c->header()->sim.num_effects > c->E) fail(HNB_ERR_NOT_READY, "sim_params.num_effects exceeds the uploaded spawner table");
         ensure_scratch(c);
-        std::vector<LaunchPlan> plans;
+        std::vector<LaunchPlan>& plans = c->frame_plans;  // reused from frame to frame: no allocation in steady state
+        plans.clear();
         plans.reserve(n);
         for (uint32_t i = 0; i < n; ++i) plans.push_back(plan_batch(c, batches[i], true));
         check_coverage(c, plans);  // nothing has been enqueued yet: a bad frame is skipped as a whole
@@ -1415,6 +1432,7 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         // cross-batch access is a child reading its parent's records, so frames with event-driven children keep
         // the reference's serial order.
         {
+            PassRange range("hanabi:init");
             uint32_t inits = 0;
             bool reads_parent = false;
             for (auto& lp : plans) {
@@ -1428,10 +1446,15 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             fork.join();
         }
         // passes "hanabi:indirect_dispatch" + "hanabi:update_prefix_sum" (mod.rs:7182-7275), fused
-        CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, copy_block ? nullptr : c->header(), c->pdl, c->stream));
-        c->launches += 1 + (c->child_rows ? 1 : 0);
+        {
+            PassRange range("hanabi:indirect_dispatch");  // + "hanabi:update_prefix_sum"
+            CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, copy_block ? nullptr : c->header(), c->pdl, c->stream));
+            c->launches += 1 + (c->child_rows ? 1 : 0);
+            std::fill(c->init_pending.begin(), c->init_pending.end(), 0);
+        }
         // pass "hanabi:update" (mod.rs:7280-7370): batches are independent (event appends are atomic)
         {
+            PassRange range("hanabi:update");
             Fork fork(c, uint32_t(plans.size()));
             uint32_t k = 0;
             for (auto& lp : plans) launch_update(c, lp, fork.lane(k++));
@@ -1466,6 +1489,7 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         bool needs_sort = false;
         for (auto& lp : plans) needs_sort |= (lp.fx->flags & HNB_EFFECT_RIBBONS) != 0;
         if (needs_sort) {
+            PassRange range("hanabi:sort");
             CUDA_CHECK(hnb::launch_prefix_sum(static_tables(c), c->B, c->stream));
             c->launches += c->B ? 1 : 0;
             for (auto& lp : plans)
@@ -1488,11 +1512,21 @@ int32_t hnb_pass_init(hnb_ctx* c, const hnb_batch_launch* b) {
     return guarded([&] {
         if (!b) fail(HNB_ERR_INVALID_ARG, "batch is NULL");
         ensure_scratch(c);
+        // The init kernel pops dead slots by rank from the counters as they stood at the START of the pass, and its
+        // alive_count / particle_counter increments are applied by the indirect pass that follows (spawn_range[]): a
+        // second stand-alone init of the same batch before that pass would pop the same slots and lose the first
+        // launch's increments (the reference's atomics accumulate, vfx_init.wgsl:141-151). Refuse it.
+        if (b->batch_info_index < c->init_pending.size() && c->init_pending[b->batch_info_index])
+            fail(HNB_ERR_INVALID_ARG, "hnb_pass_init: this batch already has an init pass pending; run hnb_pass_indirect first");
         LaunchPlan lp = plan_batch(c, *b, true);
         c->header()->num_batches = c->B;
         if (c->header()->epoch == 0) next_epoch(c);
         flush_arena(c, true);
-        if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params);
+        if (lp.init_blocks) {
+            launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params);
+            if (c->init_pending.size() <= b->batch_info_index) c->init_pending.resize(size_t(b->batch_info_index) + 1, 0);
+            c->init_pending[b->batch_info_index] = 1;
+        }
     });
 }
 
@@ -1505,6 +1539,7 @@ int32_t hnb_pass_indirect(hnb_ctx* c) {
         if (ne > c->E) fail(HNB_ERR_NOT_READY, "sim_params.num_effects exceeds the uploaded spawner table");
         CUDA_CHECK(hnb::launch_indirect(static_tables(c), ne, c->stream));
         c->launches += ne ? (1 + (c->child_rows ? 1 : 0)) : 0;
+        std::fill(c->init_pending.begin(), c->init_pending.end(), 0);  // the deferred init accounting has been applied
     });
 }
 

@@ -257,7 +257,18 @@ std::string generate_effect_source(const hnb_effect_desc& d) {
             if (end == std::string::npos) end = e.size();
             std::string item = e.substr(pos, end - pos);
             size_t eq = item.find('=');
-            if (!item.empty()) o << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
+            // The host sizes the dynamic shared memory and the grid from its own copy of these (update_smem_bytes,
+            // plan_batch): overriding them here would make the kernel's carve-up disagree with the launch. Ignored, loudly.
+            static const char* const kHostMirrored[] = {"HNB_SMEM_EFFECTS", "HNB_BLOCK", "HNB_WARPS", "HNB_ROWS_PER_LANE", "HNB_TILE_K",
+                                                        "HNB_NUM_PLANES", "HNB_INIT_ITEMS", "HNB_MAX_CHUNKS"};
+            const std::string name = item.substr(0, eq);
+            bool mirrored = false;
+            for (const char* m : kHostMirrored) mirrored |= name == m;
+            if (mirrored) {
+                fprintf(stderr, "hanabi_b200: HNB_DEFINES entry '%s' ignored (the host mirrors this constant)\n", name.c_str());
+            } else if (!item.empty()) {
+                o << "#define " << name << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
+            }
             pos = end + 1;
         }
     }

@@ -298,3 +298,25 @@ def test_random_expression_graphs_bit_exact(ctx, orc, data):
     np.testing.assert_array_equal(a, b, err_msg="generated update code:\n" + fx.update_code)
     np.testing.assert_array_equal(got["indirect"], ref.indirect)
     np.testing.assert_array_equal(got["metadata"], ref.metadata_rows())
+
+
+def test_second_standalone_init_before_indirect_is_refused(ctx):
+    """init accounting is deferred to the indirect pass; a second stand-alone init of the same batch before it
+    would pop the same dead slots. The library refuses it instead of corrupting the counters."""
+    from bevy_hanabi_b200 import _native as N, recipes, runtime as R
+    slab = ctx.slab_create(256, 32)
+    effect = ctx.effect_compile(recipes.c5_lowered())
+    ctx.metadata_insert(0, R.initial_metadata(256, 0, 8))
+    ctx.draw_args_insert(0)
+    ctx.upload_spawners([R.make_spawner(spawn=10, seed=1)])
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+    ctx.set_sim_params(1 / 60, 0.0, 1)
+    la = N.BatchLaunch.make(effect, slab, 0, 10)
+    ctx.pass_init(la)
+    with pytest.raises(Exception, match="init pass pending"):
+        ctx.pass_init(la)
+    ctx.pass_indirect()
+    assert ctx.read_metadata(0).alive_count == 10
+    ctx.pass_init(la)   # fine again once the accounting has been applied
+    ctx.pass_indirect()
+    assert ctx.read_metadata(0).alive_count == 20 and ctx.read_metadata(0).particle_counter == 20

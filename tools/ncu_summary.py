@@ -9,7 +9,11 @@ WANT = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
     "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-    "smsp__inst_executed.sum", "smsp__cycles_active.avg",
+    "smsp__inst_executed.sum", "smsp__cycles_active.avg", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "sm__maximum_warps_per_active_cycle_pct",
+    "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
 ]
@@ -30,6 +34,16 @@ def main():
                 out.append(f"  {w:70s} {r[i]:>16s} {units[i]}")
         stalls = [(float(r[i] or 0), h[len(STALL):].replace("_per_issue_active.ratio", "")) for i, h in enumerate(hdr)
                   if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and "not_issued" not in h]
+        # issue / pipe utilisation: which unit an ALU-bound kernel saturates
+        pipes = []
+        for i, h in enumerate(hdr):
+            if ("pipe" in h or "issue_active" in h or "inst_issued" in h) and "pct_of_peak_sustained_active" in h:
+                try:
+                    pipes.append((float(r[i]), h.replace(".pct_of_peak_sustained_active", "")))
+                except ValueError:
+                    pass
+        pipes.sort(reverse=True)
+        out.append("  busiest pipes / issue (% of peak, active cycles): " + ", ".join(f"{n}={v:.1f}" for v, n in pipes[:8]))
         stalls.sort(reverse=True)
         out.append("  warp stall reasons (avg warps stalled per issue-active cycle): " + ", ".join(f"{n}={v:.2f}" for v, n in stalls[:7]))
         try:
