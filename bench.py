@@ -520,8 +520,11 @@ def run_b200(args):
         if prof.exists():
             try:
                 rec = json.loads(prof.read_text())
-                # the ncu capture is of one launch over `particles_per_launch` particles: only quote it for that launch size
-                if int(rec.get("particles_per_launch", 0)) == per_rank:
+                # one ncu capture per launch size (64 Mi on one GPU, 32 / 16 / 8 Mi per GPU on 2 / 4 / 8): quote the one of THIS size
+                by_size = rec.get("by_particles_per_launch", {})
+                if str(per_rank) in by_size:
+                    line["roofline"]["traffic"] = int(by_size[str(per_rank)]["dram_bytes"])
+                elif int(rec.get("particles_per_launch", 0)) == per_rank:
                     line["roofline"]["traffic"] = rec.get("hnb_update_dram_bytes_per_launch")
             except Exception:
                 pass

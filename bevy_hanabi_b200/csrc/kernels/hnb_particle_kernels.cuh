@@ -120,10 +120,27 @@ template <typename Ptr> HNB_DI u32 hnb_find_effect(Ptr prefix, u32 lo, u32 hi, u
 #ifndef HNB_INIT_ITEMS
 #define HNB_INIT_ITEMS 4
 #endif
+// CPU prefix sums of a batch's spawn counts staged in shared memory (batches of up to this many instances; 4 KB of dynamic
+// shared memory, mirrored by hnb_rt::kInitSmemBytes on the host)
+#define HNB_INIT_SMEM_EFFECTS 1024
+// Dynamic shared memory of both kernels (hnb_init: the staged spawn prefix; hnb_update: see its carve-up)
+extern __shared__ __align__(16) unsigned char hnb_smem[];
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchParams P) {
     hnb_pdl_launch_dependents();
+    // Before the dependency wait: the words only the HOST writes — the batch info and the CPU prefix sums of the spawn counts
+    // (batch.rs:358-383), staged in shared memory so that the per-thread location search (vfx_init.wgsl:51-72; ten dependent
+    // steps for a batch of 1024 instances) runs on shared memory instead of on ten L2 round trips.
+    BatchInfo bi;
+    bi.spawner_base = P.batch_info->spawner_base;
+    bi.prefix_sum_offset = P.batch_info->prefix_sum_offset;
+    bi.prefix_sum_count = P.batch_info->prefix_sum_count;
+    u32* const sh_spawn_prefix = (u32*)hnb_smem;
+    const bool staged = bi.prefix_sum_count <= HNB_INIT_SMEM_EFFECTS;
+    if (staged) {
+        for (u32 i = threadIdx.x; i < bi.prefix_sum_count; i += HNB_BLOCK) sh_spawn_prefix[i] = P.spawn_prefix[bi.prefix_sum_offset + i];
+        __syncthreads();
+    }
     hnb_pdl_wait();  // the previous frame's update wrote the dead stack and the counters read below
-    const BatchInfo bi = *P.batch_info;
     struct Item {
         const Spawner* spawner;
         const EffectMetadata* md;
@@ -140,9 +157,15 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
         it.dead = 0u;
         if (!it.ok) continue;
         // Location in the packed init space of this batch (CPU prefix sums of spawn counts, batch.rs:358-383)
-        const u32 slot = hnb_find_effect(P.spawn_prefix, bi.prefix_sum_offset, bi.prefix_sum_offset + bi.prefix_sum_count, thread_index);
-        const u32 effect_index = slot - bi.prefix_sum_offset;
-        it.update_index = thread_index - P.spawn_prefix[slot];
+        u32 effect_index;
+        if (staged) {
+            effect_index = hnb_find_effect(sh_spawn_prefix, 0u, bi.prefix_sum_count, thread_index);
+            it.update_index = thread_index - sh_spawn_prefix[effect_index];
+        } else {
+            const u32 slot = hnb_find_effect(P.spawn_prefix, bi.prefix_sum_offset, bi.prefix_sum_offset + bi.prefix_sum_count, thread_index);
+            effect_index = slot - bi.prefix_sum_offset;
+            it.update_index = thread_index - P.spawn_prefix[slot];
+        }
         it.spawner = &P.spawners[bi.spawner_base + effect_index];
         it.md = &P.metadata[it.spawner->effect_metadata_index];
         // Cap to the number of dead particles (vfx_init.wgsl:115-119)
@@ -382,7 +405,6 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // Dynamic shared memory (size = hnb_update_smem_bytes, computed identically on the host):
     //   tile-prefix table | per warp, double-buffered: alive-list entries [2][R][32], survivor ballots [2][R], valid masks [2][R] |
     //   per warp: PendingTile | per warp: Properties staging slot
-    extern __shared__ __align__(16) unsigned char hnb_smem[];
     u32* const sh_tile_prefix = (u32*)hnb_smem;
     typedef u32 PidxBuf[HNB_ROWS_PER_LANE][32];
     typedef u32 SurvBuf[HNB_ROWS_PER_LANE];
@@ -402,6 +424,17 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // those kernels write has been read yet; from here on it is all visible. The next kernel in the stream (the next
     // frame's bookkeeping) may take SM slots as this grid's CTAs retire.
     hnb_pdl_launch_dependents();
+    // Before the dependency wait, the words only the HOST writes (batch info; the first instance's spawner row, whose
+    // `effect_metadata_index` gives the address of its metadata row): their DRAM / L2 round trips — batch info -> spawner row
+    // -> metadata row are DEPENDENT loads — overlap the predecessors' tails instead of heading this grid's critical path. The
+    // metadata row itself is device-written: it is only pulled towards L2 (the coherence point), and read after the wait.
+    const u32 bi_spawner_base = P.batch_info->spawner_base, bi_prefix_sum_offset = P.batch_info->prefix_sum_offset, n_effects = P.batch_info->prefix_sum_count;
+    {
+        const Spawner* first = &P.spawners[bi_spawner_base];
+        const u32 first_md = first->effect_metadata_index;
+        hnb_prefetch_l2(&P.metadata[first_md]);
+        hnb_prefetch_l2(first->transform);  // the row's 128 bytes
+    }
 #if HNB_PROFILE
     // per-frame timeline ring (diagnostics, tools/diag_frame_chain.py): 4 words per frame at debug[16 + 4 * (epoch & 63)]:
     // ~(earliest CTA residency), ~(earliest start after the dependency wait), ~(earliest end of a first sub-tile), latest warp end
@@ -419,9 +452,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     }
 #endif
 
-    const BatchInfo bi = *P.batch_info;
-    const u32 n_effects = bi.prefix_sum_count;
-    const u32* g_tile_prefix = P.tile_prefix + bi.prefix_sum_offset;
+    const u32* g_tile_prefix = P.tile_prefix + bi_prefix_sum_offset;
     const u32 total_tiles = *P.batch_tiles;
     const u32 epoch = P.frame->epoch;
     const bool staged = n_effects <= HNB_SMEM_EFFECTS;
@@ -499,7 +530,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                 inst_first_tile = g_tile_prefix[effect_index];
                 inst_end_tile = effect_index + 1u < n_effects ? g_tile_prefix[effect_index + 1u] : total_tiles;
             }
-            spawner = &P.spawners[bi.spawner_base + effect_index];
+            spawner = &P.spawners[bi_spawner_base + effect_index];
             base_particle = spawner->slab_offset;
             spawner_seed = spawner->seed;
             metadata_index = spawner->effect_metadata_index;

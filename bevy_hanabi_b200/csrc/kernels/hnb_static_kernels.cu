@@ -26,45 +26,78 @@ namespace hnb {
 // ---------------------------------------------------------------------------------------------
 // Per-instance step shared by k_indirect and k_bookkeeping.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 indirect_one_effect(const StaticTables& T, u32 global_effect_index, u32* capacity_out = nullptr) {
+// The words of a spawner row that only the HOST writes (GpuSpawnerParams is uploaded by the CPU every frame, mod.rs:4679-4705; the
+// device writes `render_indirect_read_index` only): they may be read before the programmatic-dependency wait.
+struct SpawnerHostWords {
+    u32 effect_metadata_index, draw_indirect_index;
+    i32 spawn;
+};
+__device__ __forceinline__ SpawnerHostWords load_spawner_host_words(const StaticTables& T, u32 global_effect_index) {
+    const Spawner* spawner = &T.spawners[global_effect_index];
+    SpawnerHostWords w;
+    w.effect_metadata_index = spawner->effect_metadata_index;
+    w.draw_indirect_index = spawner->draw_indirect_index;
+    w.spawn = spawner->spawn;
+    return w;
+}
+
+// Loads of one instance's step (phase 1), separated from its arithmetic and stores (phase 2) so that a thread handling
+// several instances has all their (dependent, latency-bound) loads in flight together.
+struct EffectLoads {
+    u32 range, alive_count, max_spawn, capacity, write_index, particle_counter, global_child_index;
+};
+__device__ __forceinline__ EffectLoads load_effect(const StaticTables& T, u32 global_effect_index, const SpawnerHostWords& hw) {
+    const EffectMetadata* md = &T.metadata[hw.effect_metadata_index];
+    EffectLoads L;
+    L.range = T.spawn_range[global_effect_index];
+    L.alive_count = md->alive_count;
+    L.max_spawn = md->max_spawn;
+    L.capacity = md->capacity;
+    L.write_index = md->indirect_write_index;
+    L.particle_counter = md->particle_counter;
+    L.global_child_index = md->global_child_index;
+    return L;
+}
+__device__ __forceinline__ u32 apply_effect(const StaticTables& T, u32 global_effect_index, const SpawnerHostWords& hw, const EffectLoads& L, u32* capacity_out = nullptr) {
     Spawner* spawner = &T.spawners[global_effect_index];
-    const u32 effect_metadata_index = spawner->effect_metadata_index;
-    EffectMetadata* md = &T.metadata[effect_metadata_index];
+    EffectMetadata* md = &T.metadata[hw.effect_metadata_index];
 
     // (a) deferred init accounting: number of init threads of this instance that passed the caps of
     // vfx_init.wgsl:115-137 in the init launch that preceded this pass (0 if there was none).
-    const u32 range = T.spawn_range[global_effect_index];
-    u32 alive_count = md->alive_count;
-    if (range != 0u) {
+    u32 alive_count = L.alive_count;
+    if (L.range != 0u) {
         u32 requested;
-        if (range & 0x80000000u) {
+        if (L.range & 0x80000000u) {
             // GPU-event driven instance: requested = event_count (vfx_init.wgsl:123-129)
-            requested = u32(T.child_infos[md->global_child_index].event_count);
+            requested = u32(T.child_infos[L.global_child_index].event_count);
         } else {
-            requested = u32(spawner->spawn);
+            requested = u32(hw.spawn);
         }
-        u32 n = min(range & 0x7fffffffu, requested);
-        n = min(n, md->max_spawn);
+        u32 n = min(L.range & 0x7fffffffu, requested);
+        n = min(n, L.max_spawn);
         alive_count += n;
         md->alive_count = alive_count;
-        md->particle_counter += n;
+        md->particle_counter = L.particle_counter + n;
         T.spawn_range[global_effect_index] = 0u;
     }
 
     // vfx_indirect.wgsl:52-89
-    const u32 dri_base = HNB_DRAW_INDEXED_INDIRECT_STRIDE * spawner->draw_indirect_index;
+    const u32 dri_base = HNB_DRAW_INDEXED_INDIRECT_STRIDE * hw.draw_indirect_index;
     T.draw_args[dri_base + 1u] = 0u;
-    const u32 capacity = md->capacity;
+    const u32 capacity = L.capacity;
     if (capacity_out) *capacity_out = capacity;
     const u32 dead_count = capacity - alive_count;
     T.prefix_sum[global_effect_index] = alive_count;
     md->max_update = alive_count;
     md->max_spawn = dead_count;
-    const u32 ping = md->indirect_write_index;
+    const u32 ping = L.write_index;
     const u32 pong = 1u - ping;
     md->indirect_write_index = pong;
     spawner->render_indirect_read_index = pong;
     return alive_count;
+}
+__device__ __forceinline__ u32 indirect_one_effect(const StaticTables& T, u32 global_effect_index, const SpawnerHostWords& hw, u32* capacity_out = nullptr) {
+    return apply_effect(T, global_effect_index, hw, load_effect(T, global_effect_index, hw), capacity_out);
 }
 
 __global__ void k_indirect(StaticTables T) {
@@ -75,7 +108,7 @@ __global__ void k_indirect(StaticTables T) {
     // NOTE: the deferred accounting above needs event_count, so it is read before being cleared
     // only when the clearing thread and the reading thread are the same; to stay race-free the clear
     // happens in a second kernel phase (see k_clear_events).
-    indirect_one_effect(T, global_effect_index);
+    indirect_one_effect(T, global_effect_index, load_spawner_host_words(T, global_effect_index));
 }
 
 __global__ void k_clear_events(StaticTables T) {
@@ -120,31 +153,92 @@ __global__ void k_prefix_sum(StaticTables T) {
 // (sim params, epoch, batch count) travels as a kernel parameter and CTA 0 stores it into the device frame block —
 // frames whose tables did not change need no host->device copy at all.
 #define BK_THREADS 256
+#define BK_ITEMS 4  // instances per thread and pass of the many-instance path
 struct FrameHeaderWords { u32 w[sizeof(FrameHeader) / 4]; };
 __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, const __grid_constant__ FrameHeaderWords header, u32 write_header) {
     __shared__ u32 s_warp_a[BK_THREADS / 32], s_warp_t[BK_THREADS / 32];
     __shared__ u32 s_carry_a, s_carry_t;
     hnb_pdl_launch_dependents();
-    hnb_pdl_wait();
-    if (write_header && blockIdx.x == 0 && threadIdx.x < sizeof(FrameHeader) / 4) ((u32*)T.frame)[threadIdx.x] = header.w[threadIdx.x];
+    // ---- Before the dependency wait: everything that only the HOST writes (batch infos, tile size word, the spawner rows'
+    // CPU words). These came with a stream-ordered copy that completed before this grid could start, and no kernel touches
+    // them, so the loads (and their DRAM / L2 round trips: batch info -> spawner row are DEPENDENT) overlap the tail of the
+    // previous frame's update kernel instead of sitting on the frame chain's critical path. Device-written state (metadata
+    // rows, spawn ranges, child infos, the frame header) is read after the wait only.
     const u32 batch_index = blockIdx.x;
     BatchInfo* bi = &T.batch_infos[batch_index];
     const u32 offset = bi->prefix_sum_offset;
     const u32 count = bi->prefix_sum_count;
     const u32 tile = T.batch_tile_size[batch_index];
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5u;
-    if (tid == 0) { s_carry_a = 0u; s_carry_t = 0u; }
-    __syncthreads();
-    for (u32 chunk = 0; chunk < count; chunk += BK_THREADS) {
-        const u32 i = chunk + tid;
+    // Batches of at most 32 instances (every single-effect batch) need one warp and no barrier.
+    const bool one_warp = count <= 32u;
+    if (one_warp && warp != 0u) return;
+    SpawnerHostWords first_hw[BK_ITEMS];
+#pragma unroll
+    for (int k = 0; k < BK_ITEMS; ++k) {
+        first_hw[k] = SpawnerHostWords();
+        const u32 i = one_warp ? (k == 0 ? tid : count) : tid * BK_ITEMS + k;
+        if (i < count) first_hw[k] = load_spawner_host_words(T, offset + i);
+    }
+    hnb_pdl_wait();
+    if (write_header && blockIdx.x == 0 && threadIdx.x < sizeof(FrameHeader) / 4) ((u32*)T.frame)[threadIdx.x] = header.w[threadIdx.x];
+    if (one_warp) {
         u32 a = 0u, t = 0u;
-        if (i < count) {
+        if (lane < count) {
             u32 capacity;
-            a = indirect_one_effect(T, offset + i, &capacity);
+            a = indirect_one_effect(T, offset + lane, first_hw[0], &capacity);
             t = hnb_tile_count((tile & HNB_TILE_SLOT_ORDER) ? capacity : a, tile);
         }
-        // block-wide exclusive scan of (a, t)
         u32 ia = a, it = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 ua = __shfl_up_sync(0xffffffffu, ia, d), ut = __shfl_up_sync(0xffffffffu, it, d);
+            if (lane >= d) { ia += ua; it += ut; }
+        }
+        if (lane < count) {
+            T.prefix_sum[offset + lane] = ia - a;
+            T.tile_prefix[offset + lane] = it - t;
+        }
+        const u32 sum = __shfl_sync(0xffffffffu, ia, 31), tiles = __shfl_sync(0xffffffffu, it, 31);
+        if (lane == 0) {
+            bi->total_update_count = sum;
+            T.dispatch_args[batch_index * 3u + 0u] = (sum + 63u) >> 6u;
+            T.dispatch_args[batch_index * 3u + 1u] = 1u;
+            T.dispatch_args[batch_index * 3u + 2u] = 1u;
+            T.batch_tiles[batch_index] = tiles;
+            T.tickets[batch_index] = 0u;
+        }
+        return;
+    }
+    if (tid == 0) { s_carry_a = 0u; s_carry_t = 0u; }
+    __syncthreads();
+    // Each thread owns BK_ITEMS CONSECUTIVE instances per pass (1024 instances = one pass): phase 1 issues the loads of all of
+    // them, phase 2 does their arithmetic and stores, then one block-wide scan over the per-thread sums.
+    for (u32 chunk = 0; chunk < count; chunk += BK_THREADS * BK_ITEMS) {
+        const u32 i0 = chunk + tid * BK_ITEMS;
+        SpawnerHostWords hw[BK_ITEMS];
+        EffectLoads L[BK_ITEMS];
+#pragma unroll
+        for (int k = 0; k < BK_ITEMS; ++k) {
+            hw[k] = first_hw[k];
+            if (chunk != 0u && i0 + k < count) hw[k] = load_spawner_host_words(T, offset + i0 + k);
+        }
+#pragma unroll
+        for (int k = 0; k < BK_ITEMS; ++k)
+            if (i0 + k < count) L[k] = load_effect(T, offset + i0 + k, hw[k]);
+        u32 a[BK_ITEMS], t[BK_ITEMS], sa = 0u, st = 0u;
+#pragma unroll
+        for (int k = 0; k < BK_ITEMS; ++k) {
+            a[k] = 0u; t[k] = 0u;
+            if (i0 + k < count) {
+                u32 capacity;
+                a[k] = apply_effect(T, offset + i0 + k, hw[k], L[k], &capacity);
+                t[k] = hnb_tile_count((tile & HNB_TILE_SLOT_ORDER) ? capacity : a[k], tile);
+            }
+            sa += a[k]; st += t[k];
+        }
+        // block-wide exclusive scan of the per-thread sums (sa, st)
+        u32 ia = sa, it = st;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const u32 ua = __shfl_up_sync(0xffffffffu, ia, d), ut = __shfl_up_sync(0xffffffffu, it, d);
@@ -155,9 +249,14 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
         u32 wa = 0u, wt = 0u;
         for (u32 w = 0; w < warp; ++w) { wa += s_warp_a[w]; wt += s_warp_t[w]; }
         const u32 carry_a = s_carry_a, carry_t = s_carry_t;
-        if (i < count) {
-            T.prefix_sum[offset + i] = carry_a + wa + ia - a;
-            T.tile_prefix[offset + i] = carry_t + wt + it - t;
+        u32 base_a = carry_a + wa + ia - sa, base_t = carry_t + wt + it - st;
+#pragma unroll
+        for (int k = 0; k < BK_ITEMS; ++k) {
+            if (i0 + k < count) {
+                T.prefix_sum[offset + i0 + k] = base_a;
+                T.tile_prefix[offset + i0 + k] = base_t;
+            }
+            base_a += a[k]; base_t += t[k];
         }
         __syncthreads();
         if (tid == BK_THREADS - 1) { s_carry_a = carry_a + wa + ia; s_carry_t = carry_t + wt + it; }

@@ -1442,7 +1442,7 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             Fork fork(c, reads_parent ? 1 : inits);
             uint32_t k = 0;
             for (auto& lp : plans)
-                if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params, 0, fork.lane(k++));
+                if (lp.init_blocks) launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params, hnb_rt::kInitSmemBytes, fork.lane(k++));
             fork.join();
         }
         // passes "hanabi:indirect_dispatch" + "hanabi:update_prefix_sum" (mod.rs:7182-7275), fused
@@ -1523,7 +1523,7 @@ int32_t hnb_pass_init(hnb_ctx* c, const hnb_batch_launch* b) {
         if (c->header()->epoch == 0) next_epoch(c);
         flush_arena(c, true);
         if (lp.init_blocks) {
-            launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params);
+            launch_kernel(c, lp.fx->km->init, lp.init_blocks, lp.params, hnb_rt::kInitSmemBytes);
             if (c->init_pending.size() <= b->batch_info_index) c->init_pending.resize(size_t(b->batch_info_index) + 1, 0);
             c->init_pending[b->batch_info_index] = 1;
         }

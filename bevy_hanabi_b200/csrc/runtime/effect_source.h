@@ -34,6 +34,7 @@ std::vector<Plane> physical_planes(uint32_t stride_bytes, bool sector_planes);
 // chosen from the record size (register footprint) at compile time, the chunk count per launch.
 // logical init threads (vfx_init.wgsl invocations) per CUDA thread of hnb_init == HNB_INIT_ITEMS of the generated kernels
 constexpr uint32_t kInitItems = 4;
+constexpr uint32_t kInitSmemBytes = 1024 * 4;  // HNB_INIT_SMEM_EFFECTS spawn-prefix entries staged by hnb_init
 uint32_t rows_per_lane();  // == HNB_ROWS_PER_LANE of the generated kernels: tile_rows <= 32 * rows_per_lane()
 uint32_t choose_tile_k(const hnb_effect_desc& d);
 // Dynamic shared memory of hnb_update for this effect (tile-prefix table + per-warp double-buffered stash +

@@ -106,7 +106,7 @@ SUBSTITUTIONS = [
     ('    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");',
      '    v = __atomic_load_n(p, __ATOMIC_RELAXED); sched_yield();  /* a poll: let the OS run somebody else */'),
     ('    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));', '    m = (1u << emu::tls.lane) - 1u;'),
-    ('    extern __shared__ __align__(16) unsigned char hnb_smem[];', '    unsigned char* const hnb_smem = emu::dyn_smem();'),
+    ('extern __shared__ __align__(16) unsigned char hnb_smem[];', '#define hnb_smem (emu::dyn_smem())'),
     ('    __shared__ u32 sh_first_ticket;', '    u32& sh_first_ticket = *emu::static_u32(0);'),
 ]
 
@@ -180,7 +180,7 @@ template <typename K> static void emu_launch(K kernel, const hnb::BatchParams& P
         }
     }
 }
-extern "C" void emu_init(const EmuBatch* b, uint32_t blocks) { emu_launch(hnb::hnb_init, make_params(b), blocks, 0, 8); }
+extern "C" void emu_init(const EmuBatch* b, uint32_t blocks) { emu_launch(hnb::hnb_init, make_params(b), blocks, HNB_INIT_SMEM_EFFECTS * 4, 8); }
 extern "C" void emu_update(const EmuBatch* b, uint32_t blocks, uint32_t smem) { emu_launch(hnb::hnb_update, make_params(b), blocks, smem); }
 extern "C" void emu_aos_to_planes(const EmuBatch* b, const uint8_t* aos, uint32_t first, uint32_t count, uint32_t stride) {
     hnb::BatchParams P = make_params(b);

@@ -165,7 +165,7 @@ def interop():
     ctx.close()
 
 
-SCENARIOS = {"c5_64m": lambda: c5(64), "c5_8m": lambda: c5(8), "c5_1m": lambda: c5(1), "c5_64m_slot": lambda: c5(64, True), "c5_init": c5_init, "c3_16m": lambda: c3(16),
+SCENARIOS = {"c5_64m": lambda: c5(64), "c5_32m": lambda: c5(32), "c5_16m": lambda: c5(16), "c5_8m": lambda: c5(8), "c5_1m": lambda: c5(1), "c5_64m_slot": lambda: c5(64, True), "c5_init": c5_init, "c3_16m": lambda: c3(16),
              "c3_1m": lambda: c3(1), "c2": c2, "c4": c4, "churn": churn, "churn_slot": lambda: churn(True), "interop": interop}
 if __name__ == "__main__":
     SCENARIOS[sys.argv[1]]()

@@ -383,7 +383,109 @@ def interop():
         ctx.close()
 
 
-SCENARIOS = {"churn_slot": churn_slot, "c5_slot": c5_slot, "chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
+def c2_small():
+    """BASELINE configs[1] at ITS size: firework trails, 32768 slots (48-byte records). The whole population is 1.5 MB: a
+    frame is pure fixed cost (launch chain + dependent-load latency), reported in microseconds per frame."""
+    from tests.test_gpu_effects import _firework_trails
+    P = 32768
+    ctx = hb.Context(0, stream.cuda_stream)
+    fx = _firework_trails(P).generate()
+    slab = ctx.slab_create(P, fx.particle_stride)
+    effect = ctx.effect_compile(fx)
+    ctx.metadata_insert(0, R.initial_metadata(P, 0, fx.particle_stride // 4))
+    ctx.draw_args_insert(0)
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+    ctx.set_sim_params(1 / 600, 0.0, 1)     # short steps: nobody expires during the measurement
+    ctx.upload_spawners([R.make_spawner(spawn=30000, seed=7)])
+    t_burst = frame_ms(ctx, [N.BatchLaunch.make(effect, slab, 0, 30000)])
+    ctx.upload_spawners([R.make_spawner(spawn=0, seed=8)])
+    la = [N.BatchLaunch.make(effect, slab, 0, 0)]
+    for _ in range(10):
+        ctx.simulate(la)
+    fr = min(frame_ms(ctx, la, 200) for _ in range(3))
+    k = timed_update(ctx, la, 50)
+    alive = ctx.read_metadata(0).alive_count
+    report(f"C2 firework @ 32768 slots: steady frame, {alive} alive", fr, (8 + 2 * 48) * alive, f"{fr * 1e3:.1f} us per frame (update kernel alone {k * 1e3:.1f} us); first burst frame of 30000 spawns (cold) {t_burst * 1e3:.1f} us")
+    # a frame that also spawns: 100 particles per frame into free slots
+    ctx.upload_spawners([R.make_spawner(spawn=8, seed=9)])
+    la8 = [N.BatchLaunch.make(effect, slab, 0, 8)]
+    for _ in range(5):
+        ctx.simulate(la8)
+    fr8 = min(frame_ms(ctx, la8, 100) for _ in range(3))
+    report("C2 firework @ 32768 slots: frame with 8 spawns (init + bookkeeping + update)", fr8, (8 + 2 * 48) * alive, f"{fr8 * 1e3:.1f} us per frame")
+    ctx.close()
+
+
+def c4_recipe():
+    """BASELINE configs[3] as stated: instancing.rs recipe, 1024 instances x 65536 slots in ONE batch, filled
+    through the real init kernel; update-only frames, then frames that spawn one particle per instance (init with a
+    depth-10 prefix search over 1024 instances + bookkeeping of 1024 instances + update)."""
+    from tests.test_gpu_config_sizes import _instancing
+    n_inst, cap = 1024, 65536
+    ctx = hb.Context(0, stream.cuda_stream)
+    fx = _instancing(cap).generate()
+    stride = fx.particle_stride
+    slab = ctx.slab_create(n_inst * cap, stride)
+    effect = ctx.effect_compile(fx)
+    for i in range(n_inst):
+        ctx.metadata_insert(i, R.initial_metadata(cap, i, stride // 4))
+        ctx.draw_args_insert(i)
+    fill = cap - 1024
+    mk = lambda spawn: [R.make_spawner(spawn=spawn, seed=1000 + i, effect_metadata_index=i, draw_indirect_index=i, slab_offset=i * cap) for i in range(n_inst)]
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, n_inst)], [i * fill for i in range(n_inst)])
+    ctx.set_sim_params(1 / 60, 0.0, n_inst)
+    ctx.upload_spawners(mk(fill))
+    t_fill = frame_ms(ctx, [N.BatchLaunch.make(effect, slab, 0, n_inst * fill)])
+    alive = n_inst * fill
+    report(f"C4 recipe: fill frame (init {alive >> 10} Ki over 1024 instances + update)", t_fill, (stride + 8) * alive + (8 + 2 * stride) * alive)
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, n_inst)], [0] * n_inst)
+    ctx.upload_spawners(mk(0))
+    la = [N.BatchLaunch.make(effect, slab, 0, 0)]
+    for _ in range(5):
+        ctx.simulate(la)
+    fr = min(frame_ms(ctx, la, 30) for _ in range(2))
+    k = timed_update(ctx, la, 20)
+    report(f"C4 recipe: update-only frame, {alive >> 10} Ki alive in 1024 instances", fr, (8 + 2 * stride) * alive, f"update kernel alone {k:.4f} ms")
+    ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, n_inst)], list(range(n_inst)))
+    ctx.upload_spawners(mk(1))
+    la1 = [N.BatchLaunch.make(effect, slab, 0, n_inst)]
+    for _ in range(5):
+        ctx.simulate(la1)
+    fr1 = min(frame_ms(ctx, la1, 30) for _ in range(2))
+    alive1 = sum(ctx.read_metadata(i).alive_count for i in (0, 511, 1023)) // 3 * n_inst
+    report(f"C4 recipe: spawn 1 / instance / step frame (init 1024 + update {alive1 >> 10} Ki)", fr1, (8 + 2 * stride) * alive1, f"+{(fr1 - fr) * 1e3:.1f} us over the update-only frame")
+    ctx.close()
+
+
+def c3_chain():
+    """C3 at its BASELINE size (1 Mi) as a frame chain (what a running effect costs per frame), strict and fast-math."""
+    from tests.test_gpu_effects import _force_field
+    P = 1 << 20
+    for fast in (False, True):
+        asset = _force_field(P)
+        ctx = hb.Context(0, stream.cuda_stream)
+        fx = asset.generate(fast_math=fast)
+        slab = ctx.slab_create(P, fx.particle_stride)
+        effect = ctx.effect_compile(fx)
+        ctx.upload_properties(effect, 0, asset.serialize_properties())
+        ctx.metadata_insert(0, R.initial_metadata(P, 0, fx.particle_stride // 4, properties_array_index=0))
+        ctx.draw_args_insert(0)
+        ctx.upload_batches([N.BatchInfo(0, 0, 0, 0, 0, 1)], [0])
+        ctx.set_sim_params(1 / 6000, 0.0, 1)
+        ctx.upload_spawners([R.make_spawner(spawn=P, seed=7)])
+        ctx.simulate([N.BatchLaunch.make(effect, slab, 0, P)])
+        ctx.upload_spawners([R.make_spawner(spawn=0, seed=8)])
+        la = [N.BatchLaunch.make(effect, slab, 0, 0)]
+        for _ in range(10):
+            ctx.simulate(la)
+        fr = min(frame_ms(ctx, la, 200) for _ in range(3))
+        k = timed_update(ctx, la, 50)
+        alive = ctx.read_metadata(0).alive_count
+        report(f"C3 force field 1Mi frame chain{' FAST_MATH' if fast else ''}, {alive >> 10} Ki alive", fr, (8 + 2 * fx.particle_stride) * alive, f"isolated update kernel {k:.4f} ms")
+        ctx.close()
+
+
+SCENARIOS = {"c2_small": c2_small, "c4_recipe": c4_recipe, "c3_chain": c3_chain, "churn_slot": churn_slot, "c5_slot": c5_slot, "chunks": chunks_sweep, "interop": interop, "frame_chain": frame_chain, "churn": churn, "churn_sector": churn_sector, "fresh_sector": fresh_sector, "many": many_batches, "c5": c5_update, "c5_dying": c5_dying, "c4": c4_topology, "c5_init": c5_init_burst, "c2": c2_trails, "c3": c3_force_field, "c3_fast": c3_fast_math}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
         try:
