@@ -473,17 +473,34 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
         fail(HNB_ERR_OUT_OF_RANGE, "batch references instances outside the uploaded spawner table");
     // Rows per warp tile: 32 lanes x K rows per lane x chunks. Larger tiles shorten the look-back chain and
     // amortise the per-tile work (ticket, state word, instance lookup); smaller tiles spread a small slab over more
-    // warps. Thresholds in units of W = one sub-tile per resident warp, from tools/sweep_small.py on C5
-    // (W = 444 Ki rows): 4 chunks win from 2 Mi rows up, 2 chunks from 256 Ki up, below that the launch is
-    // latency-bound and the tile size does not matter.
+    // warps. With W = one sub-tile per resident warp (C5 on a B200: 3552 warps x 128 rows = 444 Ki rows):
+    //  * from 8 W up the launch streams at the HBM rate and the largest tile wins at every size (tools/sweep_small.py,
+    //    profiles/r2_quantization_sweep.txt: no quantisation at whole numbers of tiles per warp);
+    //  * below, the launch is latency-bound and runs in ROUNDS: every resident warp takes one tile per round, and a tile
+    //    costs a fixed part (ticket, first alive-list entries, look-back, compaction: ~5.5 us) plus ~1.5 us per sub-tile
+    //    (fit of the 1-4 chunk timings at 2 Mi rows, profiles/r2_chunks_sweep.txt): pick the chunk count that minimises
+    //    rounds x (3.6 + chunks), preferring larger tiles on a tie. 1 Mi rows -> 3 chunks (every warp takes exactly one
+    //    tile), 2 Mi -> 3, 512 Ki -> 2, 256 Ki -> 1.
     const uint32_t sub_tile = 32u * lp.fx->tile_k;
     const uint32_t total_warps = uint32_t(lp.fx->update_blocks_per_sm) * uint32_t(c->sm_count) * 8u;
+    const uint32_t max_chunks = std::max(1u, lp.fx->rows_per_lane / lp.fx->tile_k);
     uint32_t chunks = c->tile_chunks_override;
     if (chunks == 0) {
         const uint64_t wave = uint64_t(total_warps) * sub_tile;
-        chunks = uint64_t(lp.slab->capacity) >= 4 * wave ? 4u : (uint64_t(lp.slab->capacity) * 4 >= wave ? 2u : 1u);
+        const uint64_t rows = lp.slab->capacity;
+        if (rows >= 8 * wave) {
+            chunks = max_chunks;
+        } else {
+            double best = 0.0;
+            for (uint32_t ch = 1; ch <= max_chunks; ++ch) {
+                const uint64_t tiles = (rows + uint64_t(sub_tile) * ch - 1) / (uint64_t(sub_tile) * ch) + bi.prefix_sum_count - 1;
+                const uint64_t rounds = std::max<uint64_t>(1, (tiles + total_warps - 1) / total_warps);
+                const double cost = double(rounds) * (3.6 + double(ch));
+                if (chunks == 0 || cost <= best) { best = cost; chunks = ch; }
+            }
+        }
     }
-    chunks = std::max(1u, std::min(chunks, lp.fx->rows_per_lane / lp.fx->tile_k));
+    chunks = std::max(1u, std::min(chunks, max_chunks));
     const uint32_t tile = sub_tile * chunks;
     // Tile size word shared with the bookkeeping kernels (hnb_tile_rows + flags)
     const bool slot_order = (lp.fx->flags & HNB_EFFECT_SLOT_ORDER) != 0;

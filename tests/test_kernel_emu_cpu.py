@@ -37,7 +37,7 @@ def _c5_world(rng, insts):
     return ref
 
 
-@pytest.mark.parametrize("chunks,ctas", [(1, 1), (1, 3), (2, 2), (4, 2)])
+@pytest.mark.parametrize("chunks,ctas", [(1, 1), (1, 3), (2, 2), (3, 2), (4, 2)])
 def test_update_kernel_c5_single_instance(orc, chunks, ctas):
     """Tile tickets, look-back across 10-40 tiles, deferred compaction, dead-stack pushes, last-tile totals."""
     rng = np.random.default_rng(chunks * 10 + ctas)
@@ -231,7 +231,7 @@ def test_random_worlds_through_every_kernel(orc, seed):
     dt = float(rng.choice([1 / 10, 1 / 20, 1 / 4]))
     ref = RefWorld(off, size // 4, insts, dt=dt)
     eo = EffectOracle(asset)
-    chunks, ctas = int(rng.choice([1, 2, 4])), int(rng.integers(1, 4))
+    chunks, ctas = int(rng.choice([1, 2, 3, 4])), int(rng.integers(1, 4))
     emu = EmuWorld(ref, asset.generate(), chunks=chunks, update_ctas=ctas, static_lib=static_emu.build())
     for f in range(5):
         ref.sim.time = np.float32(f) * ref.sim.delta_time
