@@ -148,38 +148,70 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
         bool ok;
     } items[HNB_INIT_ITEMS];
 
-    // ---- locate, apply the caps, pop the dead slot (all loads of all items in flight together)
+    // ---- locate, apply the caps, pop the dead slot. The chain location -> spawner row -> metadata row -> dead slot is four
+    // DEPENDENT round trips; it is walked phase by phase over ALL items, so that the items' loads of a phase are in flight
+    // together whatever instances they belong to (a batch of 1024 instances spawning one particle each gives every item of a
+    // thread a different instance: item after item would be sixteen round trips, phase after phase is four).
+    u32 md_index[HNB_INIT_ITEMS], max_spawn[HNB_INIT_ITEMS], alive_count[HNB_INIT_ITEMS], requested[HNB_INIT_ITEMS], slab_offset[HNB_INIT_ITEMS];
+    // phase A: location in the packed init space of this batch (CPU prefix sums of spawn counts, batch.rs:358-383); the
+    // spawner row's CPU words
 #pragma unroll
     for (int k = 0; k < HNB_INIT_ITEMS; ++k) {
         Item& it = items[k];
         const u32 thread_index = (blockIdx.x * HNB_INIT_ITEMS + k) * HNB_BLOCK + threadIdx.x;  // global_invocation_id.x
         it.ok = thread_index < P.init_thread_count;
-        it.dead = 0u;
-        if (!it.ok) continue;
-        // Location in the packed init space of this batch (CPU prefix sums of spawn counts, batch.rs:358-383)
-        u32 effect_index;
-        if (staged) {
-            effect_index = hnb_find_effect(sh_spawn_prefix, 0u, bi.prefix_sum_count, thread_index);
-            it.update_index = thread_index - sh_spawn_prefix[effect_index];
-        } else {
-            const u32 slot = hnb_find_effect(P.spawn_prefix, bi.prefix_sum_offset, bi.prefix_sum_offset + bi.prefix_sum_count, thread_index);
-            effect_index = slot - bi.prefix_sum_offset;
-            it.update_index = thread_index - P.spawn_prefix[slot];
-        }
-        it.spawner = &P.spawners[bi.spawner_base + effect_index];
-        it.md = &P.metadata[it.spawner->effect_metadata_index];
-        // Cap to the number of dead particles (vfx_init.wgsl:115-119)
-        it.ok = it.update_index < it.md->max_spawn;
-#if HNB_CONSUME_EVENTS
-        it.ok = it.ok && it.update_index < u32(P.child_infos[it.md->global_child_index].event_count);  // event_index = update_index
-#else
-        it.ok = it.ok && it.update_index < u32(it.spawner->spawn);
+        it.dead = 0u; it.update_index = 0u; it.alive_index = 0u;
+        it.spawner = P.spawners; it.md = P.metadata;
+        md_index[k] = 0u; requested[k] = 0u; slab_offset[k] = 0u;
+        if (it.ok) {
+            u32 effect_index;
+            if (staged) {
+                effect_index = hnb_find_effect(sh_spawn_prefix, 0u, bi.prefix_sum_count, thread_index);
+                it.update_index = thread_index - sh_spawn_prefix[effect_index];
+            } else {
+                const u32 slot = hnb_find_effect(P.spawn_prefix, bi.prefix_sum_offset, bi.prefix_sum_offset + bi.prefix_sum_count, thread_index);
+                effect_index = slot - bi.prefix_sum_offset;
+                it.update_index = thread_index - P.spawn_prefix[slot];
+            }
+            it.spawner = &P.spawners[bi.spawner_base + effect_index];
+            md_index[k] = it.spawner->effect_metadata_index;
+            slab_offset[k] = it.spawner->slab_offset;
+#if !HNB_CONSUME_EVENTS
+            requested[k] = u32(it.spawner->spawn);
 #endif
-        if (!it.ok) continue;
-        // Recycle a dead slot. Serial-order equivalent of `atomicAdd(alive_count, 1)` (:141): every thread
-        // with a smaller update_index also passed the caps above, so this thread's rank IS update_index.
-        it.alive_index = it.md->alive_count + it.update_index;
-        it.dead = P.slab.dead_index[it.spawner->slab_offset + it.alive_index];
+        }
+    }
+    // phase B: the metadata row
+#pragma unroll
+    for (int k = 0; k < HNB_INIT_ITEMS; ++k) {
+        Item& it = items[k];
+        max_spawn[k] = 0u; alive_count[k] = 0u;
+        if (it.ok) {
+            it.md = &P.metadata[md_index[k]];
+            max_spawn[k] = it.md->max_spawn;
+            alive_count[k] = it.md->alive_count;
+#if HNB_CONSUME_EVENTS
+            requested[k] = it.md->global_child_index;  // (index of the child info; its event count is loaded in phase B2)
+#endif
+        }
+    }
+#if HNB_CONSUME_EVENTS
+    // phase B2: GPU-event driven instance: requested = event_count (vfx_init.wgsl:123-129), event_index = update_index
+#pragma unroll
+    for (int k = 0; k < HNB_INIT_ITEMS; ++k)
+        if (items[k].ok) requested[k] = u32(P.child_infos[requested[k]].event_count);
+#endif
+    // phase C: cap to the number of dead particles and to the request (vfx_init.wgsl:115-137), recycle a dead slot.
+    // Serial-order equivalent of `atomicAdd(alive_count, 1)` (:141): every thread with a smaller update_index also passed
+    // the caps, so this thread's rank IS update_index.
+#pragma unroll
+    for (int k = 0; k < HNB_INIT_ITEMS; ++k) {
+        Item& it = items[k];
+        it.ok = it.ok && it.update_index < max_spawn[k] && it.update_index < requested[k];
+        if (it.ok) {
+            it.alive_index = alive_count[k] + it.update_index;
+            it.dead = P.slab.dead_index[slab_offset[k] + it.alive_index];
+        }
     }
 
     // ---- initialise and store
