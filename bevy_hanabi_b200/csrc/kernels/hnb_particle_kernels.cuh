@@ -456,17 +456,6 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // those kernels write has been read yet; from here on it is all visible. The next kernel in the stream (the next
     // frame's bookkeeping) may take SM slots as this grid's CTAs retire.
     hnb_pdl_launch_dependents();
-    // Before the dependency wait, the words only the HOST writes (batch info; the first instance's spawner row, whose
-    // `effect_metadata_index` gives the address of its metadata row): their DRAM / L2 round trips — batch info -> spawner row
-    // -> metadata row are DEPENDENT loads — overlap the predecessors' tails instead of heading this grid's critical path. The
-    // metadata row itself is device-written: it is only pulled towards L2 (the coherence point), and read after the wait.
-    const u32 bi_spawner_base = P.batch_info->spawner_base, bi_prefix_sum_offset = P.batch_info->prefix_sum_offset, n_effects = P.batch_info->prefix_sum_count;
-    {
-        const Spawner* first = &P.spawners[bi_spawner_base];
-        const u32 first_md = first->effect_metadata_index;
-        hnb_prefetch_l2(&P.metadata[first_md]);
-        hnb_prefetch_l2(first->transform);  // the row's 128 bytes
-    }
 #if HNB_PROFILE
     // per-frame timeline ring (diagnostics, tools/diag_frame_chain.py): 4 words per frame at debug[16 + 4 * (epoch & 63)]:
     // ~(earliest CTA residency), ~(earliest start after the dependency wait), ~(earliest end of a first sub-tile), latest warp end
@@ -484,6 +473,10 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     }
 #endif
 
+    // (Reading the host-written batch info / first spawner row before the wait was tried: it saves ~1 us per frame on a 1 Mi chain
+    // and costs 3-4 us on a launch that is NOT overlapped with its predecessor, because the wait then separates two groups of
+    // dependent loads that used to be issued together: profiles/r2_ab_prologue.txt. The bookkeeping kernel keeps its variant.)
+    const u32 bi_spawner_base = P.batch_info->spawner_base, bi_prefix_sum_offset = P.batch_info->prefix_sum_offset, n_effects = P.batch_info->prefix_sum_count;
     const u32* g_tile_prefix = P.tile_prefix + bi_prefix_sum_offset;
     const u32 total_tiles = *P.batch_tiles;
     const u32 epoch = P.frame->epoch;

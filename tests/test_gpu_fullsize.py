@@ -29,7 +29,8 @@ def _oracle_run(orc, n, seed, lo, hi, steps, dt):
     k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
     flags = np.zeros(n, dtype=np.uint8)
     u32p = C.POINTER(C.c_uint32)
-    threads = orc.orc_max_threads()
+    from oracle.host_threads import oracle_threads
+    threads = oracle_threads()
     for _ in range(steps):
         orc.orc_indirect(C.byref(sim), md, draw.ctypes.data_as(u32p), sp, prefix.ctypes.data_as(u32p), None, 0)
         orc.orc_prefix_sum(bi, 1, prefix.ctypes.data_as(u32p), dispatch.ctypes.data_as(u32p))
@@ -103,7 +104,8 @@ def test_c4_instancing_topology_checksum(ctx, orc):
     k = (C.c_float * 4)(0.0, -9.8, 0.0, 0.5)
     flags = np.zeros(cap, dtype=np.uint8)
     u32p = C.POINTER(C.c_uint32)
-    threads = orc.orc_max_threads()
+    from oracle.host_threads import oracle_threads
+    threads = oracle_threads()
     for _ in range(steps):
         orc.orc_indirect(C.byref(sim), md, draw.ctypes.data_as(u32p), sp, prefix.ctypes.data_as(u32p), None, 0)
         orc.orc_prefix_sum(bi, 1, prefix.ctypes.data_as(u32p), dispatch.ctypes.data_as(u32p))
