@@ -671,6 +671,10 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                             if (P.event_counts[b]) P.event_counts[b][row] = hnb_ctx.event_request[b];
                     }
 #endif
+                    // hnb_pack<false> leaves the PREV/NEXT words of raw[k] as they were LOADED, and the store below writes whole
+                    // planes: the links are written back unchanged. That equals the reference's WRITEBACK_CODE (which never
+                    // stores them) only because no kernel of this path maintains links while an update is in flight; a
+                    // link-maintaining pass added later must not overlap hnb_update (or PREV/NEXT must get a plane of their own).
                     hnb_pack<false>(particle, raw[k]);
                     hnb_store_raw(raw[k], P.slab, base_particle + pidx[k]);
                 }
