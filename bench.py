@@ -402,42 +402,47 @@ def run_b200(args):
     achieved = BYTES_PER_PARTICLE_STEP * per_rank / (k_avg_ms * 1e-3) / 1e9
 
     # -- end-to-end loop: host tables up, simulate, instance count back, every step. Like a renderer, the host keeps
-    # two frames in flight: the count read back by step i is checked while step i+1 is already queued, so the host's
-    # wake-up latency after a synchronisation is not on the critical path (every step's read-back is still checked).
+    # two frames in flight: the count of step i is checked while step i+1 is already queued, so the host's wake-up
+    # latency is not on the critical path (every step's count is still checked, on the host, against the expected value).
+    # Both transfers are the library's own low-latency paths: the step's tables (header, batch info, tile word,
+    # spawner row, range / spawn-prefix words: 232 bytes of the pinned host arena) reach the device in the parameter space of the
+    # frame's first kernel launch, and the result comes back as one 64-bit (epoch, instance_count) word that the update pass
+    # stores into pinned host memory — no copy-engine operation and no event sits between two kernels of the chain.
     FRAMES_IN_FLIGHT = 2
-    pinned = [N.lib.hnb_host_alloc(20) for _ in range(FRAMES_IN_FLIGHT)]
-    outs = [(N.DrawIndexedIndirectArgs * 1).from_address(p) for p in pinned]
-    landed = [torch.cuda.Event() for _ in range(FRAMES_IN_FLIGHT)]
-    e2e_state = {"step": 0, "checked": 0}
-    def check_slot(k):
-        if outs[k][0].instance_count != per_rank:
-            raise RuntimeError(f"instance_count {outs[k][0].instance_count} != {per_rank}")
+    ctx.set_count_mailbox(rows=1, ring=4)
+    e2e_state = {"step": 0, "checked": 0, "epochs": []}
+    def check_epoch(epoch):
+        got = ctx.mailbox_count(epoch, 0)   # spins until the word of that frame has landed in host memory
+        if got != per_rank:
+            raise RuntimeError(f"instance_count {got} != {per_rank}")
         e2e_state["checked"] += 1
     def step_e2e():
         i = e2e_state["step"]
-        k = i % FRAMES_IN_FLIGHT
-        if i >= FRAMES_IN_FLIGHT:  # slot k holds the result of step i - FRAMES_IN_FLIGHT: check it before reusing the slot
-            landed[k].synchronize()
-            check_slot(k)
+        if i >= FRAMES_IN_FLIGHT:
+            check_epoch(e2e_state["epochs"][i - FRAMES_IN_FLIGHT])
         upload_tables()
         ctx.simulate_raw(launches, 1)
-        N.check(N.lib.hnb_read_draw_args_async(ctx._h, 0, 1, pinned[k]))
-        landed[k].record(stream)
+        e2e_state["epochs"].append(ctx.last_epoch())
         e2e_state["step"] = i + 1
     def drain_e2e():
         ctx.sync()
-        for j in range(min(FRAMES_IN_FLIGHT, e2e_state["step"])):
-            check_slot((e2e_state["step"] - 1 - j) % FRAMES_IN_FLIGHT)
+        n = e2e_state["step"]
+        for e in e2e_state["epochs"][max(0, n - FRAMES_IN_FLIGHT):n]:
+            check_epoch(e)
         e2e_state["step"] = 0
+        e2e_state["epochs"] = []
+    copies0 = ctx.frame_block_copies
     for _ in range(3):
         step_e2e()
     drain_e2e()
     e2e_state["checked"] = 0
-    ms_e2e = timed(step_e2e, args.steps)  # ends with a device synchronisation: every step's read-back has landed
+    ms_e2e = timed(step_e2e, args.steps)  # ends with a device synchronisation
     drain_e2e()
     assert e2e_state["checked"] == args.steps, "every step's instance count must have been checked on the host"
+    e2e_copy_engine_ops = ctx.frame_block_copies - copies0
     e2e_value = total * args.steps / (ms_e2e * 1e-3)
-    h2d = 64 + 24 + 4 + 4 + 128 + 12  # frame header + batch info + tile size (+pad) + spawner row + range/spawn-prefix/prefix words
+    h2d = 64 + 24 + 4 + 4 + 128 + 8  # frame header + batch info + tile size (+pad) + spawner row + range / spawn-prefix words
+    ctx.set_count_mailbox(rows=0)
 
     # -- correctness guard inside the bench: nothing died, and the checksum of the whole logical instance (each shard
     # hashes its rows under their LOGICAL index; the sum over the shards is independent of how many GPUs hold it)
@@ -471,12 +476,17 @@ def run_b200(args):
                        "state_checksum": {"frames": int(frames_run), "sum_over_shards": f"0x{state_sum:016x}",
                                           "note": "order-independent 64-bit checksum of all particle records after `frames` frames, rows hashed "
                                                   "under their logical index: equal for every --gpus N at equal `frames`"}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps, "frames_in_flight": FRAMES_IN_FLIGHT,
-                    "note": "host per-frame tables (spawner row, batch info, prefix sums, sim params) copied in, "
-                            "draw-indirect instance_count copied out to pinned memory and checked on the host for every step "
-                            "(two frames in flight: step i's count is checked while step i+1 is queued); particle state "
-                            "stays in HBM as in the reference (it is never on the host there either)"},
+                    "h2d_path": "kernel parameter space of the frame's bookkeeping launch (from the pinned host arena)",
+                    "d2h_path": "64-bit (epoch, instance_count) word stored by the update kernel into pinned host memory",
+                    "copy_engine_ops_in_timed_region": int(e2e_copy_engine_ops),
+                    "note": "every step the host rewrites its per-frame tables (spawner row, batch info, prefix sums, sim params) and "
+                            "they travel to the device with that step's first kernel launch; the draw-indirect instance_count of every "
+                            "step comes back through the count mailbox and is checked on the host (two frames in flight: step i is "
+                            "checked while step i+1 is queued); particle state stays in HBM as in the reference (it is never on the "
+                            "host there either). With explicit cudaMemcpyAsync both ways the same loop costs +14 us per step "
+                            "(profiles/r2_bench_n*_copy_engine_e2e.json: 0.7634 ms at N=1, 0.1231 ms at N=8)"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "hnb_update", "kernel_ms": k_avg_ms, "peak_source": peak_src,
@@ -523,8 +533,6 @@ def run_b200(args):
             if gpu_sum != cpu_sum:
                 raise SystemExit("bench.py: GPU state differs from the CPU oracle's after the same number of frames")
         print(json.dumps(line), flush=True)
-    for ptr in pinned:
-        N.lib.hnb_host_free(ptr)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -94,6 +94,18 @@ HNB_DI u64 hnb_ld_state(const u64* p) {
     return v;
 }
 
+// one 64-bit word into the host's count mailbox (system scope: the reader is the CPU)
+HNB_DI void hnb_post_count(const BatchParams& P, u32 epoch, u32 render_index, u32 count) {
+    if (!P.mailbox || render_index >= P.mailbox_rows) return;
+    unsigned long long* slot = P.mailbox + size_t(epoch % P.mailbox_ring) * P.mailbox_rows + render_index;
+    const unsigned long long word = (u64(epoch) << 32) | u64(count);
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(word) : "memory");
+#else
+    *(volatile unsigned long long*)slot = word;
+#endif
+}
+
 HNB_DI u32 hnb_lanemask_lt() {
     u32 m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -126,7 +138,6 @@ template <typename Ptr> HNB_DI u32 hnb_find_effect(Ptr prefix, u32 lo, u32 hi, u
 // Dynamic shared memory of both kernels (hnb_init: the staged spawn prefix; hnb_update: see its carve-up)
 extern __shared__ __align__(16) unsigned char hnb_smem[];
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchParams P) {
-    hnb_pdl_launch_dependents();
     // Before the dependency wait: the words only the HOST writes — the batch info and the CPU prefix sums of the spawn counts
     // (batch.rs:358-383), staged in shared memory so that the per-thread location search (vfx_init.wgsl:51-72; ten dependent
     // steps for a batch of 1024 instances) runs on shared memory instead of on ten L2 round trips.
@@ -141,6 +152,10 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
         __syncthreads();
     }
     hnb_pdl_wait();  // the previous frame's update wrote the dead stack and the counters read below
+    // Dependents are signalled AFTER the wait: a successor (this frame's bookkeeping) reads host-written arena words before its
+    // own wait, and the arena may be (re)written by the predecessor of THIS grid when a frame block travels as a kernel
+    // parameter — a successor must therefore never become resident before this grid's predecessors are complete.
+    hnb_pdl_launch_dependents();
     struct Item {
         const Spawner* spawner;
         const EffectMetadata* md;
@@ -389,6 +404,7 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
         const u32 alive_total = alive_before + tile_alive;
         const u32 dead_total = max_update - alive_total;
         P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * pt.render_index + 1u] = alive_total;
+        hnb_post_count(P, epoch, pt.render_index, alive_total);
         md->alive_count = md->alive_count - dead_total;
         md->max_spawn = md->max_spawn + dead_total;
         // the bitmap and the counters must describe the same population (debug word 15 counts instances where they do not)
@@ -426,6 +442,7 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
         const u32 alive_total = alive_before + tile_alive;
         const u32 dead_total = max_update - alive_total;
         P.draw_args[HNB_DRAW_INDEXED_INDIRECT_STRIDE * pt.render_index + 1u] = alive_total;
+        hnb_post_count(P, epoch, pt.render_index, alive_total);
         md->alive_count = md->alive_count - dead_total;
         md->max_spawn = md->max_spawn + dead_total;
     }
@@ -454,8 +471,8 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // Programmatic dependent launch: this grid may have become resident while the bookkeeping kernel (and, behind it,
     // the previous frame's update) was still running — its launch latency and CTA start skew are hidden. Nothing
     // those kernels write has been read yet; from here on it is all visible. The next kernel in the stream (the next
-    // frame's bookkeeping) may take SM slots as this grid's CTAs retire.
-    hnb_pdl_launch_dependents();
+    // frame's bookkeeping) is signalled AFTER the wait below: it reads host-written arena words before ITS wait, and this
+    // frame's bookkeeping may be the one that writes them (frame block as a kernel parameter), so it must be complete first.
 #if HNB_PROFILE
     // per-frame timeline ring (diagnostics, tools/diag_frame_chain.py): 4 words per frame at debug[16 + 4 * (epoch & 63)]:
     // ~(earliest CTA residency), ~(earliest start after the dependency wait), ~(earliest end of a first sub-tile), latest warp end
@@ -463,6 +480,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_resident));
 #endif
     hnb_pdl_wait();
+    hnb_pdl_launch_dependents();
 #if HNB_PROFILE
     if (lane == 0 && P.debug) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); atomicMax(&P.debug[8], ~_g); }
     unsigned long long* const prof_ring = P.debug ? P.debug + 16 + 4 * (P.frame->epoch & 63u) : nullptr;

@@ -40,6 +40,23 @@ __device__ __forceinline__ SpawnerHostWords load_spawner_host_words(const Static
     w.spawn = spawner->spawn;
     return w;
 }
+// The frame block (header + every host-written table of the frame arena: batch infos, tile size words, spawner rows, spawn
+// ranges, spawn prefix) as a kernel parameter: small frames reach the device inside the launch itself, with no copy-engine
+// operation between two kernels of the frame chain (which would cost its own latency AND the programmatic overlap).
+template <int NW> struct FrameBlock { u32 w[NW]; };
+// a host-written arena word: from the parameter block when this launch carries the tables, else from the arena
+template <int NW> __device__ __forceinline__ u32 host_word(const StaticTables& T, const FrameBlock<NW>& block, bool from_block, const void* arena_address) {
+    if (from_block) return block.w[u32((const char*)arena_address - (const char*)T.frame) >> 2u];
+    return *(const u32*)arena_address;
+}
+template <int NW> __device__ __forceinline__ SpawnerHostWords load_spawner_host_words(const StaticTables& T, const FrameBlock<NW>& block, bool from_block, u32 global_effect_index) {
+    const Spawner* spawner = &T.spawners[global_effect_index];
+    SpawnerHostWords w;
+    w.effect_metadata_index = host_word(T, block, from_block, &spawner->effect_metadata_index);
+    w.draw_indirect_index = host_word(T, block, from_block, &spawner->draw_indirect_index);
+    w.spawn = i32(host_word(T, block, from_block, &spawner->spawn));
+    return w;
+}
 
 // Loads of one instance's step (phase 1), separated from its arithmetic and stores (phase 2) so that a thread handling
 // several instances has all their (dependent, latency-bound) loads in flight together.
@@ -154,8 +171,12 @@ __global__ void k_prefix_sum(StaticTables T) {
 // frames whose tables did not change need no host->device copy at all.
 #define BK_THREADS 256
 #define BK_ITEMS 4  // instances per thread and pass of the many-instance path
-struct FrameHeaderWords { u32 w[sizeof(FrameHeader) / 4]; };
-__global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, const __grid_constant__ FrameHeaderWords header, u32 write_header) {
+#define BK_HEADER_WORDS u32(sizeof(FrameHeader) / 4)
+// `block_words`: 0 = the host copied the frame block; BK_HEADER_WORDS = only the 64-byte header rides in `block` (tables unchanged
+// since the last frame); more = `block` holds the first `block_words` words of the frame arena, i.e. the header AND every
+// host-written table (frames without init launches whose tables fit the parameter space).
+template <int NW>
+__global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, const __grid_constant__ FrameBlock<NW> block, u32 block_words) {
     __shared__ u32 s_warp_a[BK_THREADS / 32], s_warp_t[BK_THREADS / 32];
     __shared__ u32 s_carry_a, s_carry_t;
     hnb_pdl_launch_dependents();
@@ -165,10 +186,11 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
     // previous frame's update kernel instead of sitting on the frame chain's critical path. Device-written state (metadata
     // rows, spawn ranges, child infos, the frame header) is read after the wait only.
     const u32 batch_index = blockIdx.x;
+    const bool from_block = block_words > BK_HEADER_WORDS;  // the tables travel with this launch: never read them from the arena
     BatchInfo* bi = &T.batch_infos[batch_index];
-    const u32 offset = bi->prefix_sum_offset;
-    const u32 count = bi->prefix_sum_count;
-    const u32 tile = T.batch_tile_size[batch_index];
+    const u32 offset = host_word(T, block, from_block, &bi->prefix_sum_offset);
+    const u32 count = host_word(T, block, from_block, &bi->prefix_sum_count);
+    const u32 tile = host_word(T, block, from_block, &T.batch_tile_size[batch_index]);
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5u;
     // Batches of at most 32 instances (every single-effect batch) need one warp and no barrier.
     const bool one_warp = count <= 32u;
@@ -178,10 +200,15 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
     for (int k = 0; k < BK_ITEMS; ++k) {
         first_hw[k] = SpawnerHostWords();
         const u32 i = one_warp ? (k == 0 ? tid : count) : tid * BK_ITEMS + k;
-        if (i < count) first_hw[k] = load_spawner_host_words(T, offset + i);
+        if (i < count) first_hw[k] = load_spawner_host_words(T, block, from_block, offset + i);
     }
     hnb_pdl_wait();
-    if (write_header && blockIdx.x == 0 && threadIdx.x < sizeof(FrameHeader) / 4) ((u32*)T.frame)[threadIdx.x] = header.w[threadIdx.x];
+    // CTA 0 puts the block into the device arena for the kernels that follow (the update pass reads spawner rows, the frame
+    // header, ...). Nobody reads those words concurrently: the previous frame's kernels are complete (the wait above), the other
+    // CTAs of this grid take their host words from `block`, and the next frame's grids cannot become resident before the
+    // update kernel of THIS frame has passed its own wait (it signals its dependents after it), i.e. after this grid is done.
+    if (blockIdx.x == 0)
+        for (u32 i = tid; i < block_words; i += (one_warp ? 32u : BK_THREADS)) ((u32*)T.frame)[i] = block.w[i];
     if (one_warp) {
         u32 a = 0u, t = 0u;
         if (lane < count) {
@@ -221,7 +248,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
 #pragma unroll
         for (int k = 0; k < BK_ITEMS; ++k) {
             hw[k] = first_hw[k];
-            if (chunk != 0u && i0 + k < count) hw[k] = load_spawner_host_words(T, offset + i0 + k);
+            if (chunk != 0u && i0 + k < count) hw[k] = load_spawner_host_words(T, block, from_block, offset + i0 + k);
         }
 #pragma unroll
         for (int k = 0; k < BK_ITEMS; ++k)
@@ -517,10 +544,10 @@ cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile,
     k_tile_prefix<<<1, BK_THREADS, 0, st>>>(T, batch_index, tile);
     return cudaGetLastError();
 }
-cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, const FrameHeader* header_by_value, bool pdl, cudaStream_t st) {
-    if (num_batches == 0) return cudaSuccess;
-    FrameHeaderWords hw{};
-    if (header_by_value) memcpy(hw.w, header_by_value, sizeof(FrameHeader));
+template <int NW>
+static cudaError_t launch_bookkeeping_t(const StaticTables& T, u32 num_batches, const u32* block_words_src, u32 block_words, bool pdl, cudaStream_t st) {
+    FrameBlock<NW> blk;
+    if (block_words) memcpy(blk.w, block_words_src, size_t(block_words) * 4);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_batches);
     cfg.blockDim = dim3(BK_THREADS);
@@ -530,7 +557,17 @@ cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_b
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_bookkeeping, T, hw, u32(header_by_value ? 1u : 0u));
+    return cudaLaunchKernelEx(&cfg, k_bookkeeping<NW>, T, blk, block_words);
+}
+cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, const void* frame_block, u32 block_bytes, bool pdl, cudaStream_t st) {
+    if (num_batches == 0) return cudaSuccess;
+    if (block_bytes & 3u) return cudaErrorInvalidValue;
+    const u32 words = frame_block ? block_bytes / 4u : 0u;
+    cudaError_t e;
+    if (words <= BK_HEADER_WORDS) e = launch_bookkeeping_t<int(sizeof(FrameHeader) / 4)>(T, num_batches, (const u32*)frame_block, words, pdl, st);
+    else if (words <= 64u) e = launch_bookkeeping_t<64>(T, num_batches, (const u32*)frame_block, words, pdl, st);
+    else if (words <= HNB_FRAME_BLOCK_MAX_BYTES / 4u) e = launch_bookkeeping_t<HNB_FRAME_BLOCK_MAX_BYTES / 4>(T, num_batches, (const u32*)frame_block, words, pdl, st);
+    else return cudaErrorInvalidValue;
     if (e != cudaSuccess) return e;
     if (T.num_child_infos) k_clear_events<<<blocks_for(num_effects, 64), 64, 0, st>>>(T);
     return cudaGetLastError();

@@ -73,9 +73,11 @@ inline u32 ordered_event_blocks(u32 capacity_rows) { return (capacity_rows + 204
 cudaError_t launch_indirect(const StaticTables& T, u32 num_effects, cudaStream_t st);
 cudaError_t launch_prefix_sum(const StaticTables& T, u32 num_batches, cudaStream_t st);
 cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile, cudaStream_t st);
-// `header_by_value`: frame header to store into T.frame from the kernel's parameter space (NULL: the host copied the frame
-// block); `pdl`: launch with programmatic stream serialization.
-cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, const FrameHeader* header_by_value, bool pdl, cudaStream_t st);
+// `frame_block` / `block_bytes`: the first bytes of the HOST frame arena to carry in the kernel's parameter space and store into
+// T.frame from there — NULL / 0: the host copied the frame block; sizeof(FrameHeader): the header only; up to
+// HNB_FRAME_BLOCK_MAX_BYTES: header + every host-written table. `pdl`: launch with programmatic stream serialization.
+#define HNB_FRAME_BLOCK_MAX_BYTES 3840u
+cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_batches, const void* frame_block, u32 block_bytes, bool pdl, cudaStream_t st);
 cudaError_t launch_fill_dispatch_args(const u32* src, u32* dst, u32 src_offset, u32 src_stride, u32 dst_offset,
                                       u32 dst_stride, u32 count, cudaStream_t st);
 cudaError_t launch_slab_reset(u32* ping, u32* pong, u32* dead, u32 first, u32 count, cudaStream_t st);

@@ -117,6 +117,11 @@ struct BatchParams {
     u32 _pad0;
     unsigned long long* debug;       // 16 counters, written only by kernels compiled with HNB_PROFILE=1
     u32* event_counts[HNB_MAX_EVENT_BINDINGS];  // HNB_EFFECT_ORDERED_EVENTS: events requested by update row r on channel b (else NULL)
+    // Count mailbox (hnb_ctx_set_count_mailbox; NULL = none): pinned HOST memory, `mailbox_ring` slots of `mailbox_rows` 64-bit
+    // words. The last tile of an instance stores (epoch << 32) | instance_count at [(epoch % ring) * rows + draw-indirect row]:
+    // the host learns a frame's counts by reading its own memory — no copy, no event, nothing between two kernels of the chain.
+    unsigned long long* mailbox;
+    u32 mailbox_rows, mailbox_ring;
 };
 
 }  // namespace hnb

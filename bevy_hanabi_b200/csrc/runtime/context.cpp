@@ -205,6 +205,9 @@ struct hnb_ctx {
     uint32_t sort_rows = 0;
     uint32_t tile_chunks_override = 0;  // HNB_TILE_CHUNKS env: fixed sub-tile count per tile (tuning)
     bool pdl = true;          // HNB_PDL=0: launch the frame chain without programmatic dependent launch
+    bool param_upload = true; // HNB_PARAM_UPLOAD=0: always copy the frame block with the copy engine (never as a kernel parameter)
+    unsigned long long* mailbox = nullptr;  // device alias of the caller's pinned count mailbox (hnb_ctx_set_count_mailbox)
+    uint32_t mailbox_rows = 0, mailbox_ring = 0;
     bool plan_dirty = false;  // plan_batch changed a tile-size or range word of the host frame block since the last upload
     uint64_t frame_copies = 0, frames = 0;  // hnb_simulate calls that needed the host->device copy of the frame block / all calls
     unsigned long long* d_debug = nullptr;  // 16 diagnostic counters + a 64-frame timeline ring of 4 words (HNB_PROFILE kernels)
@@ -606,6 +609,9 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     }
     P.init_thread_count = init_threads;
     P.debug = c->d_debug;
+    P.mailbox = c->mailbox;
+    P.mailbox_rows = c->mailbox_rows;
+    P.mailbox_ring = c->mailbox_ring;
     P.tile_rows = tile_word;
     lp.init_blocks = ceil_div(init_threads, 256 * hnb_rt::kInitItems);  // HNB_INIT_ITEMS logical init threads per CUDA thread
     uint32_t max_tiles = lp.slab->capacity / small_tile + bi.prefix_sum_count + 1;
@@ -808,6 +814,7 @@ int32_t hnb_ctx_create(int32_t cuda_device, uintptr_t external_stream, hnb_ctx**
         if (const char* env = getenv("HNB_EPOCH_START")) c->epoch = uint32_t(strtoul(env, nullptr, 0)) & 0x3fffffffu;  // tests: start near the wrap
         if (const char* env = getenv("HNB_SIDE_STREAMS")) c->max_side_streams = (uint32_t)std::max(0, std::min(atoi(env), 31));
         if (const char* env = getenv("HNB_PDL")) c->pdl = atoi(env) != 0;
+        if (const char* env = getenv("HNB_PARAM_UPLOAD")) c->param_upload = atoi(env) != 0;
         ensure_arena(c.get(), 0, 0);
         CUDA_CHECK(cudaMalloc((void**)&c->d_debug, kDebugWords * 8));
         CUDA_CHECK(cudaMemsetAsync(c->d_debug, 0, kDebugWords * 8, c->stream));
@@ -1441,10 +1448,18 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         // changed since the last upload (a steady-state frame without spawns), the only new bytes are the 64-byte
         // header (sim params, epoch), and those ride in the bookkeeping kernel's parameter space. The frame is then
         // a pure kernel chain, which programmatic dependent launch pipelines against the previous frame.
+        // ... or, third way, with the bookkeeping LAUNCH: when the frame has no init pass (nothing reads the tables before the
+        // bookkeeping kernel) and the host-written part of the arena fits the kernel parameter space, it travels there and CTA 0
+        // stores it into the device arena. A copy-engine operation between two kernels of the chain costs its own latency and
+        // the programmatic overlap of the kernel behind it (~10 us per frame of a host that rewrites its tables every frame).
         const bool copy_block = c->dirty_tables || c->plan_dirty;
-        if (copy_block) flush_arena(c, true);
+        bool any_init = false;
+        for (auto& lp : plans) any_init |= lp.init_blocks != 0;
+        const bool param_block = copy_block && !any_init && c->param_upload && c->B > 0 && c->lay.off_prefix_sum <= HNB_FRAME_BLOCK_MAX_BYTES;
+        if (copy_block && !param_block) flush_arena(c, true);
+        if (param_block) { c->dirty_tables = false; c->plan_dirty = false; }
         c->frames++;
-        c->frame_copies += copy_block ? 1 : 0;
+        c->frame_copies += (copy_block && !param_block) ? 1 : 0;
         // pass "hanabi:init" (mod.rs:7025-7179). Batches write disjoint slab rows and table rows; the only
         // cross-batch access is a child reading its parent's records, so frames with event-driven children keep
         // the reference's serial order.
@@ -1465,7 +1480,11 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         // passes "hanabi:indirect_dispatch" + "hanabi:update_prefix_sum" (mod.rs:7182-7275), fused
         {
             PassRange range("hanabi:indirect_dispatch");  // + "hanabi:update_prefix_sum"
-            CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, copy_block ? nullptr : c->header(), c->pdl, c->stream));
+            const void* block = nullptr;   // what rides in the kernel's parameter space: nothing / the 64-byte header / header + tables
+            uint32_t block_bytes = 0;
+            if (param_block) { block = c->h_arena; block_bytes = uint32_t(c->lay.off_prefix_sum); }
+            else if (!copy_block) { block = c->header(); block_bytes = uint32_t(sizeof(hnb::FrameHeader)); }
+            CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, block, block_bytes, c->pdl, c->stream));
             c->launches += 1 + (c->child_rows ? 1 : 0);
             std::fill(c->init_pending.begin(), c->init_pending.end(), 0);
         }
@@ -1655,6 +1674,30 @@ int32_t hnb_read_dispatch_args(hnb_ctx* c, uint32_t row, hnb_dispatch_indirect_a
         if (row >= c->scratch_B) fail(HNB_ERR_OUT_OF_RANGE, "dispatch args row out of range");
         CUDA_CHECK(cudaMemcpyAsync(out, c->d_dispatch_args + size_t(row) * 3, 12, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t hnb_ctx_set_count_mailbox(hnb_ctx* c, uint64_t* pinned_host, uint32_t rows, uint32_t ring) {
+    return guarded([&] {
+        if (!c) fail(HNB_ERR_INVALID_ARG, "ctx is NULL");
+        if (!pinned_host) { c->mailbox = nullptr; c->mailbox_rows = c->mailbox_ring = 0; return; }
+        if (rows == 0 || ring == 0) fail(HNB_ERR_INVALID_ARG, "count mailbox needs rows >= 1 and ring >= 1");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        void* dev = nullptr;
+        if (cudaHostGetDevicePointer(&dev, pinned_host, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            fail(HNB_ERR_INVALID_ARG, "count mailbox must be pinned host memory (hnb_host_alloc)");
+        }
+        memset(pinned_host, 0, size_t(rows) * ring * 8);
+        c->mailbox = (unsigned long long*)dev;
+        c->mailbox_rows = rows;
+        c->mailbox_ring = ring;
+    });
+}
+int32_t hnb_ctx_last_epoch(hnb_ctx* c, uint32_t* epoch) {
+    return guarded([&] {
+        if (!c || !epoch) fail(HNB_ERR_INVALID_ARG, "NULL argument");
+        *epoch = c->epoch;
     });
 }
 

@@ -399,6 +399,35 @@ class Context:
         return np.array(out[:count], dtype=np.uint32)
 
     # -- passes
+    # -- count mailbox (pinned host memory written by the update pass; see hnb_ctx_set_count_mailbox)
+    def set_count_mailbox(self, rows: int, ring: int = 4):
+        """Allocates a pinned mailbox of ring x rows 64-bit words, attaches it and returns a ctypes view of it (None: detach)."""
+        if rows == 0:
+            check(lib.hnb_ctx_set_count_mailbox(self._h, None, 0, 0))
+            return None  # (the pinned block of an earlier attach stays allocated: frames already queued may still post into it)
+        p = lib.hnb_host_alloc(rows * ring * 8)
+        if not p:
+            raise MemoryError("hnb_host_alloc")
+        check(lib.hnb_ctx_set_count_mailbox(self._h, p, rows, ring))
+        self._mailbox = ((C.c_uint64 * (rows * ring)).from_address(p), rows, ring, p)
+        return self._mailbox[0]
+
+    def last_epoch(self) -> int:
+        e = N.u32(0)
+        check(lib.hnb_ctx_last_epoch(self._h, C.byref(e)))
+        return e.value
+
+    def mailbox_count(self, epoch: int, row: int = 0, spin: bool = True):
+        """instance_count the frame `epoch` published for draw-indirect row `row` (spins until the word has landed)."""
+        view, rows, ring, _ = self._mailbox
+        i = (epoch % ring) * rows + row
+        while True:
+            w = view[i]
+            if (w >> 32) == epoch:
+                return w & 0xFFFFFFFF
+            if not spin:
+                return None
+
     def simulate(self, launches: Sequence[BatchLaunch]) -> None:
         arr = (BatchLaunch * max(1, len(launches)))(*launches)
         check(lib.hnb_simulate(self._h, arr, len(launches)))

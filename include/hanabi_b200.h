@@ -442,6 +442,15 @@ HNB_API int32_t hnb_read_dispatch_args(hnb_ctx* ctx, uint32_t row, hnb_dispatch_
 /** Enqueue an async copy of draw-args rows [first,first+count) into caller PINNED memory. */
 HNB_API int32_t hnb_read_draw_args_async(hnb_ctx* ctx, uint32_t first, uint32_t count,
                                          hnb_draw_indexed_indirect_args* pinned_out);
+/** Count mailbox. `pinned_host` (hnb_host_alloc, ring x rows x 8 bytes; NULL detaches) receives one 64-bit word per updated
+ *  instance and frame, written by the update pass itself when it publishes `instance_count` (vfx_update.wgsl:164; the draw-indirect
+ *  row is written as always): slot [(epoch % ring) * rows + draw_indirect_row] = (epoch << 32) | instance_count, where `epoch` is
+ *  the frame's number (hnb_ctx_last_epoch right after the hnb_simulate that enqueued it). The host reads its own memory — no
+ *  device-to-host copy and no event sits between two frames of the kernel chain; a slot holds frame `epoch` once its upper half
+ *  equals `epoch`. Rows beyond `rows` are not reported. Not available with HNB_EFFECT_RELAXED_ORDER (counts are atomics there). */
+HNB_API int32_t hnb_ctx_set_count_mailbox(hnb_ctx* ctx, uint64_t* pinned_host, uint32_t rows, uint32_t ring);
+/** Epoch (frame number, 30 bits, never 0) of the frame the last hnb_simulate enqueued. */
+HNB_API int32_t hnb_ctx_last_epoch(hnb_ctx* ctx, uint32_t* epoch);
 /** Pinned host memory helpers for the async paths. */
 HNB_API void* hnb_host_alloc(size_t bytes);
 HNB_API void hnb_host_free(void* p);

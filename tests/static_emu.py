@@ -104,7 +104,7 @@ using namespace hnb;
 extern "C" void semu_indirect(const StaticTables* T, uint32_t n) { StaticTables t = *T; emu_run([&] { k_indirect(t); }, (n + 63) / 64, 64); }
 extern "C" void semu_clear_events(const StaticTables* T, uint32_t n) { StaticTables t = *T; emu_run([&] { k_clear_events(t); }, (n + 63) / 64, 64); }
 extern "C" void semu_prefix_sum(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_prefix_sum(t); }, (nb + 63) / 64, 64); }
-extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_bookkeeping(t, FrameHeaderWords{}, 0u); }, nb, 256, 8); }
+extern "C" void semu_bookkeeping(const StaticTables* T, uint32_t nb) { StaticTables t = *T; emu_run([&] { k_bookkeeping<16>(t, FrameBlock<16>{}, 0u); }, nb, 256, 8); }
 extern "C" void semu_tile_prefix(const StaticTables* T, uint32_t batch, uint32_t tile) { StaticTables t = *T; emu_run([&] { k_tile_prefix(t, batch, tile); }, 1, 256); }
 extern "C" void semu_ribbon_sort_small(const RibbonSortArgs* a) { RibbonSortArgs r = *a; emu_run([&] { k_ribbon_sort_small(r); }, r.instance_count, 1024, 3); }
 extern "C" void semu_ribbon_sort_large(const RibbonSortArgs* a, uint32_t grid) { RibbonSortArgs r = *a; r.scratch_grid = grid; emu_run([&] { k_ribbon_sort_large(r); }, grid, 512); }
