@@ -435,10 +435,15 @@ def run_b200(args):
     for _ in range(3):
         step_e2e()
     drain_e2e()
-    e2e_state["checked"] = 0
-    ms_e2e = timed(step_e2e, args.steps)  # ends with a device synchronisation
-    drain_e2e()
-    assert e2e_state["checked"] == args.steps, "every step's instance count must have been checked on the host"
+    # K steps, three times; the MEDIAN run is reported (all three are listed): the timed region is ~10 ms at 8 GPUs, where a
+    # single scheduling hiccup of one rank's host process (the max over ranks sees it) shifts the result by tens of percent
+    e2e_runs = []
+    for _ in range(3):
+        e2e_state["checked"] = 0
+        e2e_runs.append(timed(step_e2e, args.steps))  # ends with a device synchronisation
+        drain_e2e()
+        assert e2e_state["checked"] == args.steps, "every step's instance count must have been checked on the host"
+    ms_e2e = sorted(e2e_runs)[1]
     e2e_copy_engine_ops = ctx.frame_block_copies - copies0
     e2e_value = total * args.steps / (ms_e2e * 1e-3)
     h2d = 64 + 24 + 4 + 4 + 128 + 8  # frame header + batch info + tile size (+pad) + spawner row + range / spawn-prefix words
@@ -481,6 +486,7 @@ def run_b200(args):
                     "h2d_path": "kernel parameter space of the frame's bookkeeping launch (from the pinned host arena)",
                     "d2h_path": "64-bit (epoch, instance_count) word stored by the update kernel into pinned host memory",
                     "copy_engine_ops_in_timed_region": int(e2e_copy_engine_ops),
+                    "ms_per_step_runs": [r / args.steps for r in e2e_runs], "reported": "median of 3 runs of `steps` steps",
                     "note": "every step the host rewrites its per-frame tables (spawner row, batch info, prefix sums, sim params) and "
                             "they travel to the device with that step's first kernel launch; the draw-indirect instance_count of every "
                             "step comes back through the count mailbox and is checked on the host (two frames in flight: step i is "
