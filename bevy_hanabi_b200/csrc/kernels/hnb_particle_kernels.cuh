@@ -138,24 +138,34 @@ template <typename Ptr> HNB_DI u32 hnb_find_effect(Ptr prefix, u32 lo, u32 hi, u
 // Dynamic shared memory of both kernels (hnb_init: the staged spawn prefix; hnb_update: see its carve-up)
 extern __shared__ __align__(16) unsigned char hnb_smem[];
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchParams P) {
-    // Before the dependency wait: the words only the HOST writes — the batch info and the CPU prefix sums of the spawn counts
-    // (batch.rs:358-383), staged in shared memory so that the per-thread location search (vfx_init.wgsl:51-72; ten dependent
-    // steps for a batch of 1024 instances) runs on shared memory instead of on ten L2 round trips.
+    // The words only the HOST writes — the batch info and the CPU prefix sums of the spawn counts (batch.rs:358-383), staged in
+    // shared memory so that the per-thread location search (vfx_init.wgsl:51-72; ten dependent steps for a batch of 1024
+    // instances) runs on shared memory instead of on ten L2 round trips — are read BEFORE the dependency wait when they came
+    // with a stream-ordered copy, and after it when the kernel just ahead of this one is the one that stores them
+    // (`late_tables`: the frame block travelled as a kernel parameter, k_frame_block).
     BatchInfo bi;
-    bi.spawner_base = P.batch_info->spawner_base;
-    bi.prefix_sum_offset = P.batch_info->prefix_sum_offset;
-    bi.prefix_sum_count = P.batch_info->prefix_sum_count;
     u32* const sh_spawn_prefix = (u32*)hnb_smem;
-    const bool staged = bi.prefix_sum_count <= HNB_INIT_SMEM_EFFECTS;
-    if (staged) {
-        for (u32 i = threadIdx.x; i < bi.prefix_sum_count; i += HNB_BLOCK) sh_spawn_prefix[i] = P.spawn_prefix[bi.prefix_sum_offset + i];
-        __syncthreads();
+    bool staged = false;
+#pragma unroll
+    for (int phase = 0; phase < 2; ++phase) {
+        if ((phase == 1) == (P.late_tables != 0u)) {
+            bi.spawner_base = P.batch_info->spawner_base;
+            bi.prefix_sum_offset = P.batch_info->prefix_sum_offset;
+            bi.prefix_sum_count = P.batch_info->prefix_sum_count;
+            staged = bi.prefix_sum_count <= HNB_INIT_SMEM_EFFECTS;
+            if (staged) {
+                for (u32 i = threadIdx.x; i < bi.prefix_sum_count; i += HNB_BLOCK) sh_spawn_prefix[i] = P.spawn_prefix[bi.prefix_sum_offset + i];
+                __syncthreads();
+            }
+        }
+        if (phase == 0) {
+            hnb_pdl_wait();  // the previous frame's update wrote the dead stack and the counters read below
+            // Dependents are signalled AFTER the wait: a successor (this frame's bookkeeping) reads host-written arena words before
+            // its own wait, and the arena may be (re)written by the predecessor of THIS grid when a frame block travels as a
+            // kernel parameter — a successor must therefore never become resident before this grid's predecessors are complete.
+            hnb_pdl_launch_dependents();
+        }
     }
-    hnb_pdl_wait();  // the previous frame's update wrote the dead stack and the counters read below
-    // Dependents are signalled AFTER the wait: a successor (this frame's bookkeeping) reads host-written arena words before its
-    // own wait, and the arena may be (re)written by the predecessor of THIS grid when a frame block travels as a kernel
-    // parameter — a successor must therefore never become resident before this grid's predecessors are complete.
-    hnb_pdl_launch_dependents();
     struct Item {
         const Spawner* spawner;
         const EffectMetadata* md;

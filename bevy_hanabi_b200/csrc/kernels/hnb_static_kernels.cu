@@ -544,6 +544,36 @@ cudaError_t launch_tile_prefix(const StaticTables& T, u32 batch_index, u32 tile,
     k_tile_prefix<<<1, BK_THREADS, 0, st>>>(T, batch_index, tile);
     return cudaGetLastError();
 }
+// The frame block of a frame WITH an init pass: init reads the tables before the bookkeeping kernel runs, so the block gets a
+// kernel of its own at the head of the frame (one CTA; the store happens after the dependency wait, like in k_bookkeeping).
+template <int NW>
+__global__ void __launch_bounds__(BK_THREADS) k_frame_block(u32* arena, const __grid_constant__ FrameBlock<NW> block, u32 block_words) {
+    hnb_pdl_wait();
+    hnb_pdl_launch_dependents();
+    for (u32 i = threadIdx.x; i < block_words; i += BK_THREADS) arena[i] = block.w[i];
+}
+template <int NW>
+static cudaError_t launch_frame_block_t(u32* arena, const u32* src, u32 words, bool pdl, cudaStream_t st) {
+    FrameBlock<NW> blk;
+    memcpy(blk.w, src, size_t(words) * 4);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(BK_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_frame_block<NW>, arena, blk, words);
+}
+cudaError_t launch_frame_block(void* device_arena, const void* frame_block, u32 block_bytes, bool pdl, cudaStream_t st) {
+    if (!frame_block || block_bytes == 0 || (block_bytes & 3u) || block_bytes > HNB_FRAME_BLOCK_MAX_BYTES) return cudaErrorInvalidValue;
+    const u32 words = block_bytes / 4u;
+    if (words <= 64u) return launch_frame_block_t<64>((u32*)device_arena, (const u32*)frame_block, words, pdl, st);
+    return launch_frame_block_t<HNB_FRAME_BLOCK_MAX_BYTES / 4>((u32*)device_arena, (const u32*)frame_block, words, pdl, st);
+}
+
 template <int NW>
 static cudaError_t launch_bookkeeping_t(const StaticTables& T, u32 num_batches, const u32* block_words_src, u32 block_words, bool pdl, cudaStream_t st) {
     FrameBlock<NW> blk;

@@ -122,6 +122,7 @@ struct BatchParams {
     // the host learns a frame's counts by reading its own memory — no copy, no event, nothing between two kernels of the chain.
     unsigned long long* mailbox;
     u32 mailbox_rows, mailbox_ring;
+    u32 late_tables, _pad1;          // 1: the host-written tables are stored by the kernel just ahead (k_frame_block): read them after the wait
 };
 
 }  // namespace hnb

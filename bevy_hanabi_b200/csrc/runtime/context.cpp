@@ -1455,7 +1455,14 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
         const bool copy_block = c->dirty_tables || c->plan_dirty;
         bool any_init = false;
         for (auto& lp : plans) any_init |= lp.init_blocks != 0;
-        const bool param_block = copy_block && !any_init && c->param_upload && c->B > 0 && c->lay.off_prefix_sum <= HNB_FRAME_BLOCK_MAX_BYTES;
+        const bool param_block = copy_block && c->param_upload && c->B > 0 && c->lay.off_prefix_sum <= HNB_FRAME_BLOCK_MAX_BYTES;
+        // with an init pass the block needs a (one-CTA) kernel of its own at the head of the frame: init reads the tables first
+        const bool block_kernel = param_block && any_init;
+        if (block_kernel) {
+            CUDA_CHECK(hnb::launch_frame_block(c->d_arena, c->h_arena, uint32_t(c->lay.off_prefix_sum), c->pdl, c->stream));
+            c->launches++;
+            for (auto& lp : plans) lp.params.late_tables = 1u;
+        }
         if (copy_block && !param_block) flush_arena(c, true);
         if (param_block) { c->dirty_tables = false; c->plan_dirty = false; }
         c->frames++;
@@ -1482,7 +1489,8 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             PassRange range("hanabi:indirect_dispatch");  // + "hanabi:update_prefix_sum"
             const void* block = nullptr;   // what rides in the kernel's parameter space: nothing / the 64-byte header / header + tables
             uint32_t block_bytes = 0;
-            if (param_block) { block = c->h_arena; block_bytes = uint32_t(c->lay.off_prefix_sum); }
+            if (param_block && !block_kernel) { block = c->h_arena; block_bytes = uint32_t(c->lay.off_prefix_sum); }
+            else if (block_kernel) { /* already stored by k_frame_block, header included */ }
             else if (!copy_block) { block = c->header(); block_bytes = uint32_t(sizeof(hnb::FrameHeader)); }
             CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, block, block_bytes, c->pdl, c->stream));
             c->launches += 1 + (c->child_rows ? 1 : 0);

@@ -70,3 +70,22 @@ def test_count_mailbox(ctx, orc):
     gpu.frame()
     ctx.sync()
     assert list(box) == snapshot
+
+
+@pytest.mark.parametrize("param_upload", ["1", "0"])
+def test_spawns_every_frame(native, orc, monkeypatch, param_upload):
+    """Frames WITH an init pass: the block is stored by a one-CTA kernel at the head of the frame (init reads the tables after its
+    dependency wait then) — the firework recipe spawning every frame into recycled slots, zero tolerance, on both upload paths."""
+    from oracle.hanabi_oracle import pcg_hash
+    from tests.test_gpu_effects import _firework_trails, _run
+    monkeypatch.setenv("HNB_PARAM_UPLOAD", param_upload)
+    ctx = native.Context(0)
+    asset = _firework_trails(4096)
+    ref = RefWorld(4096, 12, [Instance(0, 4096, alive=0)], dt=1.0 / 20.0)
+    seeds = lambda f: [int(pcg_hash(np.array([0x777 + f], dtype=np.uint32))[0])]
+    copies0 = ctx.frame_block_copies
+    _run(ctx, orc, asset, ref, 60, lambda f: [300 if f % 7 else 900], seeds=seeds, check_every=3)
+    copies = ctx.frame_block_copies - copies0
+    assert (copies == 0) if param_upload == "1" else (copies >= 60)
+    assert ref.metadata[0].particle_counter > 3 * 4096, "slots were recycled"
+    ctx.close()
