@@ -419,14 +419,20 @@ class Context:
 
     def mailbox_count(self, epoch: int, row: int = 0, spin: bool = True):
         """instance_count the frame `epoch` published for draw-indirect row `row` (spins until the word has landed)."""
+        import time
         view, rows, ring, _ = self._mailbox
         i = (epoch % ring) * rows + row
+        deadline = None
         while True:
             w = view[i]
             if (w >> 32) == epoch:
                 return w & 0xFFFFFFFF
             if not spin:
                 return None
+            if deadline is None:
+                deadline = time.monotonic() + 10.0
+            elif time.monotonic() > deadline:  # e.g. an effect compiled with RELAXED_ORDER (no mailbox), or a later frame reused the slot
+                raise TimeoutError(f"count mailbox: frame {epoch} never posted row {row} (slot holds frame {w >> 32})")
 
     def simulate(self, launches: Sequence[BatchLaunch]) -> None:
         arr = (BatchLaunch * max(1, len(launches)))(*launches)
