@@ -13,6 +13,7 @@
 // this per-instance step — and (b) the prefix step also scans the per-instance update TILE counts
 // consumed by the persistent update kernel.
 #include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <cuda_runtime.h>
@@ -44,6 +45,8 @@ __device__ __forceinline__ SpawnerHostWords load_spawner_host_words(const Static
 // ranges, spawn prefix) as a kernel parameter: small frames reach the device inside the launch itself, with no copy-engine
 // operation between two kernels of the frame chain (which would cost its own latency AND the programmatic overlap).
 template <int NW> struct FrameBlock { u32 w[NW]; };
+static_assert(offsetof(Spawner, render_indirect_read_index) == 26 * 4 && sizeof(Spawner) == 128, "k_bookkeeping skips this word when it stores a frame block");
+static_assert(offsetof(BatchInfo, total_update_count) == 4 && sizeof(BatchInfo) == 24, "k_bookkeeping skips this word when it stores a frame block");
 // a host-written arena word: from the parameter block when this launch carries the tables, else from the arena
 template <int NW> __device__ __forceinline__ u32 host_word(const StaticTables& T, const FrameBlock<NW>& block, bool from_block, const void* arena_address) {
     if (from_block) return block.w[u32((const char*)arena_address - (const char*)T.frame) >> 2u];
@@ -194,7 +197,9 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5u;
     // Batches of at most 32 instances (every single-effect batch) need one warp and no barrier.
     const bool one_warp = count <= 32u;
-    if (one_warp && warp != 0u) return;
+    // (the other warps of CTA 0 stay for the store of a large parameter block)
+    const bool block_helpers = blockIdx.x == 0 && block_words > 64u;
+    if (one_warp && warp != 0u && !block_helpers) return;
     SpawnerHostWords first_hw[BK_ITEMS];
 #pragma unroll
     for (int k = 0; k < BK_ITEMS; ++k) {
@@ -207,8 +212,19 @@ __global__ void __launch_bounds__(BK_THREADS) k_bookkeeping(StaticTables T, cons
     // header, ...). Nobody reads those words concurrently: the previous frame's kernels are complete (the wait above), the other
     // CTAs of this grid take their host words from `block`, and the next frame's grids cannot become resident before the
     // update kernel of THIS frame has passed its own wait (it signals its dependents after it), i.e. after this grid is done.
-    if (blockIdx.x == 0)
-        for (u32 i = tid; i < block_words; i += (one_warp ? 32u : BK_THREADS)) ((u32*)T.frame)[i] = block.w[i];
+    // The two word classes of the block's range that the DEVICE writes — `total_update_count` of a batch info and
+    // `render_indirect_read_index` of a spawner row, both written further down by whichever CTA owns the row — are left out of
+    // the store: every stored word is host-only, so the store races with nothing in this grid.
+    if (blockIdx.x == 0) {
+        const u32 bi0 = u32((const u32*)T.batch_infos - (const u32*)T.frame), bi1 = u32((const u32*)T.batch_tile_size - (const u32*)T.frame);
+        const u32 sp0 = u32((const u32*)T.spawners - (const u32*)T.frame), sp1 = u32((const u32*)T.spawn_range - (const u32*)T.frame);
+        for (u32 i = tid; i < block_words; i += ((one_warp && !block_helpers) ? 32u : BK_THREADS)) {
+            const bool device_word = (i >= bi0 && i < bi1 && (i - bi0) % u32(sizeof(BatchInfo) / 4) == 1u) ||
+                                     (i >= sp0 && i < sp1 && (i - sp0) % u32(sizeof(Spawner) / 4) == 26u);
+            if (!device_word) ((u32*)T.frame)[i] = block.w[i];
+        }
+    }
+    if (one_warp && warp != 0u) return;
     if (one_warp) {
         u32 a = 0u, t = 0u;
         if (lane < count) {
@@ -571,6 +587,7 @@ cudaError_t launch_frame_block(void* device_arena, const void* frame_block, u32 
     if (!frame_block || block_bytes == 0 || (block_bytes & 3u) || block_bytes > HNB_FRAME_BLOCK_MAX_BYTES) return cudaErrorInvalidValue;
     const u32 words = block_bytes / 4u;
     if (words <= 64u) return launch_frame_block_t<64>((u32*)device_arena, (const u32*)frame_block, words, pdl, st);
+    if (words <= HNB_FRAME_BLOCK_MID_BYTES / 4u) return launch_frame_block_t<HNB_FRAME_BLOCK_MID_BYTES / 4>((u32*)device_arena, (const u32*)frame_block, words, pdl, st);
     return launch_frame_block_t<HNB_FRAME_BLOCK_MAX_BYTES / 4>((u32*)device_arena, (const u32*)frame_block, words, pdl, st);
 }
 
@@ -596,6 +613,7 @@ cudaError_t launch_bookkeeping(const StaticTables& T, u32 num_effects, u32 num_b
     cudaError_t e;
     if (words <= BK_HEADER_WORDS) e = launch_bookkeeping_t<int(sizeof(FrameHeader) / 4)>(T, num_batches, (const u32*)frame_block, words, pdl, st);
     else if (words <= 64u) e = launch_bookkeeping_t<64>(T, num_batches, (const u32*)frame_block, words, pdl, st);
+    else if (words <= HNB_FRAME_BLOCK_MID_BYTES / 4u) e = launch_bookkeeping_t<HNB_FRAME_BLOCK_MID_BYTES / 4>(T, num_batches, (const u32*)frame_block, words, pdl, st);
     else if (words <= HNB_FRAME_BLOCK_MAX_BYTES / 4u) e = launch_bookkeeping_t<HNB_FRAME_BLOCK_MAX_BYTES / 4>(T, num_batches, (const u32*)frame_block, words, pdl, st);
     else return cudaErrorInvalidValue;
     if (e != cudaSuccess) return e;

@@ -14,19 +14,21 @@ from tests.test_gpu_update_c5 import ACCEL_DRAG, _fill
 pytestmark = pytest.mark.gpu
 
 
-def _world():
-    ref = RefWorld(3 * 4096, 8, [Instance(0, 4096, alive=4000, seed=1), Instance(4096, 4096, alive=1, seed=2), Instance(8192, 4096, alive=4096, seed=3)])
+def _world(batches=None):
+    ref = RefWorld(3 * 4096, 8, [Instance(0, 4096, alive=4000, seed=1), Instance(4096, 4096, alive=1, seed=2), Instance(8192, 4096, alive=4096, seed=3)], batches=batches)
     _fill(ref, np.random.default_rng(5), 0.02, 0.6)
     return ref
 
 
+@pytest.mark.parametrize("batches", [None, [[0], [1], [2]], [[0, 1], [2]]])
 @pytest.mark.parametrize("param_upload", ["1", "0"])
-def test_tables_rewritten_every_frame(native, orc, monkeypatch, param_upload):
-    """Three instances in one batch, deaths, and a host that re-uploads spawners / batches / sim params EVERY frame (GpuWorld.frame
+def test_tables_rewritten_every_frame(native, orc, monkeypatch, param_upload, batches):
+    """Three instances in one, three or two batches (= CTAs of the bookkeeping grid: CTA 0 stores the block while the others
+    write the device-owned words of their rows), deaths, and a host that re-uploads spawners / batches / sim params EVERY frame (GpuWorld.frame
     does) with new seeds: oracle parity frame by frame on both upload paths; the parameter path performs no frame-block copy."""
     monkeypatch.setenv("HNB_PARAM_UPLOAD", param_upload)
     ctx = native.Context(0)
-    ref = _world()
+    ref = _world(batches)
     gpu = GpuWorld(ctx, ref, recipes.c5_lowered())
     frames0, copies0 = ctx.frames_simulated, ctx.frame_block_copies
     for f in range(20):
@@ -89,3 +91,20 @@ def test_spawns_every_frame(native, orc, monkeypatch, param_upload):
     assert (copies == 0) if param_upload == "1" else (copies >= 60)
     assert ref.metadata[0].particle_counter > 3 * 4096, "slots were recycled"
     ctx.close()
+
+
+@pytest.mark.parametrize("n_inst", [30, 40, 200])
+def test_large_parameter_blocks(ctx, orc, n_inst):
+    """Tables beyond the classic 4 KB parameter space (30 instances: 4.2 KB, one warp + helper warps for the store; 40: the
+    many-instance path; 200: 27 KB) still travel with the launch (CUDA 12.1+: 32 KB of kernel parameters)."""
+    cap = 256
+    ref = RefWorld(n_inst * cap, 8, [Instance(i * cap, cap, alive=200 + (i % 50), seed=i) for i in range(n_inst)])
+    _fill(ref, np.random.default_rng(n_inst), 0.02, 0.4)
+    gpu = GpuWorld(ctx, ref, recipes.c5_lowered())
+    copies0 = ctx.frame_block_copies
+    for f in range(8):
+        ref.set_spawns([0] * n_inst, [1000 * f + i for i in range(n_inst)])
+        _oracle_c5_frame(ref, orc)
+        gpu.frame()
+        assert_world_equal(ref, gpu.pull(), what=f"{n_inst} instances, frame {f}")
+    assert ctx.frame_block_copies == copies0
