@@ -149,9 +149,9 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK) hnb_init(const BatchPara
 #pragma unroll
     for (int phase = 0; phase < 2; ++phase) {
         if ((phase == 1) == (P.late_tables != 0u)) {
-            bi.spawner_base = P.batch_info->spawner_base;
-            bi.prefix_sum_offset = P.batch_info->prefix_sum_offset;
-            bi.prefix_sum_count = P.batch_info->prefix_sum_count;
+            bi.spawner_base = P.bi_spawner_base;  // (kernel parameters: the host knows its batch info when it launches)
+            bi.prefix_sum_offset = P.bi_prefix_sum_offset;
+            bi.prefix_sum_count = P.bi_prefix_sum_count;
             staged = bi.prefix_sum_count <= HNB_INIT_SMEM_EFFECTS;
             if (staged) {
                 for (u32 i = threadIdx.x; i < bi.prefix_sum_count; i += HNB_BLOCK) sh_spawn_prefix[i] = P.spawn_prefix[bi.prefix_sum_offset + i];
@@ -504,7 +504,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // (Reading the host-written batch info / first spawner row before the wait was tried: it saves ~1 us per frame on a 1 Mi chain
     // and costs 3-4 us on a launch that is NOT overlapped with its predecessor, because the wait then separates two groups of
     // dependent loads that used to be issued together: profiles/r2_ab_prologue.txt. The bookkeeping kernel keeps its variant.)
-    const u32 bi_spawner_base = P.batch_info->spawner_base, bi_prefix_sum_offset = P.batch_info->prefix_sum_offset, n_effects = P.batch_info->prefix_sum_count;
+    const u32 bi_spawner_base = P.bi_spawner_base, bi_prefix_sum_offset = P.bi_prefix_sum_offset, n_effects = P.bi_prefix_sum_count;  // (kernel parameters: no load)
     const u32* g_tile_prefix = P.tile_prefix + bi_prefix_sum_offset;
     const u32 total_tiles = *P.batch_tiles;
     const u32 epoch = P.frame->epoch;
@@ -513,13 +513,6 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         for (u32 i = tid; i < n_effects; i += HNB_BLOCK) sh_tile_prefix[i] = g_tile_prefix[i];
         if (tid == 0) sh_tile_prefix[n_effects] = total_tiles;
     }
-    if (lane == 0) sh_pending[warp].valid = 0u;
-    // First tiles: one ticket request per CTA for its eight warps (all warps of the grid start within a few
-    // microseconds of each other; this keeps 7/8 of those same-address atomics off the start of the kernel).
-    __shared__ u32 sh_first_ticket;
-    if (tid == 0) sh_first_ticket = atomicAdd(P.ticket, HNB_WARPS);
-    __syncthreads();  // the only block barrier of the kernel
-
     u64* const states = P.tile_state;
     // rows per tile = 32 lanes * K rows per lane * chunks; the chunk count is chosen per launch by the
     // host (and used by the bookkeeping kernel for the tile prefix), so it is a run-time value here
@@ -550,6 +543,53 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         hnb_ctx.emit_events_capacity[i] = P.emit_events_capacity[i];
     }
 #endif
+
+    // Binds the cached descriptor of one instance of the batch. `md_known`: the metadata row index is already known (kernel
+    // parameter), so the metadata loads do not wait for the spawner row.
+    auto bind_instance = [&](u32 effect_index, bool md_known, u32 md_hint) {
+        spawner = &P.spawners[bi_spawner_base + effect_index];
+        metadata_index = md_known ? md_hint : spawner->effect_metadata_index;
+        const EffectMetadata* md = &P.metadata[metadata_index];
+        base_particle = spawner->slab_offset;
+        spawner_seed = spawner->seed;
+        max_update = md->max_update;  // :119
+#if HNB_SLOT_ORDER
+        inst_capacity = md->capacity;
+#endif
+        write_index = md->indirect_write_index;
+        render_index = md->indirect_render_index;
+        read_col = P.slab.particle_index[1u - write_index] + base_particle;
+        hnb_ctx.spawner = spawner;
+        hnb_ctx.transform = hnb_transform_from_rows(spawner->transform, spawner->transform + 4, spawner->transform + 8);
+        hnb_ctx.inverse_transform = hnb_transform_from_rows(spawner->inverse_transform, spawner->inverse_transform + 4,
+                                                            spawner->inverse_transform + 8);
+#if HNB_HAS_PROPERTIES
+        {
+            const u32* src = (const u32*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
+            __syncwarp();
+            for (u32 i = lane; i < sizeof(Properties) / 4u; i += 32u) ((u32*)sh_props[warp])[i] = src[i];
+            __syncwarp();
+            hnb_ctx.props = (const Properties*)sh_props[warp];
+        }
+#endif
+#if HNB_EMIT_EVENTS
+        hnb_ctx.base_child_index = md->base_child_index;
+#endif
+    };
+    // A batch of ONE instance (BASELINE's C2, C3, C5): which instance the first tile belongs to needs no ticket and no search, and
+    // its metadata row index came as a kernel parameter — its spawner row and metadata row are requested now, together with the
+    // tile-prefix / ticket round trip instead of two dependent round trips behind it.
+    if (n_effects == 1u) {
+        bind_instance(0u, true, P.first_md_index);
+        inst_first_tile = 0u;
+        inst_end_tile = total_tiles;
+    }
+    if (lane == 0) sh_pending[warp].valid = 0u;
+    // First tiles: one ticket request per CTA for its eight warps (all warps of the grid start within a few
+    // microseconds of each other; this keeps 7/8 of those same-address atomics off the start of the kernel).
+    __shared__ u32 sh_first_ticket;
+    if (tid == 0) sh_first_ticket = atomicAdd(P.ticket, HNB_WARPS);
+    __syncthreads();  // the only block barrier of the kernel
 
     // Tiles are handed out by a ticket counter, so every tile's predecessors in the look-back chain have
     // been taken by a running warp before it.
@@ -583,34 +623,7 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
                 inst_first_tile = g_tile_prefix[effect_index];
                 inst_end_tile = effect_index + 1u < n_effects ? g_tile_prefix[effect_index + 1u] : total_tiles;
             }
-            spawner = &P.spawners[bi_spawner_base + effect_index];
-            base_particle = spawner->slab_offset;
-            spawner_seed = spawner->seed;
-            metadata_index = spawner->effect_metadata_index;
-            const EffectMetadata* md = &P.metadata[metadata_index];
-            max_update = md->max_update;  // :119
-#if HNB_SLOT_ORDER
-            inst_capacity = md->capacity;
-#endif
-            write_index = md->indirect_write_index;
-            render_index = md->indirect_render_index;
-            read_col = P.slab.particle_index[1u - write_index] + base_particle;
-            hnb_ctx.spawner = spawner;
-            hnb_ctx.transform = hnb_transform_from_rows(spawner->transform, spawner->transform + 4, spawner->transform + 8);
-            hnb_ctx.inverse_transform = hnb_transform_from_rows(spawner->inverse_transform, spawner->inverse_transform + 4,
-                                                                spawner->inverse_transform + 8);
-#if HNB_HAS_PROPERTIES
-            {
-                const u32* src = (const u32*)((const char*)P.properties + size_t(md->properties_array_index) * P.properties_stride);
-                __syncwarp();
-                for (u32 i = lane; i < sizeof(Properties) / 4u; i += 32u) ((u32*)sh_props[warp])[i] = src[i];
-                __syncwarp();
-                hnb_ctx.props = (const Properties*)sh_props[warp];
-            }
-#endif
-#if HNB_EMIT_EVENTS
-            hnb_ctx.base_child_index = md->base_child_index;
-#endif
+            bind_instance(effect_index, false, 0u);
         }
         const u32 row0 = (tile - inst_first_tile) * tile_rows;
         u32* const survivors = sh_survivors[warp][cur];

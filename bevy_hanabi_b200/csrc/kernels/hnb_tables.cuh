@@ -122,7 +122,10 @@ struct BatchParams {
     // the host learns a frame's counts by reading its own memory — no copy, no event, nothing between two kernels of the chain.
     unsigned long long* mailbox;
     u32 mailbox_rows, mailbox_ring;
-    u32 late_tables, _pad1;          // 1: the host-written tables are stored by the kernel just ahead (k_frame_block): read them after the wait
+    u32 late_tables;
+    // this batch's GpuBatchInfo words the kernels need (the host knows them when it launches: no dependent load for them)
+    u32 bi_spawner_base, bi_prefix_sum_offset, bi_prefix_sum_count;
+    u32 first_md_index, _pad1;       // effect_metadata_index of the batch's first instance (used when the batch has exactly one)          // 1: the host-written tables are stored by the kernel just ahead (k_frame_block): read them after the wait
 };
 
 }  // namespace hnb

@@ -609,6 +609,10 @@ LaunchPlan plan_batch(hnb_ctx* c, const hnb_batch_launch& bl, bool set_ranges) {
     }
     P.init_thread_count = init_threads;
     P.debug = c->d_debug;
+    P.bi_spawner_base = bi.spawner_base;
+    P.bi_prefix_sum_offset = bi.prefix_sum_offset;
+    P.bi_prefix_sum_count = bi.prefix_sum_count;
+    P.first_md_index = bi.prefix_sum_count ? c->h_at<hnb_spawner>(c->lay.off_spawners)[bi.spawner_base].effect_metadata_index : 0u;
     P.mailbox = c->mailbox;
     P.mailbox_rows = c->mailbox_rows;
     P.mailbox_ring = c->mailbox_ring;

@@ -129,6 +129,8 @@ static hnb::BatchParams make_params(const EmuBatch* b) {
     P.prefix_sum = b->prefix_sum;
     P.tile_prefix = b->tile_prefix;
     P.batch_info = (const hnb::BatchInfo*)b->batch_info;
+    P.bi_spawner_base = P.batch_info->spawner_base; P.bi_prefix_sum_offset = P.batch_info->prefix_sum_offset; P.bi_prefix_sum_count = P.batch_info->prefix_sum_count;
+    P.first_md_index = P.spawners[P.bi_spawner_base].effect_metadata_index;
     P.batch_tiles = b->batch_tiles;
     P.ticket = b->ticket;
     P.tile_state = b->tile_state;
