@@ -36,13 +36,6 @@ HNB_DI void hnb_pdl_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
-HNB_DI void hnb_prefetch_l2(const void* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
 HNB_DI void hnb_pdl_launch_dependents() {
 #if defined(__CUDA_ARCH__)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
