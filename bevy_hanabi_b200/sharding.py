@@ -76,6 +76,7 @@ class ShardedInstance:
       * `fill_c5` gives the shard the rows of the 1-GPU state it owns (one seed, hashed with the LOGICAL row);
       * `checksum()` hashes the rows under their logical index, so the sum over the shards does not depend on `world`;
       * `counts()` are this shard's part of the logical totals (`merge_counts`).
+    The effect must publish counts through the mailbox, i.e. not be compiled with HNB_EFFECT_RELAXED_ORDER.
     """
 
     def __init__(self, ctx, lowered_effect, total_rows: int, rank: int, world: int, exchange=None, effect=None):
@@ -94,6 +95,11 @@ class ShardedInstance:
         self._batches = (N.BatchInfo * 1)(N.BatchInfo(0, 0, 0, 0, 0, 1))
         self._prefix = (N.u32 * 1)(0)
         self.last_split: list[int] = [0] * world
+        # the ONE integer a step needs from the device — this shard's free slots = rows - instance_count of the previous frame —
+        # comes through the count mailbox (pinned host memory the update pass posts into): no copy, no stream synchronisation
+        ctx.set_count_mailbox(rows=1, ring=4)
+        self._last_epoch = None
+        self._alive0 = 0
 
     def fill_c5(self, seed: int, lifetime_lo: float, lifetime_hi: float) -> None:
         """All slots alive, holding rows [first, end) of the logical instance's counter-based C5 state."""
@@ -102,20 +108,28 @@ class ShardedInstance:
         md = R.initial_metadata(self.rows, 0, self.stride // 4)
         md.alive_count, md.max_spawn = self.rows, 0
         self.ctx.metadata_insert(0, md)
+        self._alive0, self._last_epoch = self.rows, None
 
     def step(self, spawn_count: int, dt: float, time: float, seed: int) -> int:
         """One frame of the logical instance on this shard; returns the number of spawns this shard was given."""
         N, R, ctx = self._N, self._R, self.ctx
         mine = 0
         if spawn_count > 0:
-            frees = self.exchange(ctx.read_metadata(0).max_spawn)
+            frees = self.exchange(self.free_slots())
             self.last_split = split_spawn(spawn_count, frees)
             mine = self.last_split[self.rank]
         ctx.upload_spawners([R.make_spawner(spawn=mine, seed=seed)])
         ctx.upload_batches_raw(self._batches, 1, self._prefix, 1)
         ctx.set_sim_params(dt, time, 1)
         ctx.simulate([N.BatchLaunch.make(self.effect, self.slab, 0, mine)])
+        self._last_epoch = ctx.last_epoch()
         return mine
+
+    def free_slots(self) -> int:
+        """Slots this shard can still spawn into = what `max_spawn` will be at the next indirect pass (vfx_indirect.wgsl:66-70:
+        capacity - alive_count), from the previous frame's mailbox word."""
+        alive = self._alive0 if self._last_epoch is None else self.ctx.mailbox_count(self._last_epoch, 0)
+        return self.rows - alive
 
     def counts(self) -> dict:
         m = self.ctx.read_metadata(0)
