@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 A = G.Attribute
 
 
-def test_ordered_events_two_children(ctx, orc):
+@pytest.mark.parametrize("pcap", [1024, 6000])
+def test_ordered_events_two_children(ctx, orc, pcap):
     """HNB_EFFECT_ORDERED_EVENTS on the device : with
     ordered append the buffers must hold EXACTLY the canonical sequence, overflow included, and the children need no
     re-ordering of the oracle's events. Scenario: one parent, two event channels: channel 0 fed every frame by particles that are alive (EventEmitCondition::Always,
@@ -23,7 +24,7 @@ def test_ordered_events_two_children(ctx, orc):
     own buffer the frame after. Children come BEFORE the parent in batch order, as EffectSorter places them
     (batch.rs:599-603), so a child's init reads the parent's records before the parent's init recycles slots."""
     wp = G.ExprWriter()
-    parent = (G.EffectAsset(1024, wp.module, name="emitter")
+    parent = (G.EffectAsset(pcap, wp.module, name="emitter")
               .init(G.SetAttributeModifier(A.POSITION, wp.rand(G.VEC3) * wp.lit(2.) - wp.lit(1.)))
               .init(G.SetAttributeModifier(A.VELOCITY, wp.rand(G.VEC3) - wp.lit(0.5)))
               .init(G.SetAttributeModifier(A.AGE, wp.lit(0.)))
@@ -43,14 +44,14 @@ def test_ordered_events_two_children(ctx, orc):
     c_fx = [c.generate(parent=parent) for c in children]
     p_stride, c_stride = p_fx.particle_stride, c_fx[0].particle_stride
     dt = 1.0 / 30.0
-    pw = RefWorld(1024, p_stride // 4, [Instance(0, 1024, alive=0, seed=1)], dt=dt)
+    pw = RefWorld(pcap, p_stride // 4, [Instance(0, pcap, alive=0, seed=1)], dt=dt)
     cw = [RefWorld(4096, c_stride // 4, [Instance(0, 4096, alive=0, seed=2 + k)], dt=dt) for k in (0, 1)]
     po, co = EffectOracle(parent), [EffectOracle(c) for c in children]
     events = [np.zeros(EVENT_CAP, dtype=np.uint32) for _ in (0, 1)]
     event_count = [0, 0]
 
     # GPU tables: rows 0, 1 = children (batches 0, 1), row 2 = parent (batch 2); child infos 0, 1 = channels 0, 1
-    p_slab = ctx.slab_create(1024, p_stride)
+    p_slab = ctx.slab_create(pcap, p_stride)
     c_slab = [ctx.slab_create(4096, c_stride) for _ in (0, 1)]
     p_eff = ctx.effect_compile(p_fx)
     c_eff = [ctx.effect_compile(fx) for fx in c_fx]
@@ -61,12 +62,12 @@ def test_ordered_events_two_children(ctx, orc):
         md_c.global_child_index, md_c.local_child_index = k, k
         ctx.metadata_insert(k, md_c)
         ctx.draw_args_insert(k)
-    md_p = R.initial_metadata(1024, 2, p_stride // 4)
+    md_p = R.initial_metadata(pcap, 2, p_stride // 4)
     md_p.base_child_index = 0
     ctx.metadata_insert(2, md_p)
     ctx.draw_args_insert(2)
 
-    spawn_sched = [700, 0, 0, 150, 0, 0, 0, 800, 0, 0, 0, 0, 100, 0, 0, 0, 0, 0, 0, 0]
+    spawn_sched = [s * pcap // 1024 for s in [700, 0, 0, 150, 0, 0, 0, 800, 0, 0, 0, 0, 100, 0, 0, 0, 0, 0, 0, 0]]
     spawned = [0, 0]
     overflowed = False
     seen_counts = []
@@ -118,7 +119,7 @@ def test_ordered_events_two_children(ctx, orc):
 
         # ----- compare
         ctx.sync()
-        for world, slab, row, stride, rows in ((cw[0], c_slab[0], 0, c_stride, 4096), (cw[1], c_slab[1], 1, c_stride, 4096), (pw, p_slab, 2, p_stride, 1024)):
+        for world, slab, row, stride, rows in ((cw[0], c_slab[0], 0, c_stride, 4096), (cw[1], c_slab[1], 1, c_stride, 4096), (pw, p_slab, 2, p_stride, pcap)):
             m_gpu = np.frombuffer(bytes(ctx.read_metadata(row)), dtype=np.uint32)
             m_ref = world.metadata_rows()[0].copy()
             m_ref[5] = row
