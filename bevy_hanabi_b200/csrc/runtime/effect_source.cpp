@@ -225,6 +225,11 @@ uint32_t update_smem_bytes(const hnb_effect_desc& d) {
 }
 
 uint32_t choose_tile_k(const hnb_effect_desc& d) {
+    // HNB_TILE_K env for tuning experiments (rows a lane keeps in flight per sub-tile; must divide HNB_ROWS_PER_LANE)
+    if (const char* e = getenv("HNB_TILE_K")) {
+        int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && rows_per_lane() % uint32_t(v) == 0) return (uint32_t)v;
+    }
     // rows per thread: keep (index + record) register footprint around 40 words
     uint32_t words = d.particle_stride / 4 + 1;
     uint32_t k = 40 / words;
