@@ -64,6 +64,11 @@ namespace hnb {
 #define HNB_LOOKBACK_SLEEP_NS 0  // back-off between polls of an unpublished predecessor (0 = spin)
 #endif
 
+#ifndef HNB_PARK
+#define HNB_PARK 1  // tiles a warp keeps parked (simulated, compaction still to do) behind the one it streams; the stash has HNB_PARK + 1
+                    // buffers per warp (host mirror: hnb_rt::park_depth, update_smem_bytes)
+#endif
+#define HNB_STASH_BUFFERS (HNB_PARK + 1)
 #ifndef HNB_SLOT_ORDER
 #define HNB_SLOT_ORDER 0  // 1 (HNB_EFFECT_SLOT_ORDER): the update pass walks the instance's SLOTS in ascending order, guided by
                           // the slab's alive bitmap, instead of walking the alive list. See "slot order" below.
@@ -462,18 +467,19 @@ HNB_DI void hnb_compact_tile(const BatchParams& P, const PendingTile& pt, const 
 
 extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_update(const BatchParams P) {
     // Dynamic shared memory (size = hnb_update_smem_bytes, computed identically on the host):
-    //   tile-prefix table | per warp, double-buffered: alive-list entries [2][R][32], survivor ballots [2][R], valid masks [2][R] |
-    //   per warp: PendingTile | per warp: Properties staging slot
+    //   tile-prefix table | per warp, HNB_PARK + 1 buffers: alive-list entries [B][R][32], survivor ballots [B][R], valid masks [B][R] |
+    //   per warp: HNB_PARK PendingTile records | per warp: Properties staging slot
     u32* const sh_tile_prefix = (u32*)hnb_smem;
     typedef u32 PidxBuf[HNB_ROWS_PER_LANE][32];
     typedef u32 SurvBuf[HNB_ROWS_PER_LANE];
-    PidxBuf(*const sh_pidx)[2] = (PidxBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES);
-    SurvBuf(*const sh_survivors)[2] = (SurvBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES + sizeof(PidxBuf) * 2 * HNB_WARPS);
-    SurvBuf(*const sh_valids)[2] = (SurvBuf(*)[2])(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * 2 * HNB_WARPS);  // slot order
-    PendingTile* const sh_pending = (PendingTile*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + 2 * sizeof(SurvBuf)) * 2 * HNB_WARPS);
+    enum : size_t { kStash = (sizeof(PidxBuf) + 2 * sizeof(SurvBuf)) * HNB_STASH_BUFFERS * HNB_WARPS };
+    PidxBuf(*const sh_pidx)[HNB_STASH_BUFFERS] = (PidxBuf(*)[HNB_STASH_BUFFERS])(hnb_smem + HNB_SMEM_PREFIX_BYTES);
+    SurvBuf(*const sh_survivors)[HNB_STASH_BUFFERS] = (SurvBuf(*)[HNB_STASH_BUFFERS])(hnb_smem + HNB_SMEM_PREFIX_BYTES + sizeof(PidxBuf) * HNB_STASH_BUFFERS * HNB_WARPS);
+    SurvBuf(*const sh_valids)[HNB_STASH_BUFFERS] = (SurvBuf(*)[HNB_STASH_BUFFERS])(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + sizeof(SurvBuf)) * HNB_STASH_BUFFERS * HNB_WARPS);  // slot order
+    PendingTile(*const sh_pending)[HNB_PARK] = (PendingTile(*)[HNB_PARK])(hnb_smem + HNB_SMEM_PREFIX_BYTES + kStash);
 #if HNB_HAS_PROPERTIES
     typedef unsigned char PropsBuf[(sizeof(Properties) + 15) / 16 * 16];
-    PropsBuf* const sh_props = (PropsBuf*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + (sizeof(PidxBuf) + 2 * sizeof(SurvBuf)) * 2 * HNB_WARPS + sizeof(PendingTile) * HNB_WARPS);
+    PropsBuf* const sh_props = (PropsBuf*)(hnb_smem + HNB_SMEM_PREFIX_BYTES + kStash + sizeof(PendingTile) * HNB_PARK * HNB_WARPS);
 #endif
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
@@ -518,7 +524,8 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     // host (and used by the bookkeeping kernel for the tile prefix), so it is a run-time value here
     const u32 tile_rows = hnb_tile_rows(P.tile_rows);
     const u32 chunks = tile_rows / (32u * HNB_TILE_K);
-    PendingTile& pending = sh_pending[warp];
+    PendingTile* const parked = sh_pending[warp];  // FIFO of this warp's parked tiles: q_len records starting at q_head
+    u32 q_head = 0u, q_len = 0u;
     u32 cur = 0u;  // buffer the tile being streamed uses
 
     // cached descriptor of the instance the current tile belongs to (reloaded when a tile leaves
@@ -584,7 +591,6 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         inst_first_tile = 0u;
         inst_end_tile = total_tiles;
     }
-    if (lane == 0) sh_pending[warp].valid = 0u;
     // First tiles: one ticket request per CTA for its eight warps (all warps of the grid start within a few
     // microseconds of each other; this keeps 7/8 of those same-address atomics off the start of the kernel).
     __shared__ u32 sh_first_ticket;
@@ -754,12 +760,15 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
         // aggregates a whole pass 1 ago, so the look-back finds them immediately.
 #if HNB_DEFER_COMPACTION
         __syncwarp();
-        if (pending.valid) {
-            const PendingTile pt = pending;
+        if (q_len == u32(HNB_PARK)) {  // the queue is full: resolve the oldest parked tile (its stash buffer is the next one to be reused)
+            const PendingTile pt = parked[q_head];
             hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_valids[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
+            q_head = (q_head + 1u) % u32(HNB_PARK);
+            q_len -= 1u;
         }
         __syncwarp();
         if (lane == 0) {
+            PendingTile& pending = parked[(q_head + q_len) % u32(HNB_PARK)];
             pending.valid = 1u; pending.tile = tile; pending.row0 = row0; pending.tile_alive = tile_alive;
             pending.base_particle = base_particle; pending.max_update = max_update; pending.write_index = write_index;
             pending.render_index = render_index; pending.inst_first_tile = inst_first_tile; pending.inst_end_tile = inst_end_tile;
@@ -769,7 +778,8 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
             pending.tile_valid = tile_valid;
 #endif
         }
-        cur ^= 1u;
+        q_len += 1u;
+        cur = (cur + 1u) % u32(HNB_STASH_BUFFERS);
         __syncwarp();
 #else
         {
@@ -796,9 +806,10 @@ extern "C" __global__ void __launch_bounds__(HNB_BLOCK, HNB_MIN_BLOCKS) hnb_upda
     }
 #if HNB_DEFER_COMPACTION
     __syncwarp();
-    if (pending.valid) {
-        const PendingTile pt = pending;
+    for (; q_len != 0u; --q_len) {  // no more tiles: resolve what is parked, oldest first
+        const PendingTile pt = parked[q_head];
         hnb_compact_tile(P, pt, sh_survivors[warp][pt.buffer], sh_valids[warp][pt.buffer], sh_pidx[warp][pt.buffer], chunks, epoch, lane, prof_polls);
+        q_head = (q_head + 1u) % u32(HNB_PARK);
     }
 #endif
 #if HNB_PROFILE

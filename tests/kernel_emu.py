@@ -357,7 +357,7 @@ class EmuWorld:
             self.batch_tiles[0] = tiles.sum()
             self.ticket[0] = 0
         # ---- update (vfx_update.wgsl): a persistent grid of a few CTAs
-        self.lib.emu_update(C.byref(self.b), self.update_ctas, 64 * 1024)
+        self.lib.emu_update(C.byref(self.b), self.update_ctas, 160 * 1024)
         if self.ribbons:
             self._sort_ribbons(orc)
 
@@ -518,7 +518,7 @@ class EmuScene:
         self.static.semu_bookkeeping(C.byref(self.T), n)   # indirect + prefix sums (+ deferred init accounting), then the event clear
         self.static.semu_clear_events(C.byref(self.T), n)
         for slab in self.slabs:                     # pass "hanabi:update"
-            slab["lib"].emu_update(C.byref(slab["b"]), self.update_ctas, 64 * 1024)
+            slab["lib"].emu_update(C.byref(slab["b"]), self.update_ctas, 160 * 1024)
         from tests.static_emu import EventAppendArgs
         for b, m in enumerate(self.members):        # HNB_EFFECT_ORDERED_EVENTS: the three k_events_* launches per channel
             if not m.get("ordered"):
