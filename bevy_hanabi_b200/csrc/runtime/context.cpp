@@ -1468,7 +1468,7 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             for (auto& lp : plans) lp.params.late_tables = 1u;
         }
         if (copy_block && !param_block) flush_arena(c, true);
-        if (param_block) { c->dirty_tables = false; c->plan_dirty = false; }
+        if (block_kernel) { c->dirty_tables = false; c->plan_dirty = false; }  // (stored by k_frame_block, enqueued above)
         c->frames++;
         c->frame_copies += (copy_block && !param_block) ? 1 : 0;
         // pass "hanabi:init" (mod.rs:7025-7179). Batches write disjoint slab rows and table rows; the only
@@ -1497,6 +1497,7 @@ int32_t hnb_simulate(hnb_ctx* c, const hnb_batch_launch* batches, uint32_t n) {
             else if (block_kernel) { /* already stored by k_frame_block, header included */ }
             else if (!copy_block) { block = c->header(); block_bytes = uint32_t(sizeof(hnb::FrameHeader)); }
             CUDA_CHECK(hnb::launch_bookkeeping(static_tables(c), c->header()->sim.num_effects, c->B, block, block_bytes, c->pdl, c->stream));
+            if (param_block && !block_kernel) { c->dirty_tables = false; c->plan_dirty = false; }  // the tables went with this launch
             c->launches += 1 + (c->child_rows ? 1 : 0);
             std::fill(c->init_pending.begin(), c->init_pending.end(), 0);
         }
