@@ -420,7 +420,8 @@ def run_b200(args):
         i = e2e_state["step"]
         if i >= FRAMES_IN_FLIGHT:
             check_epoch(e2e_state["epochs"][i - FRAMES_IN_FLIGHT])
-        upload_tables()
+        spawners[0].seed = 0x9E3779B9 * (i + 1) & 0xFFFFFFFF  # the tables differ from the previous step's (identical uploads are
+        upload_tables()                                       # elided by the library); C5's update draws no random numbers
         ctx.simulate_raw(launches, 1)
         e2e_state["epochs"].append(ctx.last_epoch())
         e2e_state["step"] = i + 1

@@ -1337,7 +1337,14 @@ int32_t hnb_set_sim_params(hnb_ctx* c, const hnb_sim_params* p) {
 int32_t hnb_upload_spawners(hnb_ctx* c, const hnb_spawner* rows, uint32_t n) {
     return guarded([&] {
         if (n && !rows) fail(HNB_ERR_INVALID_ARG, "rows is NULL");
+        const uint32_t old_e = c->E, old_b = c->B;
+        const char* const old_arena = c->h_arena;
         ensure_arena(c, n, c->B);
+        // A host that uploads its tables every frame whether they changed or not (the reference does: mod.rs:4679-4705) should not
+        // pay for it: identical rows over an unchanged layout leave the frame a header-only frame.
+        if (old_arena == c->h_arena && old_e == c->E && old_b == c->B && n &&
+            memcmp(c->h_arena + c->lay.off_spawners, rows, size_t(n) * sizeof(hnb_spawner)) == 0)
+            return;
         memcpy(c->h_arena + c->lay.off_spawners, rows, size_t(n) * sizeof(hnb_spawner));
         c->dirty_tables = true;
     });
@@ -1346,8 +1353,14 @@ int32_t hnb_upload_spawners(hnb_ctx* c, const hnb_spawner* rows, uint32_t n) {
 int32_t hnb_upload_batches(hnb_ctx* c, const hnb_batch_info* rows, uint32_t nb, const uint32_t* prefix, uint32_t np) {
     return guarded([&] {
         if ((nb && !rows) || (np && !prefix)) fail(HNB_ERR_INVALID_ARG, "NULL table");
+        const uint32_t old_e = c->E, old_b = c->B;
+        const char* const old_arena = c->h_arena;
         ensure_arena(c, std::max(c->E, np), nb);
         if (np > c->E) fail(HNB_ERR_OUT_OF_RANGE, "more prefix entries than instances");
+        if (old_arena == c->h_arena && old_e == c->E && old_b == c->B && nb &&
+            memcmp(c->h_arena + c->lay.off_batch_infos, rows, size_t(nb) * sizeof(hnb_batch_info)) == 0 &&
+            (np == 0 || memcmp(c->h_arena + c->lay.off_spawn_prefix, prefix, size_t(np) * 4) == 0))
+            return;  // unchanged (see hnb_upload_spawners); the per-frame spawn ranges are recomputed by every launch plan
         memcpy(c->h_arena + c->lay.off_batch_infos, rows, size_t(nb) * sizeof(hnb_batch_info));
         memcpy(c->h_arena + c->lay.off_spawn_prefix, prefix, size_t(np) * 4);
         memcpy(c->h_arena + c->lay.off_prefix_sum, prefix, size_t(np) * 4);  // same buffer in the reference (batch.rs:194-216)
